@@ -1,0 +1,237 @@
+// dmk_api.cu -- extern "C" entry points of libdmk.so (see include/dmk.h).
+#include <atomic>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "dmk_fd.cuh"
+#include "dmk_td.cuh"
+
+namespace {
+
+thread_local char g_err[512] = "";
+thread_local char g_kernel[128] = "";
+std::atomic<long long> g_launches{0};
+
+int fail(int code, const char* fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+int cuda_fail(cudaError_t e, const char* what)
+{
+    return fail(DMK_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
+}
+
+// Host half of the prologue: everything that is a function of the parameters only is computed
+// here in IEEE float64 with the same operations NumPy applies.
+int build_desc(const dmk_desc* h, bool freq_domain, dmk::DevDesc& d)
+{
+    using namespace dmk;
+    if (!h) return fail(DMK_ERR_INVALID_ARG, "desc is NULL");
+    if (h->rx_filter) return fail(DMK_ERR_UNSUPPORTED, "ofdm.rx_filter=1 (LPF, channel.py:193-194) is not implemented");
+    for (int s = 0; s < 2; ++s) {
+        const int32_t* shp = s == 0 ? h->bs_shape : h->ue_shape;
+        if (shp[0] < 1 || shp[1] < 1) return fail(DMK_ERR_INVALID_ARG, "antenna shape must be >= 1 (got %d x %d)", shp[0], shp[1]);
+        if (h->pattern[s] != DMK_PATTERN_ISOTROPIC && h->pattern[s] != DMK_PATTERN_HALFWAVE_DIPOLE)
+            return fail(DMK_ERR_UNSUPPORTED, "unknown radiation pattern id %d", h->pattern[s]);
+    }
+    if (h->n_cols < 1 || h->n_cols > kMaxPaths)
+        return fail(DMK_ERR_INVALID_ARG, "n_cols=%d outside [1, %d]", h->n_cols, kMaxPaths);
+    if (h->num_paths < 0) return fail(DMK_ERR_INVALID_ARG, "num_paths=%d < 0", h->num_paths);
+    if (!(h->bandwidth > 0)) return fail(DMK_ERR_INVALID_ARG, "bandwidth must be > 0");
+    if (h->n_subcarriers < 1) return fail(DMK_ERR_INVALID_ARG, "ofdm.subcarriers must be >= 1");
+    if (freq_domain) {
+        if (h->n_selected < 0) return fail(DMK_ERR_INVALID_ARG, "n_selected < 0");
+        if (h->n_selected > 1 && !h->subcarriers && h->subc_step == 0)
+            return fail(DMK_ERR_INVALID_ARG, "subcarriers is NULL and subc_step == 0");
+    }
+    if (h->n_times < 0 || h->n_times > DMK_MAX_TIMES) return fail(DMK_ERR_INVALID_ARG, "n_times=%d outside [0, %d]", h->n_times, DMK_MAX_TIMES);
+    if (h->n_times > 0 && !h->times) return fail(DMK_ERR_INVALID_ARG, "n_times > 0 but times is NULL");
+
+    memset(&d, 0, sizeof(d));
+    d.bs0 = h->bs_shape[0]; d.bs1 = h->bs_shape[1];
+    d.ue0 = h->ue_shape[0]; d.ue1 = h->ue_shape[1];
+    d.Mt = d.bs0 * d.bs1; d.Mr = d.ue0 * d.ue1; d.M = d.Mt * d.Mr;
+    d.P0 = h->n_cols; d.P = h->num_paths < h->n_cols ? h->num_paths : h->n_cols;
+    d.N = h->n_subcarriers; d.K = h->n_selected;
+    d.T = h->n_times > 0 ? h->n_times : 1; d.has_time_axis = h->n_times > 0;
+    d.fov_any = h->fov_any; d.fov_side[0] = h->fov_side_enabled[0]; d.fov_side[1] = h->fov_side_enabled[1];
+    d.pat[0] = h->pattern[0]; d.pat[1] = h->pattern[1];
+    d.subc = h->subcarriers; d.subc_start = h->subc_start; d.subc_step = h->subc_step;
+    d.times = h->times;
+    d.sp[0] = h->bs_spacing; d.sp[1] = h->ue_spacing;
+    const double k = M_PI / 180.0;                         // np.deg2rad (float64): x * (pi/180)
+    for (int s = 0; s < 2; ++s) {
+        const double* r = s == 0 ? h->bs_rot_deg : h->ue_rot_deg;
+        const double rx = r[0] * k, ry = r[1] * k;
+        d.sx[s] = std::sin(rx); d.cx[s] = std::cos(rx);    // geometry.py:296,:299
+        d.sy[s] = std::sin(ry); d.cy[s] = std::cos(ry);    // geometry.py:295,:298
+        d.rz[s] = r[2] * k;
+        const double* f = s == 0 ? h->bs_fov_deg : h->ue_fov_deg;
+        const double fh = f[0] * k, fv = f[1] * k;          // geometry.py:184
+        d.h_lo[s] = 0 + fh / 2;                             // :187
+        d.h_hi[s] = 2 * M_PI - fh / 2;
+        d.v_hi[s] = M_PI / 2 + fv / 2;                      // :190
+        d.v_lo[s] = M_PI / 2 - fv / 2;
+    }
+    d.ts_f32 = (float)(1.0 / h->bandwidth);                 // channel.py:223 then float32 (NEP 50 weak scalar)
+    d.n_f32 = (float)d.N;
+    d.inv_n = 1.0 / (double)d.N;
+    return DMK_OK;
+}
+
+void bind_arrays(dmk::DevDesc& d, const float* power, const float* phase, const float* delay,
+                 const float* aoa_az, const float* aoa_el, const float* aod_az, const float* aod_el,
+                 const double* ue_rot, const float* doppler, int64_t n, int32_t ld)
+{
+    d.power = power; d.phase = phase; d.delay = delay;
+    d.az[0] = aod_az; d.el[0] = aod_el; d.az[1] = aoa_az; d.el[1] = aoa_el;
+    d.ue_rot = ue_rot; d.doppler = doppler;
+    d.n_users = n; d.ld = ld;
+}
+
+int check_arrays(const float* a, const float* b, const float* c, const float* e, const float* f, const float* g,
+                 const float* h, int64_t n, int32_t ld, int n_cols)
+{
+    if (n < 0) return fail(DMK_ERR_INVALID_ARG, "n_users < 0");
+    if (ld < n_cols) return fail(DMK_ERR_INVALID_ARG, "ld=%d < n_cols=%d", ld, n_cols);
+    if (n > 0 && (!a || !b || !c || !e || !f || !g || !h)) return fail(DMK_ERR_INVALID_ARG, "a path matrix pointer is NULL");
+    return DMK_OK;
+}
+
+int device_sm_count()
+{
+    static int sms = 0;
+    if (!sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (sms <= 0) sms = 148;
+    }
+    return sms;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* dmk_last_error(void) { return g_err; }
+int dmk_abi_version(void) { return DMK_ABI_VERSION; }
+int64_t dmk_launch_count(void) { return g_launches.load(); }
+const char* dmk_last_kernel(void) { return g_kernel; }
+
+int dmk_channels_fd(const dmk_desc* desc, const float* power_dbw, const float* phase_deg, const float* delay_s,
+                    const float* aoa_az_deg, const float* aoa_el_deg, const float* aod_az_deg, const float* aod_el_deg,
+                    const double* ue_rot_deg, const float* doppler_hz, int64_t n_users, int32_t ld, void* out_c64,
+                    uint8_t* fov_mask, uint8_t* valid_mask, uint8_t* clip_mask, void* cuda_stream)
+{
+    using namespace dmk;
+    DevDesc d;
+    int rc = build_desc(desc, true, d);
+    if (rc) return rc;
+    rc = check_arrays(power_dbw, phase_deg, delay_s, aoa_az_deg, aoa_el_deg, aod_az_deg, aod_el_deg, n_users, ld, d.P0);
+    if (rc) return rc;
+    if (n_users == 0 || d.K == 0) return DMK_OK;
+    if (!out_c64) return fail(DMK_ERR_INVALID_ARG, "out is NULL");
+    if ((long long)d.K * d.T > 0x7fffffffLL / 8) return fail(DMK_ERR_INVALID_ARG, "K*T too large");
+    bind_arrays(d, power_dbw, phase_deg, delay_s, aoa_az_deg, aoa_el_deg, aod_az_deg, aod_el_deg, ue_rot_deg, doppler_hz, n_users, ld);
+    d.out = reinterpret_cast<float2*>(out_c64);
+    d.fov_mask = fov_mask; d.valid_mask = valid_mask; d.clip_mask = clip_mask;
+
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(cuda_stream);
+    const int ncols = d.K * d.T;
+    const int n_ct = (ncols + kTK - 1) / kTK;
+    // Few users: split each user's column tiles over several CTAs so the grid covers >= 4 waves.
+    const long long want = 4LL * 2 * device_sm_count();
+    long long ksplit = (want + n_users - 1) / n_users;
+    if (ksplit > n_ct) ksplit = n_ct;
+    if (ksplit < 1) ksplit = 1;
+    const long long grid = n_users * ksplit;
+    if (grid > 0x7fffffffLL) return fail(DMK_ERR_INVALID_ARG, "grid too large: split the user range");
+    const size_t smem = (size_t)kMaxPaths * (kTK + kTM) * sizeof(float2);
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(fd_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(fd_tile_kernel)");
+        attr_set = true;
+    }
+    fd_tile_kernel<<<(unsigned)grid, kFdThreads, smem, st>>>(d, (int)ksplit);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "fd_tile_kernel launch");
+    g_launches.fetch_add(1);
+    snprintf(g_kernel, sizeof(g_kernel), "fd_tile_kernel<64x128> grid=%lld ksplit=%lld", grid, ksplit);
+    return DMK_OK;
+}
+
+int dmk_channels_td(const dmk_desc* desc, const float* power_dbw, const float* phase_deg, const float* delay_s,
+                    const float* aoa_az_deg, const float* aoa_el_deg, const float* aod_az_deg, const float* aod_el_deg,
+                    const double* ue_rot_deg, const float* doppler_hz, int64_t n_users, int32_t ld, void* out_c64,
+                    uint8_t* fov_mask, uint8_t* valid_mask, int32_t* path_slot, void* cuda_stream)
+{
+    using namespace dmk;
+    DevDesc d;
+    int rc = build_desc(desc, false, d);
+    if (rc) return rc;
+    rc = check_arrays(power_dbw, phase_deg, delay_s, aoa_az_deg, aoa_el_deg, aod_az_deg, aod_el_deg, n_users, ld, d.P0);
+    if (rc) return rc;
+    if (n_users == 0 || d.P == 0) return DMK_OK;
+    if (!out_c64) return fail(DMK_ERR_INVALID_ARG, "out is NULL");
+    if (n_users > 0x7fffffffLL) return fail(DMK_ERR_INVALID_ARG, "grid too large: split the user range");
+    bind_arrays(d, power_dbw, phase_deg, delay_s, aoa_az_deg, aoa_el_deg, aod_az_deg, aod_el_deg, ue_rot_deg, doppler_hz, n_users, ld);
+    d.out = reinterpret_cast<float2*>(out_c64);
+    d.fov_mask = fov_mask; d.valid_mask = valid_mask; d.path_slot = path_slot;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(cuda_stream);
+    td_kernel<<<(unsigned)n_users, kTdThreads, 0, st>>>(d);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "td_kernel launch");
+    g_launches.fetch_add(1);
+    snprintf(g_kernel, sizeof(g_kernel), "td_kernel grid=%lld", (long long)n_users);
+    return DMK_OK;
+}
+
+int dmk_path_prologue(const dmk_desc* desc, const float* power_dbw, const float* aoa_az_deg, const float* aoa_el_deg,
+                      const float* aod_az_deg, const float* aod_el_deg, const double* ue_rot_deg, int64_t n_users,
+                      int32_t ld, double* angles_rot, double* power_gain, uint8_t* fov_mask, void* cuda_stream)
+{
+    using namespace dmk;
+    DevDesc d;
+    int rc = build_desc(desc, false, d);
+    if (rc) return rc;
+    rc = check_arrays(power_dbw, power_dbw, power_dbw, aoa_az_deg, aoa_el_deg, aod_az_deg, aod_el_deg, n_users, ld, d.P0);
+    if (rc) return rc;
+    if (n_users == 0) return DMK_OK;
+    // phase/delay are not needed for the by-products: alias them to power (finite or NaN, never dereferenced wrongly)
+    bind_arrays(d, power_dbw, power_dbw, power_dbw, aoa_az_deg, aoa_el_deg, aod_az_deg, aod_el_deg, ue_rot_deg, nullptr, n_users, ld);
+    d.fov_mask = fov_mask;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(cuda_stream);
+    const long long total = n_users * d.P0;
+    const long long grid = (total + 255) / 256;
+    if (grid > 0x7fffffffLL) return fail(DMK_ERR_INVALID_ARG, "grid too large: split the user range");
+    prologue_kernel<<<(unsigned)grid, 256, 0, st>>>(d, angles_rot, power_gain);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "prologue_kernel launch");
+    g_launches.fetch_add(1);
+    return DMK_OK;
+}
+
+int dmk_np_sincosf(const float* x, float* s, float* c, int64_t n, void* cuda_stream)
+{
+    if (n < 0) return fail(DMK_ERR_INVALID_ARG, "n < 0");
+    if (n == 0) return DMK_OK;
+    if (!x || !s || !c) return fail(DMK_ERR_INVALID_ARG, "NULL pointer");
+    const long long grid = (n + 255) / 256;
+    if (grid > 0x7fffffffLL) return fail(DMK_ERR_INVALID_ARG, "n too large");
+    dmk::np_sincosf_kernel<<<(unsigned)grid, 256, 0, reinterpret_cast<cudaStream_t>(cuda_stream)>>>(x, s, c, n);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "np_sincosf_kernel launch");
+    g_launches.fetch_add(1);
+    return DMK_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,168 @@
+// dmk_fd.cuh -- fused frequency-domain channel kernel.
+//
+//   H[u, m, q] = sum_p A[m,p] * W[p,q]          m = r*Mt + t  (M rows), q = k_idx*T + it (K*T columns)
+//   A[m,p] = c_p * exp(j 2 pi (y_t u_t + z_t v_t + y_r u_r + z_r v_r))      (steering, gain folded in)
+//   W[p,q] = exp(j 2 pi (f_D[p] t_it - k delay_n[p] / N))                   (channel.py:196-197)
+//
+// One CTA owns one user (or a slice of its column tiles when there are few users).  Warp 0 runs
+// the per-path prologue and compacts the contributing paths into shared memory; the CTA then
+// walks 64 x 128 output tiles: W tile and A tile are built in shared memory with the phase
+// argument reduced in float64, and each thread accumulates an 8 x 4 complex register tile over
+// the (compacted) paths with FP32 FMAs.  Output is written once, coalesced, streaming.
+#pragma once
+#include "dmk_prologue.cuh"
+
+namespace dmk {
+
+constexpr int kFdThreads = 256;
+constexpr int kTM = 64;      // rows per CTA tile  (8 warps x 8 rows)
+constexpr int kTK = 128;     // columns per CTA tile (32 lanes x 4 columns)
+
+struct FdShared {
+    float2 c[kMaxPaths];
+    double wcyc[kMaxPaths];
+    double fd[kMaxPaths];
+    double u[2][kMaxPaths];
+    double v[2][kMaxPaths];
+    int    np;
+};
+
+// Warp 0: prologue for the P0 path columns of `user`, masks out, contributing paths compacted.
+__device__ __forceinline__ void fd_warp_prologue(const DevDesc& d, long long user, FdShared& sh, bool write_masks)
+{
+    const int lane = threadIdx.x & 31;
+    PathState st;
+    bool active = lane < d.P0;
+    st.contrib = false; st.valid = false; st.fov = true; st.over = false;
+    if (active) path_prologue<true>(d, user, lane, st);
+    const unsigned ballot = __ballot_sync(0xffffffffu, active && st.contrib);
+    if (active && st.contrib) {
+        const int j = __popc(ballot & ((1u << lane) - 1u));
+        sh.c[j] = st.c; sh.wcyc[j] = st.wcyc; sh.fd[j] = st.fd;
+        sh.u[0][j] = st.u[0]; sh.v[0][j] = st.v[0];
+        sh.u[1][j] = st.u[1]; sh.v[1][j] = st.v[1];
+    }
+    if (lane == 0) sh.np = __popc(ballot);
+    if (write_masks && active) {
+        const long long o = user * (long long)d.P0 + lane;
+        if (d.fov_mask)   d.fov_mask[o]   = st.fov ? 1 : 0;
+        if (d.valid_mask) d.valid_mask[o] = st.valid ? 1 : 0;
+        if (d.clip_mask)  d.clip_mask[o]  = (st.valid && st.over) ? 1 : 0;
+    }
+}
+
+__global__ void __launch_bounds__(kFdThreads, 2)
+fd_tile_kernel(const DevDesc d, const int ksplit)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2* sW = reinterpret_cast<float2*>(smem_raw);                    // [kMaxPaths][kTK]
+    float2* sA = sW + kMaxPaths * kTK;                                   // [kMaxPaths][kTM]
+    __shared__ FdShared sh;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const long long user = blockIdx.x / ksplit;
+    const int ks = blockIdx.x % ksplit;
+
+    if (warp == 0) fd_warp_prologue(d, user, sh, ks == 0);
+    __syncthreads();
+    const int np = sh.np;
+
+    const int ncols = d.K * d.T;
+    const int n_ct = (ncols + kTK - 1) / kTK;
+    const int n_rt = (d.M + kTM - 1) / kTM;
+    float2* out_u = d.out + user * (long long)d.M * ncols;
+    const bool vec_ok = ((ncols & 1) == 0) && ((reinterpret_cast<uintptr_t>(d.out) & 15) == 0);
+
+    for (int ct = ks; ct < n_ct; ct += ksplit) {
+        const int col0 = ct * kTK;
+        __syncthreads();                                   // previous tile's readers are done with sW
+        // ---- W tile: per-(path, column) phasor, phase reduced in float64
+        for (int e = tid; e < np * kTK; e += kFdThreads) {
+            const int p = e / kTK, cidx = e % kTK;
+            const int col = col0 + cidx;
+            float2 w = make_float2(0.f, 0.f);
+            if (col < ncols) {
+                const int ki = col / d.T, it = col - ki * d.T;
+                const double kval = (double)subcarrier_at(d, ki);
+                double cyc = -(sh.wcyc[p] * kval);
+                if (d.has_time_axis) cyc += sh.fd[p] * d.times[it];
+                w = phasor_cycles(cyc);
+            }
+            sW[p * kTK + cidx] = w;
+        }
+        for (int rt = 0; rt < n_rt; ++rt) {
+            const int row0 = rt * kTM;
+            if (rt > 0) __syncthreads();                   // previous row tile's readers are done with sA
+            // ---- A tile: gain * TX steering * RX steering, one phasor per (row, path)
+            for (int e = tid; e < np * kTM; e += kFdThreads) {
+                const int p = e / kTM, r = e % kTM;
+                const int m = row0 + r;
+                float2 a = make_float2(0.f, 0.f);
+                if (m < d.M) {
+                    const int rr = m / d.Mt, t = m - rr * d.Mt;
+                    const int yt = t % d.bs0, zt = t / d.bs0;
+                    const int yr = rr % d.ue0, zr = rr / d.ue0;
+                    const double cyc = (double)yt * sh.u[0][p] + (double)zt * sh.v[0][p]
+                                     + (double)yr * sh.u[1][p] + (double)zr * sh.v[1][p];
+                    a = cmul(sh.c[p], phasor_cycles(cyc));
+                }
+                sA[p * kTM + r] = a;
+            }
+            __syncthreads();
+
+            // ---- rank-np accumulation, 8 rows x 4 columns per thread
+            float2 acc[8][4];
+            #pragma unroll
+            for (int i = 0; i < 8; ++i)
+                #pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = make_float2(0.f, 0.f);
+
+            const float4* wrow = reinterpret_cast<const float4*>(sW) + lane;          // columns 2*lane, 2*lane+1
+            const float4* arow = reinterpret_cast<const float4*>(sA) + warp * 4;      // rows warp*8 .. +7
+            #pragma unroll 1
+            for (int p = 0; p < np; ++p) {
+                const float4 w01 = wrow[p * (kTK / 2)];
+                const float4 w23 = wrow[p * (kTK / 2) + 32];
+                const float2 w[4] = {make_float2(w01.x, w01.y), make_float2(w01.z, w01.w),
+                                     make_float2(w23.x, w23.y), make_float2(w23.z, w23.w)};
+                float2 a[8];
+                #pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float4 t = arow[p * (kTM / 2) + i];
+                    a[2 * i] = make_float2(t.x, t.y);
+                    a[2 * i + 1] = make_float2(t.z, t.w);
+                }
+                #pragma unroll
+                for (int i = 0; i < 8; ++i)
+                    #pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        acc[i][j].x = fmaf(a[i].x, w[j].x, acc[i][j].x);
+                        acc[i][j].x = fmaf(-a[i].y, w[j].y, acc[i][j].x);
+                        acc[i][j].y = fmaf(a[i].x, w[j].y, acc[i][j].y);
+                        acc[i][j].y = fmaf(a[i].y, w[j].x, acc[i][j].y);
+                    }
+            }
+
+            // ---- store: each lane owns columns {2l, 2l+1} and {64+2l, 64+2l+1} of the tile
+            #pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int m = row0 + warp * 8 + i;
+                if (m >= d.M) break;
+                float2* orow = out_u + (long long)m * ncols + col0;
+                #pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int c = h * 64 + 2 * lane;
+                    if (vec_ok && col0 + c + 1 < ncols) {
+                        __stcs(reinterpret_cast<float4*>(orow + c),
+                               make_float4(acc[i][2 * h].x, acc[i][2 * h].y, acc[i][2 * h + 1].x, acc[i][2 * h + 1].y));
+                    } else {
+                        if (col0 + c < ncols)     __stcs(orow + c, acc[i][2 * h]);
+                        if (col0 + c + 1 < ncols) __stcs(orow + c + 1, acc[i][2 * h + 1]);
+                    }
+                }
+            }
+        }
+    }
+}
+
+}  // namespace dmk

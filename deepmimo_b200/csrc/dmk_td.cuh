@@ -1,0 +1,138 @@
+// dmk_td.cuh -- fused time-domain channel kernel (freq_domain = 0) and per-path by-product kernels.
+//
+//   H[u, m, j, it] = c_{p_j} * exp(j 2 pi (steer(m, p_j) + f_D[p_j] t_it))     j < n_valid(u)
+//                  = 0                                                        otherwise
+// p_j is the j-th column of user u whose power is not NaN (channel.py:260,:274-287); a path outside
+// the FoV keeps its slot and is zero (dataset.py:508-511 + geometry.py:65-80).  The kernel is bound
+// by the output write: every element is one complex multiply of two shared-memory table entries.
+#pragma once
+#include "dmk_prologue.cuh"
+
+namespace dmk {
+
+constexpr int kTdThreads = 256;
+constexpr int kTdRows = 64;               // rows of the steering table built per pass
+
+struct TdShared {
+    float2 c[kMaxPaths];
+    double fd[kMaxPaths];
+    double u[2][kMaxPaths];
+    double v[2][kMaxPaths];
+    unsigned char contrib[kMaxPaths];
+    int nv;
+};
+
+__device__ __forceinline__ void td_warp_prologue(const DevDesc& d, long long user, TdShared& sh)
+{
+    const int lane = threadIdx.x & 31;
+    PathState st;
+    const bool active = lane < d.P0;
+    st.contrib = false; st.valid = false; st.fov = true; st.over = false;
+    if (active) path_prologue<false>(d, user, lane, st);
+    const unsigned ballot = __ballot_sync(0xffffffffu, active && st.valid);
+    const int j = __popc(ballot & ((1u << lane) - 1u));
+    if (active && st.valid) {
+        sh.c[j] = st.c; sh.fd[j] = st.fd; sh.contrib[j] = st.contrib ? 1 : 0;
+        sh.u[0][j] = st.u[0]; sh.v[0][j] = st.v[0];
+        sh.u[1][j] = st.u[1]; sh.v[1][j] = st.v[1];
+    }
+    if (lane == 0) sh.nv = __popc(ballot);
+    if (active) {
+        const long long o = user * (long long)d.P0 + lane;
+        if (d.fov_mask)   d.fov_mask[o]   = st.fov ? 1 : 0;
+        if (d.valid_mask) d.valid_mask[o] = st.valid ? 1 : 0;
+        if (d.path_slot)  d.path_slot[o]  = st.valid ? j : -1;
+    }
+}
+
+__global__ void __launch_bounds__(kTdThreads, 4)
+td_kernel(const DevDesc d)
+{
+    __shared__ TdShared sh;
+    __shared__ float2 sA[kTdRows * kMaxPaths];        // [row][slot] gain * steering
+    __shared__ float2 sD[kMaxPaths * 64];             // [slot][it] Doppler phasors, 64 snapshots per pass
+
+    const int tid = threadIdx.x;
+    const long long user = blockIdx.x;
+    if (tid < 32) td_warp_prologue(d, user, sh);
+    __syncthreads();
+    const int nv = sh.nv;
+    const int P = d.P, T = d.T;
+    float2* out_u = d.out + user * (long long)d.M * P * T;
+
+    for (int it0 = 0; it0 < T; it0 += 64) {
+        const int tn = min(64, T - it0);
+        __syncthreads();
+        if (d.has_time_axis) {
+            for (int e = tid; e < nv * tn; e += kTdThreads) {
+                const int j = e / tn, it = e - j * tn;
+                sD[j * 64 + it] = phasor_cycles(sh.fd[j] * d.times[it0 + it]);
+            }
+        }
+        for (int row0 = 0; row0 < d.M; row0 += kTdRows) {
+            const int rn = min(kTdRows, d.M - row0);
+            __syncthreads();
+            for (int e = tid; e < rn * P; e += kTdThreads) {
+                const int r = e / P, j = e - r * P;
+                float2 a = make_float2(0.f, 0.f);
+                if (j < nv && sh.contrib[j]) {
+                    const int m = row0 + r;
+                    const int rr = m / d.Mt, t = m - rr * d.Mt;
+                    const int yt = t % d.bs0, zt = t / d.bs0;
+                    const int yr = rr % d.ue0, zr = rr / d.ue0;
+                    const double cyc = (double)yt * sh.u[0][j] + (double)zt * sh.v[0][j]
+                                     + (double)yr * sh.u[1][j] + (double)zr * sh.v[1][j];
+                    a = cmul(sh.c[j], phasor_cycles(cyc));
+                }
+                sA[r * P + j] = a;
+            }
+            __syncthreads();
+            if (!d.has_time_axis) {
+                // [rn, P] block is contiguous in the output
+                float2* o = out_u + (long long)row0 * P;
+                for (int e = tid; e < rn * P; e += kTdThreads) __stcs(o + e, sA[e]);
+            } else {
+                for (int e = tid; e < rn * P * tn; e += kTdThreads) {
+                    const int rj = e / tn, it = e - rj * tn;         // rj = r*P + j
+                    const int j = rj % P;
+                    float2 val = make_float2(0.f, 0.f);
+                    if (j < nv) val = cmul(sA[rj], sD[j * 64 + it]);
+                    __stcs(out_u + ((long long)row0 * P + rj) * T + it0 + it, val);
+                }
+            }
+        }
+    }
+}
+
+// Per-path by-products (Dataset caches): rotated angles, power with antenna gain, FoV mask.
+__global__ void __launch_bounds__(256)
+prologue_kernel(const DevDesc d, double* __restrict__ angles_rot, double* __restrict__ power_gain)
+{
+    const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const long long total = d.n_users * d.P0;
+    if (idx >= total) return;
+    const long long user = idx / d.P0;
+    const int p = (int)(idx - user * d.P0);
+    PathState st;
+    path_prologue<false>(d, user, p, st);
+    if (angles_rot) {
+        angles_rot[0 * total + idx] = st.th[0];
+        angles_rot[1 * total + idx] = st.ph[0];
+        angles_rot[2 * total + idx] = st.th[1];
+        angles_rot[3 * total + idx] = st.ph[1];
+    }
+    if (power_gain) power_gain[idx] = st.pw;
+    if (d.fov_mask) d.fov_mask[idx] = st.fov ? 1 : 0;
+}
+
+__global__ void np_sincosf_kernel(const float* __restrict__ x, float* __restrict__ s, float* __restrict__ c, long long n)
+{
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i < n) {
+        float ss, cc;
+        np_sincosf(x[i], ss, cc);
+        s[i] = ss; c[i] = cc;
+    }
+}
+
+}  // namespace dmk
