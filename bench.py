@@ -1,0 +1,450 @@
+#!/usr/bin/env python
+"""bench.py -- H coefficients/s of the channel-generation hot path on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg2] [--impl b200|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" = one pass of the fused channel kernel over every user of the rank's synthetic scenario,
+inputs already resident in HBM (`value`); `e2e` is the same metric through the public drop-in call
+`compute_channels(dataset, params)` with HOST buffers (pinned H2D of the path matrices, kernels, D2H of
+H into pinned host memory) inside the timed region.  Users are independent: ranks process disjoint
+shards with no data-path collective (`scaling: weak`); NCCL is used only for the barrier and the
+max-over-ranks of the device time.  Rank 0 prints ONE JSON line.
+
+`--impl reference` times the CPU restatement of the reference's NumPy path (oracle/channel_oracle.py,
+bit-identical to the live reference on the golden cases; the reference is pure Python and cannot travel
+to the GPU box) on all host cores over a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+os.environ.setdefault("TQDM_DISABLE", "1")
+
+METRIC = "H coefficients/s (complex64)"
+UNIT = "coef/s"
+WORKLOADS = {"cfg1": 1, "cfg2": 2, "cfg3": 3, "cfg4": 4, "cfg5": 5}
+# --impl reference: users per host core in one step (about 3 s of NumPy work per core at the default K + W)
+CPU_SAMPLE_USERS = {1: 12000, 2: 24, 3: 48, 4: 3000, 5: 160}
+# cpu_baseline leg of the b200 arm: one core, about 10-30 s of NumPy work
+CPU_BASELINE_USERS = {1: 80000, 2: 128, 3: 256, 4: 20000, 5: 1024}
+FP32_LANES_PER_SM = 128
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return float(p["hbm_gbs"]), float(p.get("sm_max_mhz", 1965.0)), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, 1965.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------------
+# workload bookkeeping
+# ------------------------------------------------------------------------------------------------
+def scenario_for(workload: str, rank: int, users):
+    from deepmimo_b200.synth import scenario
+    cfg = WORKLOADS[workload]
+    if cfg == 5:
+        return scenario(5, users, bs_index=rank)            # one BS per GPU
+    return scenario(cfg, users, shard=rank)
+
+
+def oracle_call(s, lo, hi):
+    from oracle import channel_oracle as orc
+    from util import oracle_kwargs_from_params
+    data = {k: (v[lo:hi] if v.shape[0] == s.n_ue else v) for k, v in s.data.items()}
+    kw = oracle_kwargs_from_params(s.params, s.bs_fov, s.ue_fov)
+    rot = np.asarray(kw["ue_rotation"])
+    if rot.ndim == 2 and rot.shape[0] == s.n_ue:
+        kw["ue_rotation"] = rot[lo:hi]
+    dop = None if s.doppler_hz is None else s.doppler_hz[lo:hi]
+    return orc.compute_channels(data, **kw, doppler_hz=dop, times=s.times)["H"]
+
+
+def _oracle_worker(args):
+    s, lo, hi = args
+    return int(oracle_call(s, lo, hi).size)
+
+
+def algorithmic_counts(s, plan, info):
+    """bytes = 8 n_coef + 28 n P (+24 n per-user rotation); FD flops = 8 per (coef, valid in-FoV path),
+    TD flops = 6 per written slot."""
+    n, p0 = plan.n_users, plan.n_cols
+    shape = plan.out_shape()
+    n_coef = int(np.prod(shape))
+    per_user_cols = int(np.prod(shape[1:]))
+    bytes_alg = 8 * n_coef + 28 * n * p0 + (24 * n if plan.ue_rot is not None else 0) + \
+        (4 * n * p0 if plan.doppler is not None else 0)
+    active = info.valid.copy()
+    if info.fov_mask is not None:
+        active &= info.fov_mask[:, :active.shape[1]]
+    if plan.spec.freq_domain:
+        flops = 8 * per_user_cols * int(active.sum())
+    else:
+        t = 1 if plan.spec.times is None else len(plan.spec.times)
+        flops = 6 * plan.spec.m_rx * plan.spec.m_tx * t * int(active.sum())
+    return n_coef, bytes_alg, flops, float(active.sum()) / max(n, 1)
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    REASONS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+               0x80: "hw_power_brake_slowdown", 0x2: "applications_clocks_setting", 0x10: "sync_boost"}
+
+    def __init__(self, device_index: int, interval=0.01):
+        super().__init__(daemon=True)
+        self.interval, self.samples, self.reasons, self.power = interval, [], set(), []
+        self.stop_flag = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            import torch
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            uuid = str(torch.cuda.get_device_properties(device_index).uuid)
+            try:
+                self.h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid).encode())
+            except Exception:  # noqa: BLE001
+                self.h = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception as e:  # noqa: BLE001
+            log(f"[bench] NVML unavailable ({e}); clocks not sampled")
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        while not self.stop_flag.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+                    else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in self.REASONS.items():
+                    if r & bit:
+                        self.reasons.add(name)
+                self.power.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
+            except Exception:  # noqa: BLE001
+                pass
+            time.sleep(self.interval)
+
+    def result(self):
+        if not self.ok or not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(statistics.median(self.samples)), "sm_min_mhz": float(min(self.samples)),
+                "sm_max_mhz": float(self.max_mhz), "reasons": sorted(self.reasons), "samples": len(self.samples),
+                "power_w_max": max(self.power) if self.power else None}
+
+
+# ------------------------------------------------------------------------------------------------
+# the GPU arm
+# ------------------------------------------------------------------------------------------------
+def time_plan(plan, out_ring, chunk, steps, warmup, flush, dist, world):
+    """Per-step CUDA-event timing on the launch stream; L2 flushed (untimed) between steps.
+    Returns (sum of step times in ms on this rank, list of step ms)."""
+    import torch
+    stream = torch.cuda.current_stream()
+    n = plan.n_users
+
+    def one_step():
+        i = 0
+        for a in range(0, n, chunk):
+            b = min(a + chunk, n)
+            plan.run(out_ring[i % len(out_ring)][: b - a], a, b)
+            i += 1
+
+    for _ in range(warmup):
+        one_step()
+        flush.fill_(1)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    for k in range(steps):
+        flush.fill_(k)                      # > L2 (126 MB): evict inputs/outputs of the previous step
+        ev[k][0].record(stream)
+        one_step()
+        ev[k][1].record(stream)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ms = [a.elapsed_time(b) for a, b in ev]
+    return float(sum(ms)), ms
+
+
+def run_workload(workload, users, steps, warmup, rank, world, dist, flush, want_clocks=True):
+    import torch
+    import deepmimo_b200 as dmb
+    from deepmimo_b200 import _lib
+    from deepmimo_b200.channels import default_chunk_users
+
+    s = scenario_for(workload, rank, users)
+    ds = dmb.Dataset(dict(s.data))
+    if s.bs_fov is not None:
+        ds.apply_fov(bs_fov=s.bs_fov, ue_fov=s.ue_fov)
+    params = dmb.ChannelGenParameters(s.params)
+    plan, _ = dmb.make_plan(ds, params, times=s.times, doppler=s.doppler_hz, warn=False)
+    per_user = plan.spec.coefs_per_user(plan.n_cols) * 8
+    total_bytes = per_user * plan.n_users
+    free_b, _tot = torch.cuda.mem_get_info()
+    if total_bytes <= min(64 << 30, int(free_b * 0.6)):
+        chunk, ring = plan.n_users, [plan.alloc_out()]
+        layout = f"single [{plan.n_users} users] output tensor ({total_bytes / 2**30:.1f} GiB) rewritten every step"
+    else:
+        chunk = default_chunk_users(plan, 4 << 30)          # ring of 4 GiB chunks (SURVEY.md 8d cfg 5)
+        ring = [plan.alloc_out(chunk) for _ in range(3)]
+        layout = f"ring of 3 x {chunk} users ({chunk * per_user / 2**30:.1f} GiB) output chunks in HBM"
+    # masks once (also gives the algorithmic flop count)
+    masks = plan.alloc_masks()
+    i = 0
+    for a in range(0, plan.n_users, chunk):
+        b = min(a + chunk, plan.n_users)
+        plan.run(ring[i % len(ring)][: b - a], a, b, {k: v[a:b] for k, v in masks.items()})
+        i += 1
+    torch.cuda.synchronize()
+    info = plan.info_from_masks(masks)
+    n_coef, bytes_alg, flops, pbar = algorithmic_counts(s, plan, info)
+
+    sampler = ClockSampler(torch.cuda.current_device()) if want_clocks else None
+    l0 = _lib.launch_count()
+    if sampler:
+        sampler.start()
+    total_ms, ms = time_plan(plan, ring, chunk, steps, warmup, flush, dist, world)
+    if sampler:
+        sampler.stop_flag.set()
+        sampler.join()
+    launches = (_lib.launch_count() - l0) * steps // (steps + warmup)      # launches inside the timed region
+    return dict(scenario=s, plan=plan, ds=ds, params=params, total_ms=total_ms, ms=ms, n_coef=n_coef, bytes_alg=bytes_alg,
+                flops=flops, pbar=pbar, layout=layout, launches=launches, kernel=_lib.last_kernel(),
+                clocks=sampler.result() if sampler else None, launches_per_step=(plan.n_users + chunk - 1) // chunk)
+
+
+def run_e2e(res, steps, rank, world, dist, cap_bytes=4 << 30):
+    """Public-API path with host buffers: pinned H2D of the path matrices + kernels + D2H of H, every step."""
+    import torch
+    import deepmimo_b200 as dmb
+    s, plan = res["scenario"], res["plan"]
+    per_user = plan.spec.coefs_per_user(plan.n_cols) * 8
+    n = int(max(1, min(plan.n_users, cap_bytes // per_user)))
+
+    def pinned(a):
+        return torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()
+
+    data = {k: (pinned(v[:n]) if v.shape[0] == s.n_ue else v) for k, v in s.data.items()}
+    prm = dmb.ChannelGenParameters(s.params)
+    rot = np.asarray(prm.ue_antenna.rotation)
+    if rot.ndim == 2 and rot.shape[0] == s.n_ue:
+        prm.ue_antenna.rotation = pinned(rot[:n])
+    dop = None if s.doppler_hz is None else pinned(s.doppler_hz[:n])
+    ds = dmb.Dataset(data)
+    if s.bs_fov is not None:
+        ds.apply_fov(bs_fov=s.bs_fov, ue_fov=s.ue_fov)
+    shape = plan.spec.out_shape(n, plan.n_cols)
+    host_out = torch.empty(shape, dtype=torch.complex64, pin_memory=True)
+    h2d = sum(int(data[k].nbytes) for k in ("power", "phase", "delay", "aoa_az", "aoa_el", "aod_az", "aod_el"))
+    h2d += (int(np.asarray(prm.ue_antenna.rotation).nbytes) if rot.ndim == 2 else 0) + (int(dop.nbytes) if dop is not None else 0)
+    d2h = int(np.prod(shape)) * 8
+
+    def call():
+        return dmb.compute_channels(ds, prm, times=s.times, doppler=dop, host_out=host_out, cache=False, warn=False)
+
+    for _ in range(2):
+        call()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        call()                              # returns after the copy stream has drained (host array complete)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    if world > 1:
+        dist.barrier()
+    return dict(seconds=dt, steps=steps, users=n, coefs_per_step=int(np.prod(shape)), h2d=h2d, d2h=d2h)
+
+
+def cpu_baseline(s, workload, cores=1):
+    cfg = WORKLOADS[workload]
+    n = min(s.n_ue, CPU_BASELINE_USERS[cfg])
+    t0 = time.perf_counter()
+    H = oracle_call(s, 0, n)
+    dt = time.perf_counter() - t0
+    return {"value": H.size / dt, "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": f"{n} users of {workload} ({H.size} coefficients) in {dt:.1f} s, oracle/channel_oracle.py "
+                      f"(NumPy {np.__version__}, single thread like the reference's per-user loop)"}
+
+
+def gpu_main(args):
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device; there is no CPU fallback for the b200 arm")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    hbm_peak, sm_max_mhz, peak_src = measured_peaks()
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")
+    users = args.users
+
+    res = run_workload(args.workload, users, args.steps, args.warmup, rank, world, dist, flush)
+    t_local = torch.tensor([res["total_ms"]], dtype=torch.float64, device="cuda")
+    coefs = torch.tensor([float(res["n_coef"])], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t_local, op=dist.ReduceOp.MAX)
+        dist.all_reduce(coefs, op=dist.ReduceOp.SUM)
+    total_ms, total_coefs = float(t_local.item()), float(coefs.item())
+    value = total_coefs * args.steps / (total_ms / 1e3)
+
+    e2e = run_e2e(res, args.e2e_steps, rank, world, dist)
+    e_t = torch.tensor([e2e["seconds"]], dtype=torch.float64, device="cuda")
+    e_c = torch.tensor([float(e2e["coefs_per_step"])], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(e_t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(e_c, op=dist.ReduceOp.SUM)
+    e2e_value = float(e_c.item()) * e2e["steps"] / float(e_t.item())
+
+    extra = {}
+    if rank == 0 and world == 1 and args.others:
+        for w in [w for w in ("cfg1", "cfg3", "cfg4", "cfg5") if w != args.workload]:
+            try:
+                r = run_workload(w, None, 5, 3, 0, 1, dist, flush, want_clocks=False)
+                ms = r["total_ms"] / 5
+                extra[w] = {"coef_per_s": r["n_coef"] / (ms / 1e3), "ms_per_step": ms, "users": r["plan"].n_users,
+                            "gb_per_s": r["bytes_alg"] / (ms / 1e3) / 1e9, "tflops_fp32": r["flops"] / (ms / 1e3) / 1e12,
+                            "mean_active_paths": r["pbar"], "layout": r["layout"], "kernel": r["kernel"].split(" ")[0]}
+                del r
+                torch.cuda.empty_cache()
+            except Exception as e:  # noqa: BLE001
+                extra[w] = {"error": str(e)[:200]}
+
+    if rank == 0:
+        ms_step = total_ms / args.steps
+        n_launch = res["launches_per_step"]
+        t_kernel = (res["total_ms"] / args.steps) / 1e3 / n_launch        # average launch duration on rank 0
+        gbps = res["bytes_alg"] / n_launch / t_kernel / 1e9
+        clocks = res["clocks"] or {}
+        f_clk = sm_max_mhz * 1e6
+        fp32_peak = 2 * 148 * FP32_LANES_PER_SM * f_clk / 1e12
+        tfl = res["flops"] / n_launch / t_kernel / 1e12
+        t_write = res["bytes_alg"] / (hbm_peak * 1e9)
+        t_fma = res["flops"] / (fp32_peak * 1e12)
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tpath):
+            with open(tpath) as f:
+                traffic = json.load(f).get(args.workload)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: {res['scenario'].notes}", "users_per_gpu": res["plan"].n_users,
+                       "out_shape_per_gpu": list(res["plan"].out_shape()), "mean_active_paths_per_user": res["pbar"],
+                       "sharding": "independent (BS, user) shards per GPU, no data-path collective",
+                       "output": res["layout"],
+                       "l2": "512 MiB flush write between timed steps (untimed); output per step >> 126 MB L2",
+                       "timing": "per-step CUDA events on the launch stream, summed; max over ranks"},
+            "roofline": {"bound": "hbm", "achieved": gbps, "peak": hbm_peak, "unit": "GB/s", "frac": gbps / hbm_peak,
+                         "traffic": traffic, "peak_source": peak_src, "kernel": res["kernel"],
+                         "algorithmic_bytes_per_launch": res["bytes_alg"] / n_launch,
+                         "fp32": {"achieved_tflops": tfl, "peak_tflops": fp32_peak, "frac": tfl / fp32_peak,
+                                  "peak_source": f"2*148 SM*128 lanes*{sm_max_mhz:.0f} MHz (nominal max clock)",
+                                  "algorithmic_flops_per_launch": res["flops"] / n_launch},
+                         "t_min_over_t": max(t_write, t_fma) / (ms_step / 1e3 * (1 if world == 1 else 1)),
+                         "t_min_bound": "fp32" if t_fma > t_write else "hbm"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"],
+                    "users_per_gpu": e2e["users"], "steps": e2e["steps"],
+                    "path": "deepmimo_b200.compute_channels(dataset, params, host_out=pinned): pinned H2D + fused kernel "
+                            "(1 GiB chunks, 2 device buffers) + D2H overlapped on a copy stream"},
+            "gpu_launches": res["launches"],
+            "clocks": clocks,
+        }
+        if world == 1 and not args.no_cpu:
+            line["cpu_baseline"] = cpu_baseline(res["scenario"], args.workload)
+        if extra:
+            line["workloads"] = extra
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------------
+# the reference (CPU) arm
+# ------------------------------------------------------------------------------------------------
+def reference_main(args):
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    cfg = WORKLOADS[args.workload]
+    cores = os.cpu_count() or 1
+    # bounded sample: scale the per-step sample so that K + W steps end within a few minutes
+    per = max(1, int(CPU_SAMPLE_USERS[cfg] * min(1.0, 15.0 / (args.steps + args.warmup))))
+    s = scenario_for(args.workload, 0, per * cores)
+    jobs = [(s, i * per, (i + 1) * per) for i in range(cores)]
+    ctx = mp.get_context("fork")
+    times, coefs = [], 0
+    with ctx.Pool(cores) as pool:
+        for k in range(args.warmup + args.steps):
+            t0 = time.perf_counter()
+            sizes = pool.map(_oracle_worker, jobs)
+            dt = time.perf_counter() - t0
+            if k >= args.warmup:
+                times.append(dt)
+                coefs = sum(sizes)
+    total = sum(times)
+    value = coefs * len(times) / total
+    sample = (f"{per * cores} users of {args.workload} per step ({coefs} coefficients), {cores} processes x {per} users, "
+              f"oracle/channel_oracle.py (NumPy {np.__version__}); the reference itself is single-threaded")
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": int(os.environ.get("WORLD_SIZE", 1)),
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": total / len(times) * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64/c128 (NumPy)", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: {s.notes}", "sample_users_per_step": per * cores},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--users", type=int, default=None, help="users per GPU (default: the configuration's size)")
+    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--others", action="store_true", default=True, help="also time the other configurations briefly (N=1)")
+    ap.add_argument("--no-others", dest="others", action="store_false")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return reference_main(args)
+    return gpu_main(args)
+
+
+if __name__ == "__main__":
+    main()

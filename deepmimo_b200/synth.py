@@ -97,23 +97,27 @@ def doppler_from_velocity(data: dict, seed: int, carrier_hz: float, vmax: float 
     return fd.astype(np.float32)
 
 
-def scenario(cfg: int, n_ue: Optional[int] = None, *, bs_index: int = 0) -> Scenario:
-    """The five BASELINE.json configurations, optionally with fewer users."""
+def scenario(cfg: int, n_ue: Optional[int] = None, *, bs_index: int = 0, shard: int = 0) -> Scenario:
+    """The five BASELINE.json configurations, optionally with fewer users.
+
+    `shard` offsets every seed by 100*shard (distinct data per rank in weak-scaling runs); `bs_index`
+    selects the base station of config 5 (seed 1005 + 10*b)."""
+    so = 100 * shard
     if cfg == 1:
         n = 80_000 if n_ue is None else n_ue
-        d = make_paths(n, 1001, n_sc=64, bandwidth=10e6)
+        d = make_paths(n, 1001 + so, n_sc=64, bandwidth=10e6)
         return Scenario("cfg1_asu_8x1_K64", d, _params([8, 1], [1, 1], 64, 64, 10e6),
                         notes="1 BS, 8x1 ULA, 1 UE antenna, N=K=64, B=10 MHz, FD, isotropic")
     if cfg == 2:
         n = 4096 if n_ue is None else n_ue
-        d = make_paths(n, 1002, n_sc=512, bandwidth=50e6)
-        ue_rot = np.random.default_rng(42).uniform(0, 45, (n, 3))
+        d = make_paths(n, 1002 + so, n_sc=512, bandwidth=50e6)
+        ue_rot = np.random.default_rng(42 + so).uniform(0, 45, (n, 3))
         return Scenario("cfg2_32x8_2x2_K512", d,
                         _params([32, 8], [2, 2], 512, 512, 50e6, bs_rot=[30, 40, 30], ue_rot=ue_rot),
                         notes="32x8 rotated BS UPA + 2x2 UE (per-user rotation), N=K=512, B=50 MHz, 3.5 GHz, isotropic")
     if cfg == 3:
         n = 8192 if n_ue is None else n_ue
-        d = make_paths(n, 1003, n_sc=1024, bandwidth=100e6)
+        d = make_paths(n, 1003 + so, n_sc=1024, bandwidth=100e6)
         return Scenario("cfg3_64x4_dipole_fov_K1024", d,
                         _params([64, 4], [1, 1], 1024, 1024, 100e6, bs_rot=[0, 30, -135],
                                 bs_pat="halfwave-dipole", ue_pat="halfwave-dipole"),
@@ -121,15 +125,15 @@ def scenario(cfg: int, n_ue: Optional[int] = None, *, bs_index: int = 0) -> Scen
                         notes="64x4 UPA, half-wave dipole, BS FoV [140,120], UE FoV [90,80], N=K=1024, B=100 MHz")
     if cfg == 4:
         n = 50_000 if n_ue is None else n_ue
-        d = make_paths(n, 1004, n_sc=512, bandwidth=10e6)
-        fd = doppler_from_velocity(d, 2004, 3.5e9)
+        d = make_paths(n, 1004 + so, n_sc=512, bandwidth=10e6)
+        fd = doppler_from_velocity(d, 2004 + so, 3.5e9)
         return Scenario("cfg4_td_doppler_T16", d,
                         _params([8, 4], [2, 1], 512, 1, 10e6, freq_domain=0),
                         doppler_hz=fd, times=np.arange(16) * 1e-3,
                         notes="time domain, 8x4 BS, 2x1 UE, 25 path slots, 16 snapshots of 1 ms, Doppler from UE velocity")
     if cfg == 5:
         n = 200_000 if n_ue is None else n_ue
-        d = make_paths(n, 1005 + 10 * bs_index, n_sc=1024, bandwidth=100e6)
+        d = make_paths(n, 1005 + 10 * bs_index + so, n_sc=1024, bandwidth=100e6)
         return Scenario(f"cfg5_city_bs{bs_index}_8x8_K1024", d, _params([8, 8], [1, 1], 1024, 1024, 100e6),
                         notes="city-scale shard: one BS x 200k users, 8x8 BS UPA, 1 UE antenna, N=K=1024, B=100 MHz")
     raise ValueError(f"unknown config {cfg}")

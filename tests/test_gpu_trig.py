@@ -32,11 +32,11 @@ def test_device_np_sincosf_degrees_grid_and_specials():
     rng = np.random.default_rng(7)
     deg = np.concatenate([rng.uniform(0, 180, 4_000_000), np.arange(0, 180.5, 0.5), rng.uniform(-360, 360, 500_000)])
     x = np.deg2rad(deg.astype(np.float32))
-    x = np.concatenate([x, np.array([0.0, -0.0, np.nan, np.float32(np.pi), np.float32(np.pi / 2), 0x1.f6a7a4p+1], np.float32)])
+    x = np.concatenate([x, np.array([0.0, -0.0, np.nan, np.float32(np.pi), np.float32(np.pi / 2), float.fromhex('0x1.f6a7a4p+1')], np.float32)])
     s, c = _device_sincos(x)
-    assert np.array_equal(s.view(np.uint32)[:-4], np.sin(x).view(np.uint32)[:-4])
-    assert np.array_equal(c.view(np.uint32)[:-4], np.cos(x).view(np.uint32)[:-4])
     ok = ~np.isnan(x)
+    assert np.array_equal(s.view(np.uint32)[ok], np.sin(x).view(np.uint32)[ok])
+    assert np.array_equal(c.view(np.uint32)[ok], np.cos(x).view(np.uint32)[ok])
     assert np.array_equal(s[ok], np.sin(x)[ok]) and np.array_equal(c[ok], np.cos(x)[ok])
     assert np.isnan(s[~ok]).all() and np.isnan(c[~ok]).all()
 
