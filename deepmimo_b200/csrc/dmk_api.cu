@@ -4,6 +4,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 
 #include "dmk_fd.cuh"
 #include "dmk_td.cuh"
@@ -154,6 +155,39 @@ int dmk_channels_fd(const dmk_desc* desc, const float* power_dbw, const float* p
     if (ksplit < 1) ksplit = 1;
     const long long grid = n_users * ksplit;
     if (grid > 0x7fffffffLL) return fail(DMK_ERR_INVALID_ARG, "grid too large: split the user range");
+    // Production path: affine subcarrier selection, no time axis, tables fit in shared memory.
+    const bool affine = (d.subc_step != 0) || (d.K == 1);
+    FastCfg cfg;
+    size_t fast_smem = 0;
+    {
+        const int pc = d.P > 0 ? d.P : 1;
+        auto take = [&](size_t bytes) { size_t o = fast_smem; fast_smem += (bytes + 15) & ~size_t(15); return (int)o; };
+        cfg.pcap = pc;
+        cfg.nA = (d.K + 15) / 16;
+        cfg.off_W  = take((size_t)pc * kTK * sizeof(float2));
+        cfg.off_A  = take((size_t)8 * pc * 8 * sizeof(float2));
+        cfg.off_tY = take((size_t)pc * d.bs0 * sizeof(float2));
+        cfg.off_tZ = take((size_t)pc * d.bs1 * sizeof(float2));
+        cfg.off_tR = take((size_t)pc * d.Mr * sizeof(float2));
+        cfg.off_wA = take((size_t)pc * cfg.nA * sizeof(float2));
+        cfg.off_wB = take((size_t)pc * 16 * sizeof(float2));
+    }
+    const bool use_fast = affine && !d.has_time_axis && fast_smem <= 110 * 1024 && !getenv("DMK_FORCE_TILE_KERNEL");
+    if (use_fast) {
+        if (d.K == 1 && d.subc_step == 0) d.subc_step = 1;
+        static size_t attr_fast = 0;
+        if (fast_smem > attr_fast) {
+            cudaError_t e = cudaFuncSetAttribute(fd_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(110 * 1024));
+            if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(fd_fast_kernel)");
+            attr_fast = 110 * 1024;
+        }
+        fd_fast_kernel<<<(unsigned)grid, kFdThreads, fast_smem, st>>>(d, cfg, (int)ksplit);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return cuda_fail(e, "fd_fast_kernel launch");
+        g_launches.fetch_add(1);
+        snprintf(g_kernel, sizeof(g_kernel), "fd_fast_kernel<64x128,ffma2> grid=%lld ksplit=%lld smem=%zu", grid, ksplit, fast_smem);
+        return DMK_OK;
+    }
     const size_t smem = (size_t)kMaxPaths * (kTK + kTM) * sizeof(float2);
     static bool attr_set = false;
     if (!attr_set) {
