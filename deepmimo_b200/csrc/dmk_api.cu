@@ -147,14 +147,6 @@ int dmk_channels_fd(const dmk_desc* desc, const float* power_dbw, const float* p
 
     cudaStream_t st = reinterpret_cast<cudaStream_t>(cuda_stream);
     const int ncols = d.K * d.T;
-    const int n_ct = (ncols + kTK - 1) / kTK;
-    // Few users: split each user's column tiles over several CTAs so the grid covers >= 4 waves.
-    const long long want = 4LL * 2 * device_sm_count();
-    long long ksplit = (want + n_users - 1) / n_users;
-    if (ksplit > n_ct) ksplit = n_ct;
-    if (ksplit < 1) ksplit = 1;
-    const long long grid = n_users * ksplit;
-    if (grid > 0x7fffffffLL) return fail(DMK_ERR_INVALID_ARG, "grid too large: split the user range");
     // Production path: affine subcarrier selection, no time axis, tables fit in shared memory.
     const bool affine = (d.subc_step != 0) || (d.K == 1);
     FastCfg cfg;
@@ -164,15 +156,28 @@ int dmk_channels_fd(const dmk_desc* desc, const float* power_dbw, const float* p
         auto take = [&](size_t bytes) { size_t o = fast_smem; fast_smem += (bytes + 15) & ~size_t(15); return (int)o; };
         cfg.pcap = pc;
         cfg.nA = (d.K + 15) / 16;
-        cfg.off_W  = take((size_t)pc * kTK * sizeof(float2));
-        cfg.off_A  = take((size_t)8 * pc * 8 * sizeof(float2));
+        cfg.off_W  = take((size_t)pc * kTKW * sizeof(float2));
+        cfg.off_A  = take((size_t)8 * pc * 8 * sizeof(float4));
         cfg.off_tY = take((size_t)pc * d.bs0 * sizeof(float2));
-        cfg.off_tZ = take((size_t)pc * d.bs1 * sizeof(float2));
-        cfg.off_tR = take((size_t)pc * d.Mr * sizeof(float2));
+        cfg.off_tQ = take((size_t)pc * d.Mr * d.bs1 * sizeof(float2));
         cfg.off_wA = take((size_t)pc * cfg.nA * sizeof(float2));
         cfg.off_wB = take((size_t)pc * 16 * sizeof(float2));
+        // q = umulhi(m, ceil(2^32/d)) == m / d exactly while m * d < 2^32; d == 1 is handled as mul = 0 (q = 0 is wrong),
+        // so the multiplier is only used for d > 1 and d == 1 takes mul = 0xffffffff + special case below.
+        cfg.mul_mt  = d.Mt  > 1 ? (unsigned)((0x100000000ULL + d.Mt - 1) / d.Mt) : 0u;
+        cfg.mul_bs0 = d.bs0 > 1 ? (unsigned)((0x100000000ULL + d.bs0 - 1) / d.bs0) : 0u;
     }
-    const bool use_fast = affine && !d.has_time_axis && fast_smem <= 110 * 1024 && !getenv("DMK_FORCE_TILE_KERNEL");
+    const bool div_ok = (unsigned long long)d.M * (unsigned long long)(d.Mt > d.bs0 ? d.Mt : d.bs0) < 0xffffffffULL;
+    const bool use_fast = affine && !d.has_time_axis && div_ok && fast_smem <= 110 * 1024 && !getenv("DMK_FORCE_TILE_KERNEL");
+    const int tile_w = use_fast ? kTKW : kTK;
+    const int n_ct = (ncols + tile_w - 1) / tile_w;
+    // Few users: split each user's column tiles over several CTAs so the grid covers >= 4 waves.
+    const long long want = 4LL * 2 * device_sm_count();
+    long long ksplit = (want + n_users - 1) / n_users;
+    if (ksplit > n_ct) ksplit = n_ct;
+    if (ksplit < 1) ksplit = 1;
+    const long long grid = n_users * ksplit;
+    if (grid > 0x7fffffffLL) return fail(DMK_ERR_INVALID_ARG, "grid too large: split the user range");
     if (use_fast) {
         if (d.K == 1 && d.subc_step == 0) d.subc_step = 1;
         static size_t attr_fast = 0;
@@ -185,7 +190,7 @@ int dmk_channels_fd(const dmk_desc* desc, const float* power_dbw, const float* p
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return cuda_fail(e, "fd_fast_kernel launch");
         g_launches.fetch_add(1);
-        snprintf(g_kernel, sizeof(g_kernel), "fd_fast_kernel<64x128,ffma2> grid=%lld ksplit=%lld smem=%zu", grid, ksplit, fast_smem);
+        snprintf(g_kernel, sizeof(g_kernel), "fd_fast_kernel<64x256,ffma2> grid=%lld ksplit=%lld smem=%zu", grid, ksplit, fast_smem);
         return DMK_OK;
     }
     const size_t smem = (size_t)kMaxPaths * (kTK + kTM) * sizeof(float2);

@@ -172,33 +172,39 @@ fd_tile_kernel(const DevDesc d, const int ksplit)
 // Same mathematics as fd_tile_kernel; what changes is how often transcendental work is redone and
 // how the FP32 pipe is fed:
 //   * per user, once: separable phasor tables in shared memory
-//        tY[p][y], tZ[p][z]  TX steering along the panel's y / z axes
-//        tR[p][r]            RX steering of element r with the path gain c_p folded in
+//        tY[p][y]            TX steering along the panel's y axis
+//        tQ[p][r*bs1 + z]    RX steering of element r  x  TX steering along z  x  path gain c_p
 //        wA[p][a], wB[p][b]  delay phasors: column q = 16a + b  ->  W[p,q] = wA[p][a] * wB[p][b]
-//     every table entry has its phase reduced in float64 (phasor_cycles); tiles are then products of
-//     2-3 unit-modulus float32 phasors (relative error ~1e-7 each).
-//   * W tile [np][128] rebuilt per column tile by the whole CTA (one complex multiply per entry);
-//     A sub-tile [np][8 rows] rebuilt per row tile by each warp for its own rows -> no CTA barrier
-//     inside the row loop, only __syncwarp.
-//   * inner loop on packed FP32: acc(re,im) += a.re * (w.re, w.im); acc += a.im * (-w.im, w.re)
-//     = 2 FFMA2 per complex MAC (SASS: scalar-broadcast A operand, .LO_HI swap on W), i.e. 64 FFMA2
-//     + 6 LDS.128 + 4 FADD issue slots per path for 128 FMA-pipe cycles.
+//     every table entry has its phase reduced in float64 (phasor_cycles); tile entries are products
+//     of 2-3 unit-modulus float32 phasors (relative error ~1e-7 each).
+//   * W tile [np][256] rebuilt per column tile by the whole CTA (one complex multiply per entry);
+//     A strip [np][8 rows] rebuilt per row tile by each warp for its own rows and used for two
+//     128-column passes -> no CTA barrier inside the row loop, only __syncwarp.
+//   * inner loop on packed FP32, 2 FFMA2 per complex MAC:
+//        acc(re,im) += (a.re, a.re) * (w.re, w.im);   acc += (-a.im, a.im) * (w.im, w.re)
+//     A entries are stored as (re, re, im, im) so that the second operand pair is a plain register
+//     pair with the per-half negate modifier and W needs only the free .LO_HI swap: per path
+//     64 FFMA2 + 10 LDS.128 issue slots for 128 FMA-pipe cycles, no fix-up instructions.
 // =================================================================================================
+constexpr int kTKW = 256;    // W tile width of the fast kernel (two passes of kTK columns)
+
 struct FastCfg {
-    int off_W, off_A, off_tY, off_tZ, off_tR, off_wA, off_wB;   // byte offsets into dynamic smem
-    int nA;                                                      // ceil(K / 16)
-    int pcap;                                                    // path capacity the layout was sized for
+    int off_W, off_A, off_tY, off_tQ, off_wA, off_wB;   // byte offsets into dynamic smem
+    int nA;                                              // ceil(K / 16)
+    int pcap;                                            // path capacity the layout was sized for
+    unsigned mul_mt, mul_bs0;                            // ceil(2^32 / Mt), ceil(2^32 / bs0): exact division for m < 2^32 / d
 };
+
+__device__ __forceinline__ float4 ldsA(const float4* p) { return *p; }
 
 __global__ void __launch_bounds__(kFdThreads, 2)
 fd_fast_kernel(const DevDesc d, const FastCfg cfg, const int ksplit)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    float2* sW = reinterpret_cast<float2*>(smem_raw + cfg.off_W);    // [pcap][kTK]
-    float2* sA = reinterpret_cast<float2*>(smem_raw + cfg.off_A);    // [8 warps][pcap][8]
+    float2* sW = reinterpret_cast<float2*>(smem_raw + cfg.off_W);    // [pcap][kTKW]
+    float4* sA = reinterpret_cast<float4*>(smem_raw + cfg.off_A);    // [8 warps][pcap][8] (re,re,im,im)
     float2* tY = reinterpret_cast<float2*>(smem_raw + cfg.off_tY);   // [pcap][bs0]
-    float2* tZ = reinterpret_cast<float2*>(smem_raw + cfg.off_tZ);   // [pcap][bs1]
-    float2* tR = reinterpret_cast<float2*>(smem_raw + cfg.off_tR);   // [pcap][Mr]
+    float2* tQ = reinterpret_cast<float2*>(smem_raw + cfg.off_tQ);   // [pcap][Mr*bs1]
     float2* wA = reinterpret_cast<float2*>(smem_raw + cfg.off_wA);   // [pcap][nA]
     float2* wB = reinterpret_cast<float2*>(smem_raw + cfg.off_wB);   // [pcap][16]
     __shared__ FdShared sh;
@@ -211,30 +217,28 @@ fd_fast_kernel(const DevDesc d, const FastCfg cfg, const int ksplit)
     __syncthreads();
     const int np = sh.np;
     const int ncols = d.K;
-    const int n_ct = (ncols + kTK - 1) / kTK;
+    const int n_ct = (ncols + kTKW - 1) / kTKW;
     const int n_rt = (d.M + kTM - 1) / kTM;
     float2* out_u = d.out + user * (long long)d.M * ncols;
     const bool vec_ok = ((ncols & 1) == 0) && ((reinterpret_cast<uintptr_t>(d.out) & 15) == 0);
+    const int nq = d.Mr * d.bs1;
 
     // ---- per-user tables (phase reduced in float64 for every entry)
     {
-        const int bs0 = d.bs0, bs1 = d.bs1, Mr = d.Mr, nA = cfg.nA;
+        const int bs0 = d.bs0, bs1 = d.bs1, nA = cfg.nA;
         for (int e = tid; e < np * bs0; e += kFdThreads) {
             const int p = e / bs0, y = e - p * bs0;
-            tY[e] = phasor_cycles((double)y * sh.u[0][p]);
+            tY[p * bs0 + y] = phasor_cycles((double)y * sh.u[0][p]);
         }
-        for (int e = tid; e < np * bs1; e += kFdThreads) {
-            const int p = e / bs1, z = e - p * bs1;
-            tZ[e] = phasor_cycles((double)z * sh.v[0][p]);
-        }
-        for (int e = tid; e < np * Mr; e += kFdThreads) {
-            const int p = e / Mr, r = e - p * Mr;
+        for (int e = tid; e < np * nq; e += kFdThreads) {
+            const int p = e / nq, q = e - p * nq;
+            const int r = q / bs1, z = q - r * bs1;
             const int yr = r % d.ue0, zr = r / d.ue0;
-            tR[e] = cmul(sh.c[p], phasor_cycles((double)yr * sh.u[1][p] + (double)zr * sh.v[1][p]));
+            tQ[p * nq + q] = cmul(sh.c[p], phasor_cycles((double)z * sh.v[0][p] + (double)yr * sh.u[1][p] + (double)zr * sh.v[1][p]));
         }
         for (int e = tid; e < np * nA; e += kFdThreads) {
             const int p = e / nA, a = e - p * nA;
-            wA[e] = phasor_cycles(-(sh.wcyc[p] * (double)(d.subc_start + d.subc_step * 16 * a)));
+            wA[p * nA + a] = phasor_cycles(-(sh.wcyc[p] * (double)(d.subc_start + d.subc_step * 16 * a)));
         }
         for (int e = tid; e < np * 16; e += kFdThreads) {
             const int p = e >> 4, b = e & 15;
@@ -242,90 +246,95 @@ fd_fast_kernel(const DevDesc d, const FastCfg cfg, const int ksplit)
         }
     }
 
-    float2* sAw = sA + warp * cfg.pcap * 8;
+    float4* sAw = sA + warp * cfg.pcap * 8;
     const int my_i = lane & 7;                   // row of the warp's 8-row strip this lane builds
     const int p_lane = lane >> 3;                // first path this lane builds (then +4, +8, ...)
 
     for (int ct = ks; ct < n_ct; ct += ksplit) {
-        const int col0 = ct * kTK;
+        const int col0 = ct * kTKW;
         __syncthreads();                          // tables ready (first pass) / W tile readers done
-        for (int e = tid; e < np * kTK; e += kFdThreads) {
-            const int p = e >> 7, c = e & (kTK - 1);
+        for (int e = tid; e < np * kTKW; e += kFdThreads) {
+            const int p = e >> 8, c = e & (kTKW - 1);
             const int col = col0 + c;
             float2 w = make_float2(0.f, 0.f);
             if (col < ncols) w = cmul(wA[p * cfg.nA + (col >> 4)], wB[p * 16 + (col & 15)]);
             sW[e] = w;
         }
         __syncthreads();
+        const int n_pass = (ncols - col0 > kTK) ? 2 : 1;
 
         for (int rt = 0; rt < n_rt; ++rt) {
             const int row0 = rt * kTM + warp * 8;
             if (row0 >= d.M) break;              // warp-uniform
-            // ---- this warp's A strip: [np][8 rows]
+            // ---- this warp's A strip: [np][8 rows], one complex multiply per entry
             __syncwarp();
             {
                 const int m = row0 + my_i;
                 const bool ok = m < d.M;
-                const int mm = ok ? m : 0;
-                const int r = mm / d.Mt, t = mm - r * d.Mt;
-                const int zt = t / d.bs0, yt = t - zt * d.bs0;
+                const unsigned mm = ok ? (unsigned)m : 0u;
+                const unsigned r = cfg.mul_mt ? __umulhi(mm, cfg.mul_mt) : mm;        // Mt == 1 -> r = m
+                const unsigned t = mm - r * (unsigned)d.Mt;
+                const unsigned zt = cfg.mul_bs0 ? __umulhi(t, cfg.mul_bs0) : t;       // bs0 == 1 -> z = t
+                const unsigned yt = t - zt * (unsigned)d.bs0;
+                const float2* q_ptr = tQ + (r * (unsigned)d.bs1 + zt);
+                const float2* y_ptr = tY + yt;
                 for (int p = p_lane; p < np; p += 4) {
-                    float2 a = cmul(cmul(tR[p * d.Mr + r], tY[p * d.bs0 + yt]), tZ[p * d.bs1 + zt]);
+                    float2 a = cmul(q_ptr[p * nq], y_ptr[p * d.bs0]);
                     if (!ok) a = make_float2(0.f, 0.f);
-                    sAw[p * 8 + my_i] = a;
+                    sAw[p * 8 + my_i] = make_float4(a.x, a.x, a.y, a.y);
                 }
             }
             __syncwarp();
 
-            float2 acc[8][4];
-            #pragma unroll
-            for (int i = 0; i < 8; ++i)
+            for (int pass = 0; pass < n_pass; ++pass) {
+                float2 acc[8][4];
                 #pragma unroll
-                for (int j = 0; j < 4; ++j) acc[i][j] = make_float2(0.f, 0.f);
+                for (int i = 0; i < 8; ++i)
+                    #pragma unroll
+                    for (int j = 0; j < 4; ++j) acc[i][j] = make_float2(0.f, 0.f);
 
-            const float4* wrow = reinterpret_cast<const float4*>(sW) + lane;
-            const float4* arow = reinterpret_cast<const float4*>(sAw);
-            #pragma unroll 2
-            for (int p = 0; p < np; ++p) {
-                const float4 w01 = wrow[p * (kTK / 2)];
-                const float4 w23 = wrow[p * (kTK / 2) + 32];
-                float2 w[4] = {make_float2(w01.x, w01.y), make_float2(w01.z, w01.w),
-                               make_float2(w23.x, w23.y), make_float2(w23.z, w23.w)};
-                float2 a[8];
-                #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const float4 t = arow[p * 4 + q];
-                    a[2 * q] = make_float2(t.x, t.y);
-                    a[2 * q + 1] = make_float2(t.z, t.w);
+                const float4* wrow = reinterpret_cast<const float4*>(sW) + pass * (kTK / 2) + lane;
+                #pragma unroll 1
+                for (int p = 0; p < np; ++p) {
+                    const float4 w01 = wrow[p * (kTKW / 2)];
+                    const float4 w23 = wrow[p * (kTKW / 2) + 32];
+                    const float2 w[4]  = {make_float2(w01.x, w01.y), make_float2(w01.z, w01.w),
+                                          make_float2(w23.x, w23.y), make_float2(w23.z, w23.w)};
+                    const float2 ws[4] = {make_float2(w01.y, w01.x), make_float2(w01.w, w01.z),
+                                          make_float2(w23.y, w23.x), make_float2(w23.w, w23.z)};
+                    #pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const float4 a = sAw[p * 8 + i];
+                        const float2 a1 = make_float2(a.x, a.y), a2 = make_float2(-a.z, a.w);
+                        #pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            acc[i][j] = __ffma2_rn(a1, w[j], acc[i][j]);
+                            acc[i][j] = __ffma2_rn(a2, ws[j], acc[i][j]);
+                        }
+                    }
                 }
-                #pragma unroll
-                for (int i = 0; i < 8; ++i)
-                    #pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        acc[i][j] = __ffma2_rn(make_float2(a[i].x, a[i].x), w[j], acc[i][j]);
-                #pragma unroll
-                for (int j = 0; j < 4; ++j) w[j] = make_float2(-w[j].y, w[j].x);       // j * w
-                #pragma unroll
-                for (int i = 0; i < 8; ++i)
-                    #pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        acc[i][j] = __ffma2_rn(make_float2(a[i].y, a[i].y), w[j], acc[i][j]);
-            }
 
-            #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int m = row0 + i;
-                if (m >= d.M) break;
-                float2* orow = out_u + (long long)m * ncols + col0;
-                #pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const int c = h * 64 + 2 * lane;
-                    if (vec_ok && col0 + c + 1 < ncols) {
-                        __stcs(reinterpret_cast<float4*>(orow + c),
-                               make_float4(acc[i][2 * h].x, acc[i][2 * h].y, acc[i][2 * h + 1].x, acc[i][2 * h + 1].y));
-                    } else {
-                        if (col0 + c < ncols)     __stcs(orow + c, acc[i][2 * h]);
-                        if (col0 + c + 1 < ncols) __stcs(orow + c + 1, acc[i][2 * h + 1]);
+                // ---- store: lane owns columns {2l, 2l+1} and {64+2l, 64+2l+1} of this 128-column pass
+                const int colp = col0 + pass * kTK;
+                float2* obase = out_u + (long long)row0 * ncols + colp + 2 * lane;
+                if (vec_ok && row0 + 8 <= d.M && colp + kTK <= ncols) {
+                    #pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        float4* o = reinterpret_cast<float4*>(obase + (long long)i * ncols);
+                        __stcs(o,      make_float4(acc[i][0].x, acc[i][0].y, acc[i][1].x, acc[i][1].y));
+                        __stcs(o + 32, make_float4(acc[i][2].x, acc[i][2].y, acc[i][3].x, acc[i][3].y));
+                    }
+                } else {
+                    #pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        if (row0 + i >= d.M) break;
+                        float2* orow = obase + (long long)i * ncols;
+                        #pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            const int c = colp + h * 64 + 2 * lane;
+                            if (c < ncols)     __stcs(orow + h * 64, acc[i][2 * h]);
+                            if (c + 1 < ncols) __stcs(orow + h * 64 + 1, acc[i][2 * h + 1]);
+                        }
                     }
                 }
             }
