@@ -1,0 +1,50 @@
+"""oracle/np_trig_emul.c against NumPy's float32 sin/cos on this host (rounding point R2).
+The exhaustive run over all float32 in [-2pi, 2pi] is oracle/verify_np_trig.py (minutes); this is the
+strided version that fits the CPU suite."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SO = os.path.join(ROOT, "oracle", "_build", "libnptrig.so")
+
+
+@pytest.fixture(scope="module")
+def lib():
+    if not os.path.exists(SO):
+        subprocess.run(["make", "-C", os.path.join(ROOT, "oracle")], check=True, capture_output=True)
+    lib = ctypes.CDLL(SO)
+    for f in (lib.np_sinf_emul_array, lib.np_cosf_emul_array):
+        f.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t]
+    return lib
+
+
+def _both(lib, x):
+    s = np.empty_like(x); c = np.empty_like(x)
+    lib.np_sinf_emul_array(x.ctypes.data, s.ctypes.data, x.size)
+    lib.np_cosf_emul_array(x.ctypes.data, c.ctypes.data, x.size)
+    return s, c
+
+
+def test_strided_sweep_bit_exact(lib):
+    hi = int(np.float32(2 * np.pi).view(np.uint32)) + 1
+    for sign in (0, 0x80000000):
+        bits = np.arange(0, hi, 251, dtype=np.uint32) | np.uint32(sign)
+        x = bits.view(np.float32)
+        s, c = _both(lib, x)
+        assert np.array_equal(s.view(np.uint32), np.sin(x).view(np.uint32))
+        assert np.array_equal(c.view(np.uint32), np.cos(x).view(np.uint32))
+
+
+def test_degree_grid_and_fused_quadrant_case(lib):
+    deg = np.concatenate([np.arange(0, 180.25, 0.25), np.random.default_rng(5).uniform(0, 180, 1_000_000)]).astype(np.float32)
+    x = np.deg2rad(deg)
+    x = np.concatenate([x, np.array([float.fromhex("0x1.f6a7a4p+1")], np.float32)])   # needs the fused q = fma(x, 2/pi, magic)
+    s, c = _both(lib, x)
+    assert np.array_equal(s.view(np.uint32), np.sin(x).view(np.uint32))
+    assert np.array_equal(c.view(np.uint32), np.cos(x).view(np.uint32))
+    s, c = _both(lib, np.array([np.nan], np.float32))
+    assert np.isnan(s[0]) and np.isnan(c[0])
