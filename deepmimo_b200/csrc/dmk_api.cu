@@ -7,6 +7,7 @@
 #include <cstdlib>
 
 #include "dmk_fd.cuh"
+#include "dmk_fd_tc.cuh"
 #include "dmk_td.cuh"
 
 namespace {
@@ -168,8 +169,37 @@ int dmk_channels_fd(const dmk_desc* desc, const float* power_dbw, const float* p
         cfg.mul_bs0 = d.bs0 > 1 ? (unsigned)((0x100000000ULL + d.bs0 - 1) / d.bs0) : 0u;
     }
     const bool div_ok = (unsigned long long)d.M * (unsigned long long)(d.Mt > d.bs0 ? d.Mt : d.bs0) < 0xffffffffULL;
-    const bool use_fast = affine && !d.has_time_axis && div_ok && fast_smem <= 110 * 1024 && !getenv("DMK_FORCE_TILE_KERNEL");
-    const int tile_w = use_fast ? kTKW : kTK;
+    // Kernel choice: tensor-core (3xTF32 tcgen05) > packed-FP32 CUDA-core > generic tile kernel.
+    // DMK_FD_KERNEL=tc|ffma|tile overrides it (parity tests and A/B timing use this).
+    const char* force = getenv("DMK_FD_KERNEL");
+    const bool want_tile = force && !strcmp(force, "tile");
+    const bool want_ffma = force && !strcmp(force, "ffma");
+    TcCfg tcfg;
+    size_t tc_smem = 1024;                                   // slack for the 1024-byte alignment of the operand tiles
+    {
+        const int pc = d.P > 0 ? d.P : 1;
+        size_t off = 0;
+        auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 15) & ~size_t(15); return (int)o; };
+        tcfg.pcap = pc;
+        tcfg.nA = (d.K + 15) / 16;
+        tcfg.mtile = d.M > 64 ? 128 : 64;
+        tcfg.off_A  = take(2 * 128 * 128);                   // A_hi, A_lo (also the epilogue staging)
+        tcfg.off_B  = take(2 * kTcN * 128);                  // B_hi, B_lo
+        tcfg.sY = d.bs0 | 1; tcfg.sQ = (d.Mr * d.bs1) | 1; tcfg.sA = tcfg.nA | 1; tcfg.sB = 17;   // odd strides: no bank conflicts across paths
+        tcfg.off_tY = take((size_t)pc * tcfg.sY * sizeof(float2));
+        tcfg.off_tQ = take((size_t)pc * tcfg.sQ * sizeof(float2));
+        tcfg.off_wA = take((size_t)pc * tcfg.sA * sizeof(float2));
+        tcfg.off_wB = take((size_t)pc * tcfg.sB * sizeof(float2));
+        tcfg.mul_mt = cfg.mul_mt; tcfg.mul_bs0 = cfg.mul_bs0;
+        tc_smem += off;
+    }
+    // Shapes with fewer than 128 rows per user leave the 128-row tensor tile half empty and rebuild B for every
+    // tile: the packed-FP32 kernel is faster there (profiles/README.md); DMK_FD_KERNEL=tc still forces it.
+    const bool want_tc = force && !strcmp(force, "tc");
+    const bool use_tc = affine && !d.has_time_axis && div_ok && (d.K % (kTcN / 2) == 0) && tc_smem <= 112 * 1024 &&
+                        !want_tile && !want_ffma && (d.M >= 128 || want_tc);
+    const bool use_fast = !use_tc && affine && !d.has_time_axis && div_ok && fast_smem <= 110 * 1024 && !want_tile;
+    const int tile_w = use_tc ? (kTcN / 2) : (use_fast ? kTKW : kTK);
     const int n_ct = (ncols + tile_w - 1) / tile_w;
     // Few users: split each user's column tiles over several CTAs so the grid covers >= 4 waves.
     const long long want = 4LL * 2 * device_sm_count();
@@ -178,6 +208,21 @@ int dmk_channels_fd(const dmk_desc* desc, const float* power_dbw, const float* p
     if (ksplit < 1) ksplit = 1;
     const long long grid = n_users * ksplit;
     if (grid > 0x7fffffffLL) return fail(DMK_ERR_INVALID_ARG, "grid too large: split the user range");
+    if (use_tc) {
+        if (d.K == 1 && d.subc_step == 0) d.subc_step = 1;
+        static bool attr_tc = false;
+        if (!attr_tc) {
+            cudaError_t e = cudaFuncSetAttribute(fd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(112 * 1024));
+            if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(fd_tc_kernel)");
+            attr_tc = true;
+        }
+        fd_tc_kernel<<<(unsigned)grid, kTcThreads, tc_smem, st>>>(d, tcfg, (int)ksplit);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return cuda_fail(e, "fd_tc_kernel launch");
+        g_launches.fetch_add(1);
+        snprintf(g_kernel, sizeof(g_kernel), "fd_tc_kernel<%dx128,3xtf32> grid=%lld ksplit=%lld smem=%zu", tcfg.mtile, grid, ksplit, tc_smem);
+        return DMK_OK;
+    }
     if (use_fast) {
         if (d.K == 1 && d.subc_step == 0) d.subc_step = 1;
         static size_t attr_fast = 0;

@@ -1,0 +1,320 @@
+// dmk_fd_tc.cuh -- FD channel kernel on the 5th-generation tensor cores (tcgen05, kind::tf32, TMEM).
+//
+// Why: with P ~ 12 contributing paths per user the FP32 FMA pipe, not HBM, bounds the CUDA-core kernel
+// (profiles/r01_ncu_fd_fast_kernel_*.txt: top stall math_pipe_throttle, DRAM = algorithmic bytes).  The
+// rank-P sum is a small-K complex GEMM per user,
+//     H[m, k] = sum_p A[m,p] W[p,k]           A: M x P,  W: P x K   (complex)
+// written as one real GEMM whose output columns are already the interleaved complex64 layout:
+//     D[m, 2k+s] = sum_{p,e} A'[m, 2p+e] B'[2k+s, 2p+e]
+//     A'[m,2p] = Re A, A'[m,2p+1] = Im A;  B'[2k,2p] = Re W, B'[2k,2p+1] = -Im W, B'[2k+1,2p] = Im W, B'[2k+1,2p+1] = Re W.
+// TF32 keeps 11 significant bits, so every operand is split x = hi + lo (hi = tf32(x), lo = tf32(x - hi)) and
+// D = A_hi B_hi + A_hi B_lo + A_lo B_hi accumulates in FP32 in tensor memory: relative error ~2^-21 per term
+// (measured per-user relative Frobenius error vs the reference: see tests), far inside the 1e-5 budget.
+//
+// Structure (one CTA = one user or a slice of its column tiles, 256 threads, 2 CTAs per SM):
+//   warp 0: per-path prologue (float64) -> compacted path records;  all threads: separable phasor tables
+//   per 128-float (64-subcarrier) column tile, per row tile of 128 (or 64) rows, per chunk of 16 paths:
+//     all threads write A_hi/A_lo (rows x 32 tf32) and B_hi/B_lo (128 x 32 tf32) straight into shared memory
+//     in the K-major SWIZZLE_128B UMMA layout (one complex multiply of table entries + split per entry);
+//     fence.proxy.async; barrier; one thread issues 3 x ksteps tcgen05.mma (M x 128 x 8) and commits to an
+//     mbarrier; everyone waits on it.
+//   epilogue: every warp pulls its TMEM quarter with tcgen05.ld 32x32b.x32, stages it through (the now free)
+//   A buffer with an XOR swizzle and writes 128-byte row segments with streaming 16-byte stores.
+// The tensor pipe needs ~25-50 % of the HBM time of a tile, the operand generation a few hundred issue
+// cycles, so the kernel is bound by the output write; the second resident CTA fills the bubbles of the
+// synchronous phases.
+#pragma once
+#include "dmk_fd.cuh"
+
+namespace dmk {
+
+constexpr int kTcThreads = 256;
+constexpr int kTcN       = 128;   // real output columns per tile = 64 subcarriers
+constexpr int kTcChunk   = 16;    // paths per K chunk (32 tf32 = one 128-byte swizzle row)
+
+struct TcCfg {
+    int off_A, off_B, off_tY, off_tQ, off_wA, off_wB;   // byte offsets from the 1024-aligned base
+    int nA, pcap, mtile;                                 // mtile = 128 or 64 (tcgen05 M)
+    int sY, sQ, sA, sB;                                  // per-path table strides (float2 units), odd -> lanes that differ
+                                                         // in the path index hit different shared-memory banks
+    unsigned mul_mt, mul_bs0;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ uint64_t umma_desc_kmajor_sw128(uint32_t saddr)
+{
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);      // start address >> 4
+    d |= (uint64_t)1 << 16;                       // leading byte offset (ignored for swizzled K-major)
+    d |= (uint64_t)(1024 >> 4) << 32;             // stride byte offset: 8 rows x 128 B
+    d |= (uint64_t)1 << 46;                       // descriptor version (sm_100)
+    d |= (uint64_t)2 << 61;                       // SWIZZLE_128B
+    return d;
+}
+
+__device__ __forceinline__ uint32_t tf32_rna(float x)
+{
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return r;
+}
+
+// byte offset of element pair (row, path slot j: k = 2j, 2j+1) in a K-major SWIZZLE_128B tile of 32 tf32 per row
+__device__ __forceinline__ int sw128_pair_offset(int row, int j)
+{
+    return (row >> 3) * 1024 + (row & 7) * 128 + ((((j >> 1) ^ (row & 7)) & 7) << 4) + (j & 1) * 8;
+}
+
+// x = hi + lo with hi = tf32(x) (round to nearest, ties away: integer add on the sign-magnitude pattern) and
+// lo = x - hi exact in FP32; the tensor core reads the top 19 bits of lo (|lo| <= 2^-11 |x| -> error <= 2^-22 |x|).
+__device__ __forceinline__ void st_split_pair(unsigned char* hi, unsigned char* lo, int off, float x, float y)
+{
+    const uint32_t xh = (__float_as_uint(x) + 0x1000u) & 0xffffe000u;
+    const uint32_t yh = (__float_as_uint(y) + 0x1000u) & 0xffffe000u;
+    const float xl = x - __uint_as_float(xh), yl = y - __uint_as_float(yh);
+    *reinterpret_cast<uint2*>(hi + off) = make_uint2(xh, yh);
+    *reinterpret_cast<float2*>(lo + off) = make_float2(xl, yl);
+}
+
+__device__ __forceinline__ void st_split_quad(unsigned char* hi, unsigned char* lo, int off, float x0, float y0, float x1, float y1)
+{
+    const uint32_t a = (__float_as_uint(x0) + 0x1000u) & 0xffffe000u, b = (__float_as_uint(y0) + 0x1000u) & 0xffffe000u;
+    const uint32_t c = (__float_as_uint(x1) + 0x1000u) & 0xffffe000u, e = (__float_as_uint(y1) + 0x1000u) & 0xffffe000u;
+    *reinterpret_cast<uint4*>(hi + off) = make_uint4(a, b, c, e);
+    *reinterpret_cast<float4*>(lo + off) = make_float4(x0 - __uint_as_float(a), y0 - __uint_as_float(b),
+                                                        x1 - __uint_as_float(c), y1 - __uint_as_float(e));
+}
+
+__device__ __forceinline__ void mbar_wait_parity(uint32_t bar, uint32_t parity)
+{
+    uint32_t ok = 0;
+    for (unsigned spins = 0; !ok; ++spins) {
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+        if (spins > (1u << 26)) __trap();     // a lost commit must fail loudly, never hang the device
+    }
+}
+
+__global__ void __launch_bounds__(kTcThreads, 2)
+fd_tc_kernel(const DevDesc d, const TcCfg cfg, const int ksplit)
+{
+    extern __shared__ unsigned char smem_raw[];
+    __shared__ FdShared sh;
+    __shared__ uint64_t mbar;
+    __shared__ uint32_t tmem_base_s;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const long long user = blockIdx.x / ksplit;
+    const int ks = blockIdx.x % ksplit;
+
+    unsigned char* sm = smem_raw + (((smem_u32(smem_raw) + 1023u) & ~1023u) - smem_u32(smem_raw));
+    unsigned char* sAhi = sm + cfg.off_A;                    // [mtile rows][128 B]   (also epilogue staging)
+    unsigned char* sAlo = sAhi + 128 * 128;
+    unsigned char* sBhi = sm + cfg.off_B;                    // [128 rows][128 B]
+    unsigned char* sBlo = sBhi + kTcN * 128;
+    float2* tY = reinterpret_cast<float2*>(sm + cfg.off_tY);
+    float2* tQ = reinterpret_cast<float2*>(sm + cfg.off_tQ);
+    float2* wA = reinterpret_cast<float2*>(sm + cfg.off_wA);
+    float2* wB = reinterpret_cast<float2*>(sm + cfg.off_wB);
+
+    if (warp == 0) fd_warp_prologue(d, user, sh, ks == 0);
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(&tmem_base_s)), "r"(kTcN));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    if (tid == 64) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&mbar)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = tmem_base_s;
+    const int np = sh.np;
+    const int K = d.K, M = d.M;
+    const int mtile = cfg.mtile;
+    const int n_ct = K / (kTcN / 2);
+    const int n_rt = (M + mtile - 1) / mtile;
+    float* out_u = reinterpret_cast<float*>(d.out + user * (long long)M * K);
+    const long long pitch = 2LL * K;                                  // floats per output row
+    const int nq = d.Mr * d.bs1;
+
+    if (np == 0) {
+        // users without contributing paths: zeros (channel.py:257,:269-271), coalesced
+        float4* o = reinterpret_cast<float4*>(out_u);
+        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+        const int c4 = tid & 31, r0 = tid >> 5;                       // 32 float4 per row of a column tile, 8 rows per pass
+        for (int ct = ks; ct < n_ct; ct += ksplit) {
+            float4* ot = o + ct * (kTcN / 4) + c4;
+            for (int m = r0; m < M; m += kTcThreads / 32) __stcs(ot + (long long)m * (pitch / 4), z);
+        }
+    } else {
+        // ---- per-user tables (phase reduced in float64 for every entry)
+        {
+            const int bs0 = d.bs0, bs1 = d.bs1, nA = cfg.nA;
+            for (int e = tid; e < np * bs0; e += kTcThreads) {
+                const int p = e / bs0, y = e - p * bs0;
+                tY[p * cfg.sY + y] = phasor_cycles((double)y * sh.u[0][p]);
+            }
+            for (int e = tid; e < np * nq; e += kTcThreads) {
+                const int p = e / nq, q = e - p * nq;
+                const int r = q / bs1, z = q - r * bs1;
+                const int yr = r % d.ue0, zr = r / d.ue0;
+                tQ[p * cfg.sQ + q] = cmul(sh.c[p], phasor_cycles((double)z * sh.v[0][p] + (double)yr * sh.u[1][p] + (double)zr * sh.v[1][p]));
+            }
+            for (int e = tid; e < np * nA; e += kTcThreads) {
+                const int p = e / nA, a = e - p * nA;
+                wA[p * cfg.sA + a] = phasor_cycles(-(sh.wcyc[p] * (double)(d.subc_start + d.subc_step * 16 * a)));
+            }
+            for (int e = tid; e < np * 16; e += kTcThreads) {
+                const int p = e >> 4, b = e & 15;
+                wB[p * cfg.sB + b] = phasor_cycles(-(sh.wcyc[p] * (double)(d.subc_step * b)));
+            }
+        }
+        __syncthreads();
+
+        const int nchunk = (np + kTcChunk - 1) / kTcChunk;
+        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kTcN >> 3) << 17) | ((uint32_t)(mtile >> 4) << 24);
+        const uint64_t dAhi = umma_desc_kmajor_sw128(smem_u32(sAhi)), dAlo = umma_desc_kmajor_sw128(smem_u32(sAlo));
+        const uint64_t dBhi = umma_desc_kmajor_sw128(smem_u32(sBhi)), dBlo = umma_desc_kmajor_sw128(smem_u32(sBlo));
+        uint32_t phase = 0;
+        // Operand builders: a thread owns one row (A) / one subcarrier (B) and a group of consecutive path slots, so
+        // the row -> (rx element, z, y) decomposition is done once per tile, table reads of neighbouring lanes are
+        // consecutive or broadcast, and two path slots (re,im,re,im) go out as one conflict-free 16-byte store.
+        const int a_row  = tid & (mtile - 1);                       // row of the tile this thread fills
+        const int a_grp  = tid / mtile;                             // 0..(256/mtile - 1)
+        const int a_nsl  = kTcChunk / (kTcThreads / mtile);         // slots per thread: 8 (mtile 128) or 4 (mtile 64)
+        const int a_off0 = (a_row >> 3) * 1024 + (a_row & 7) * 128;
+        const int b_col  = tid & 63;                                // subcarrier of the tile this thread fills
+        const int b_grp  = tid >> 6;                                // 0..3 -> slots 4*b_grp .. +3
+        const int b_off0 = ((2 * b_col) >> 3) * 1024 + ((2 * b_col) & 7) * 128;      // row 2*b_col; row 2*b_col+1 is +128 bytes
+
+        for (int ct = ks; ct < n_ct; ct += ksplit) {
+            const int col0 = ct * (kTcN / 2);        // first subcarrier (complex column) of the tile
+            bool b_valid = false;                     // B tile of chunk 0 currently in smem (single-chunk users reuse it)
+            for (int rt = 0; rt < n_rt; ++rt) {
+                const int row0 = rt * mtile;
+                // row decomposition of this thread's row (once per tile)
+                const int am = row0 + a_row;
+                const bool a_ok = am < M;
+                int a_q = 0, a_y = 0;
+                if (a_ok) {
+                    const unsigned mm = (unsigned)am;
+                    const unsigned rr = cfg.mul_mt ? __umulhi(mm, cfg.mul_mt) : mm;
+                    const unsigned t = mm - rr * (unsigned)d.Mt;
+                    const unsigned zt = cfg.mul_bs0 ? __umulhi(t, cfg.mul_bs0) : t;
+                    a_y = (int)(t - zt * (unsigned)d.bs0);
+                    a_q = (int)(rr * (unsigned)d.bs1 + zt);
+                }
+                for (int ch = 0; ch < nchunk; ++ch) {
+                    // ---- A_hi / A_lo
+                    {
+                        const int j0 = a_grp * a_nsl;
+                        const float2* tQp = tQ + (ch * kTcChunk + j0) * cfg.sQ + a_q;
+                        const float2* tYp = tY + (ch * kTcChunk + j0) * cfg.sY + a_y;
+                        const int pmax = np - ch * kTcChunk - j0;                      // slots < pmax hold a path
+                        #pragma unroll 2
+                        for (int jj = 0; jj < a_nsl; jj += 2) {
+                            float2 a0 = make_float2(0.f, 0.f), a1 = make_float2(0.f, 0.f);
+                            if (a_ok && jj < pmax)     a0 = cmul(tQp[jj * cfg.sQ], tYp[jj * cfg.sY]);
+                            if (a_ok && jj + 1 < pmax) a1 = cmul(tQp[(jj + 1) * cfg.sQ], tYp[(jj + 1) * cfg.sY]);
+                            const int off = a_off0 + (((((j0 + jj) >> 1) ^ (a_row & 7)) & 7) << 4);
+                            st_split_quad(sAhi, sAlo, off, a0.x, a0.y, a1.x, a1.y);
+                        }
+                    }
+                    // ---- B_hi / B_lo (rows 2c -> Re H, 2c+1 -> Im H)
+                    if (!(b_valid && nchunk == 1)) {
+                        const int j0 = b_grp * 4;
+                        const int col = col0 + b_col;
+                        const float2* wAp = wA + (ch * kTcChunk + j0) * cfg.sA + (col >> 4);
+                        const float2* wBp = wB + (ch * kTcChunk + j0) * cfg.sB + (col & 15);
+                        const int pmax = np - ch * kTcChunk - j0;
+                        #pragma unroll
+                        for (int jj = 0; jj < 4; jj += 2) {
+                            float2 w0 = make_float2(0.f, 0.f), w1 = make_float2(0.f, 0.f);
+                            if (jj < pmax)     w0 = cmul(wAp[jj * cfg.sA], wBp[jj * cfg.sB]);
+                            if (jj + 1 < pmax) w1 = cmul(wAp[(jj + 1) * cfg.sA], wBp[(jj + 1) * cfg.sB]);
+                            const int sl = (j0 + jj) >> 1;
+                            const int r0 = (2 * b_col) & 7;
+                            st_split_quad(sBhi, sBlo, b_off0 + (((sl ^ r0) & 7) << 4), w0.x, -w0.y, w1.x, -w1.y);
+                            st_split_quad(sBhi, sBlo, b_off0 + 128 + (((sl ^ (r0 + 1)) & 7) << 4), w0.y, w0.x, w1.y, w1.x);
+                        }
+                    }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    __syncthreads();
+                    if (tid == 0) {
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        const int npc = min(kTcChunk, np - ch * kTcChunk);
+                        const int ksteps = (2 * npc + 7) >> 3;
+                        #pragma unroll 1
+                        for (int s = 0; s < 3; ++s) {
+                            const uint64_t da = (s == 2) ? dAlo : dAhi;
+                            const uint64_t db = (s == 1) ? dBlo : dBhi;
+                            #pragma unroll 1
+                            for (int kk = 0; kk < ksteps; ++kk) {
+                                const uint32_t accum = (ch | s | kk) != 0;
+                                asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+                                             "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}"
+                                             :: "r"(tmem_base), "l"(da + 2 * kk), "l"(db + 2 * kk), "r"(idesc), "r"(accum) : "memory");
+                            }
+                        }
+                        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
+                                     :: "r"(smem_u32(&mbar)) : "memory");
+                    }
+                    mbar_wait_parity(smem_u32(&mbar), phase);
+                    phase ^= 1;
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                }
+                b_valid = true;
+
+                // ---- epilogue: TMEM -> registers -> swizzled staging (A buffer) -> 128-byte row segments
+                {
+                    const int q = warp & 3, h = warp >> 2;
+                    unsigned char* stage = sAhi + warp * 4096;              // 32 rows x 128 B per warp
+                    #pragma unroll 1
+                    for (int c = 0; c < 2; ++c) {
+                        const int colf = 64 * h + 32 * c;                   // float column inside the tile
+                        uint32_t v[32];
+                        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)colf;
+                        asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                                     "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+                                     : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                                       "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                                       "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                                       "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                                     : "r"(taddr));
+                        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                        __syncwarp();                                        // previous pass's readers are done with the staging rows
+                        #pragma unroll
+                        for (int i = 0; i < 8; ++i)
+                            *reinterpret_cast<uint4*>(stage + lane * 128 + (((i ^ lane) & 7) << 4)) =
+                                make_uint4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+                        __syncwarp();
+                        // lanes 8r'..8r'+7 write one 128-byte segment of one row; 4 rows per instruction
+                        #pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const int rl = 4 * i + (lane >> 3);             // TMEM lane of this warp's quarter
+                            const int jj = lane & 7;
+                            const uint4 val = *reinterpret_cast<const uint4*>(stage + rl * 128 + (((jj ^ rl) & 7) << 4));
+                            // M = 128: lane = row.  M = 64: rows 16q .. 16q+15 live in lanes 0..15 of quarter q.
+                            const int rt_row = (mtile == 128) ? (q * 32 + rl) : (rl < 16 ? q * 16 + rl : -1);
+                            const int m = row0 + rt_row;
+                            if (rt_row >= 0 && m < M)
+                                __stcs(reinterpret_cast<uint4*>(out_u + (long long)m * pitch + ct * kTcN + colf) + jj, val);
+                        }
+                    }
+                }
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncthreads();                      // staging (A buffer) and TMEM are free for the next tile
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            }
+        }
+    }
+
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"(kTcN));
+}
+
+}  // namespace dmk

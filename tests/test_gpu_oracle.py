@@ -204,3 +204,24 @@ def test_byproduct_caches_match_oracle_functions():
     np.testing.assert_allclose(got_ph[ok], ph[ok], rtol=0, atol=1e-12)
     o = orc.compute_channels(s.data, **oracle_kwargs_from_params(s.params, s.bs_fov, s.ue_fov))
     assert np.array_equal(ds["_fov_mask"], o["fov_mask"])
+
+
+@pytest.mark.parametrize("cfg,n", [(2, 12), (3, 48), (5, 64), (1, 500)])
+def test_fd_kernel_variants_agree_with_oracle(cfg, n, monkeypatch):
+    """The three FD kernels (tcgen05 3xTF32, packed-FP32 CUDA-core, generic tile) are selected by
+    DMK_FD_KERNEL; each must meet the 1e-5 bar on its own and write identical masks."""
+    import deepmimo_b200 as dmb
+    from deepmimo_b200.synth import scenario
+    from oracle import channel_oracle as orc
+    s = scenario(cfg, n)
+    o = orc.compute_channels(s.data, **oracle_kwargs_from_params(s.params, s.bs_fov, s.ue_fov))
+    seen = set()
+    for variant in ("tc", "ffma", "tile"):
+        monkeypatch.setenv("DMK_FD_KERNEL", variant)
+        ds = make_dataset(dmb, s, s.bs_fov, s.ue_fov)
+        H, info = ds.compute_channels(dmb.ChannelGenParameters(s.params), return_info=True, warn=False)
+        err = assert_channels_close(H, o["H"], what=f"{s.name}/{variant}")
+        _check_masks(info, o, True)
+        seen.add(info.kernel.split("<")[0])
+        print(f"{s.name} {variant}: {info.kernel.split(' ')[0]} max rel. Frobenius {err:.2e}")
+    assert {"fd_tc_kernel", "fd_fast_kernel", "fd_tile_kernel"} <= seen
