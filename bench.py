@@ -295,6 +295,11 @@ def cpu_baseline(s, workload, cores=1):
 
 
 def gpu_main(args):
+    # stdout must carry exactly one JSON line: libraries (NCCL prints its version banner) write to fd 1, so
+    # fd 1 is pointed at stderr for the run and the JSON line goes to the saved descriptor.
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     import torch
     import torch.distributed as dist
     rank = int(os.environ.get("RANK", 0))
@@ -385,7 +390,7 @@ def gpu_main(args):
             line["cpu_baseline"] = cpu_baseline(res["scenario"], args.workload)
         if extra:
             line["workloads"] = extra
-        print(json.dumps(line), flush=True)
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
