@@ -182,7 +182,7 @@ int dmk_channels_fd(const dmk_desc* desc, const float* power_dbw, const float* p
         auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 15) & ~size_t(15); return (int)o; };
         tcfg.pcap = pc;
         tcfg.nA = (d.K + 15) / 16;
-        tcfg.mtile = d.M > 64 ? 128 : 64;
+        tcfg.mtile = d.M >= 128 ? 128 : (d.M > 32 ? 64 : (d.M > 16 ? 32 : 16));   // antenna rows per tile = tcgen05 N
         tcfg.off_A  = take(2 * 128 * 128);                   // A_hi, A_lo (also the epilogue staging)
         tcfg.off_B  = take(2 * kTcN * 128);                  // B_hi, B_lo
         tcfg.sY = d.bs0 | 1; tcfg.sQ = (d.Mr * d.bs1) | 1; tcfg.sA = tcfg.nA | 1; tcfg.sB = 17;   // odd strides: no bank conflicts across paths

@@ -4,9 +4,13 @@
 // (profiles/r01_ncu_fd_fast_kernel_*.txt: top stall math_pipe_throttle, DRAM = algorithmic bytes).  The
 // rank-P sum is a small-K complex GEMM per user,
 //     H[m, k] = sum_p A[m,p] W[p,k]           A: M x P,  W: P x K   (complex)
-// written as one real GEMM whose output columns are already the interleaved complex64 layout:
-//     D[m, 2k+s] = sum_{p,e} A'[m, 2p+e] B'[2k+s, 2p+e]
+// written as one real GEMM whose rows are already the interleaved complex64 layout of a 64-subcarrier segment:
+//     Dt[2k+s, m] = sum_{p,e} B'[2k+s, 2p+e] A'[m, 2p+e]        (the tensor core computes the TRANSPOSED tile)
 //     A'[m,2p] = Re A, A'[m,2p+1] = Im A;  B'[2k,2p] = Re W, B'[2k,2p+1] = -Im W, B'[2k+1,2p] = Im W, B'[2k+1,2p+1] = Re W.
+// TMEM lanes = the 128 floats (re/im of 64 subcarriers) of an output row segment, TMEM columns = antenna rows m:
+// register i of a tcgen05.ld holds, across the 32 lanes of a warp, 32 consecutive floats of output row m_i, so every
+// warp-wide 4-byte store is one full 128-byte line -- no shared-memory staging -- and the MMA N dimension adapts to
+// small arrays (M = 64 -> N = 64, M = 8 -> N = 16) without idle tensor rows.
 // TF32 keeps 11 significant bits, so every operand is split x = hi + lo (hi = tf32(x), lo = tf32(x - hi)) and
 // D = A_hi B_hi + A_hi B_lo + A_lo B_hi accumulates in FP32 in tensor memory: relative error ~2^-21 per term
 // (measured per-user relative Frobenius error vs the reference: see tests), far inside the 1e-5 budget.
@@ -18,11 +22,11 @@
 //     in the K-major SWIZZLE_128B UMMA layout (one complex multiply of table entries + split per entry);
 //     fence.proxy.async; barrier; one thread issues 3 x ksteps tcgen05.mma (M x 128 x 8) and commits to an
 //     mbarrier; everyone waits on it.
-//   epilogue: every warp pulls its TMEM quarter with tcgen05.ld 32x32b.x32, stages it through (the now free)
-//   A buffer with an XOR swizzle and writes 128-byte row segments with streaming 16-byte stores.
+//   epilogue: every warp pulls its TMEM lane quarter with tcgen05.ld 32x32b.xN and writes each register as one
+//   128-byte row segment (streaming stores).  The accumulator is double-buffered in TMEM (2 x 128 columns): the
+//   epilogue of tile t-1 runs while the tensor core works on tile t.
 // The tensor pipe needs ~25-50 % of the HBM time of a tile, the operand generation a few hundred issue
-// cycles, so the kernel is bound by the output write; the second resident CTA fills the bubbles of the
-// synchronous phases.
+// cycles, so the kernel is bound by the output write; the second resident CTA fills the remaining bubbles.
 #pragma once
 #include "dmk_fd.cuh"
 
@@ -34,7 +38,7 @@ constexpr int kTcChunk   = 16;    // paths per K chunk (32 tf32 = one 128-byte s
 
 struct TcCfg {
     int off_A, off_B, off_tY, off_tQ, off_wA, off_wB;   // byte offsets from the 1024-aligned base
-    int nA, pcap, mtile;                                 // mtile = 128 or 64 (tcgen05 M)
+    int nA, pcap, mtile;                                 // mtile = antenna rows per tile = tcgen05 N: 16, 32, 64 or 128
     int sY, sQ, sA, sB;                                  // per-path table strides (float2 units), odd -> lanes that differ
                                                          // in the path index hit different shared-memory banks
     unsigned mul_mt, mul_bs0;
@@ -96,6 +100,66 @@ __device__ __forceinline__ void mbar_wait_parity(uint32_t bar, uint32_t parity)
     }
 }
 
+// tcgen05.ld 32x32b: lane t of the warp reads TMEM lane (quarter base + t), NR consecutive columns.
+template <int NR> __device__ __forceinline__ void tmem_ld(uint32_t taddr, uint32_t (&v)[32]);
+template <> __device__ __forceinline__ void tmem_ld<32>(uint32_t taddr, uint32_t (&v)[32])
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                 "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                   "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                   "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                 : "r"(taddr));
+}
+template <> __device__ __forceinline__ void tmem_ld<16>(uint32_t taddr, uint32_t (&v)[32])
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                 : "r"(taddr));
+}
+template <> __device__ __forceinline__ void tmem_ld<8>(uint32_t taddr, uint32_t (&v)[32])
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "r"(taddr));
+}
+
+// Write NR antenna rows of one accumulator: register i = row (r_first + i), lanes = 32 consecutive floats of that row.
+template <int NR>
+__device__ __forceinline__ void tc_store_rows(uint32_t taddr, float* out_rows, long long pitch, int r_first, int M)
+{
+    uint32_t v[32];
+    tmem_ld<NR>(taddr, v);
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    #pragma unroll
+    for (int i = 0; i < NR; ++i)
+        if (r_first + i < M) __stcs(out_rows + (long long)i * pitch, __uint_as_float(v[i]));
+}
+
+struct TcTile { int row0, ct, acc; };
+
+__device__ __noinline__ void tc_epilogue(const TcTile& t, uint32_t tmem_base, float* out_u, long long pitch, int M, int mtile,
+                                            int warp, int lane)
+{
+    const int q = warp & 3, h = warp >> 2;                 // TMEM lane quarter (32 floats of the segment), half of the rows
+    const int rows_half = mtile >> 1;                      // 64, 32, 16 or 8 antenna rows per warp
+    const int r_base = t.row0 + h * rows_half;
+    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(t.acc * 128 + h * rows_half);
+    float* o = out_u + (long long)r_base * pitch + t.ct * kTcN + q * 32 + lane;
+    if (rows_half == 64) {
+        tc_store_rows<32>(taddr, o, pitch, r_base, M);
+        tc_store_rows<32>(taddr + 32, o + 32 * pitch, pitch, r_base + 32, M);
+    } else if (rows_half == 32) {
+        tc_store_rows<32>(taddr, o, pitch, r_base, M);
+    } else if (rows_half == 16) {
+        tc_store_rows<16>(taddr, o, pitch, r_base, M);
+    } else {
+        tc_store_rows<8>(taddr, o, pitch, r_base, M);
+    }
+}
+
 __global__ void __launch_bounds__(kTcThreads, 2)
 fd_tc_kernel(const DevDesc d, const TcCfg cfg, const int ksplit)
 {
@@ -120,7 +184,7 @@ fd_tc_kernel(const DevDesc d, const TcCfg cfg, const int ksplit)
 
     if (warp == 0) fd_warp_prologue(d, user, sh, ks == 0);
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(&tmem_base_s)), "r"(kTcN));
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(&tmem_base_s)), "r"(2 * 128));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
     }
     if (tid == 64) {
@@ -175,16 +239,21 @@ fd_tc_kernel(const DevDesc d, const TcCfg cfg, const int ksplit)
         __syncthreads();
 
         const int nchunk = (np + kTcChunk - 1) / kTcChunk;
-        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kTcN >> 3) << 17) | ((uint32_t)(mtile >> 4) << 24);
+        // instruction descriptor: D = F32, A = B = TF32, both K-major, N = antenna rows of the tile, M = 128 subcarrier floats
+        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(mtile >> 3) << 17) | ((uint32_t)(kTcN >> 4) << 24);
         const uint64_t dAhi = umma_desc_kmajor_sw128(smem_u32(sAhi)), dAlo = umma_desc_kmajor_sw128(smem_u32(sAlo));
         const uint64_t dBhi = umma_desc_kmajor_sw128(smem_u32(sBhi)), dBlo = umma_desc_kmajor_sw128(smem_u32(sBlo));
         uint32_t phase = 0;
+        bool pending = false, have_prev = false;      // an MMA commit is outstanding / a tile waits for its epilogue
+        TcTile prev = {0, 0, 0};
+        int tile_idx = 0;
         // Operand builders: a thread owns one row (A) / one subcarrier (B) and a group of consecutive path slots, so
         // the row -> (rx element, z, y) decomposition is done once per tile, table reads of neighbouring lanes are
         // consecutive or broadcast, and two path slots (re,im,re,im) go out as one conflict-free 16-byte store.
-        const int a_row  = tid & (mtile - 1);                       // row of the tile this thread fills
-        const int a_grp  = tid / mtile;                             // 0..(256/mtile - 1)
-        const int a_nsl  = kTcChunk / (kTcThreads / mtile);         // slots per thread: 8 (mtile 128) or 4 (mtile 64)
+        const int a_row  = tid & (mtile - 1);                       // antenna row of the tile this thread fills
+        const int a_ngrp = min(kTcThreads / mtile, 8);              // thread groups over the 16 path slots (>= 2 slots each)
+        const int a_grp  = tid / mtile;                             // threads with a_grp >= a_ngrp (mtile = 16) sit the A build out
+        const int a_nsl  = kTcChunk / a_ngrp;                       // slots per thread: 8, 4, 2 or 2
         const int a_off0 = (a_row >> 3) * 1024 + (a_row & 7) * 128;
         const int b_col  = tid & 63;                                // subcarrier of the tile this thread fills
         const int b_grp  = tid >> 6;                                // 0..3 -> slots 4*b_grp .. +3
@@ -208,8 +277,14 @@ fd_tc_kernel(const DevDesc d, const TcCfg cfg, const int ksplit)
                     a_q = (int)(rr * (unsigned)d.bs1 + zt);
                 }
                 for (int ch = 0; ch < nchunk; ++ch) {
+                    if (pending) {                    // the previous MMA group has finished reading A/B (and writing its accumulator)
+                        mbar_wait_parity(smem_u32(&mbar), phase);
+                        phase ^= 1;
+                        pending = false;
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    }
                     // ---- A_hi / A_lo
-                    {
+                    if (a_grp < a_ngrp) {
                         const int j0 = a_grp * a_nsl;
                         const float2* tQp = tQ + (ch * kTcChunk + j0) * cfg.sQ + a_q;
                         const float2* tYp = tY + (ch * kTcChunk + j0) * cfg.sY + a_y;
@@ -242,6 +317,7 @@ fd_tc_kernel(const DevDesc d, const TcCfg cfg, const int ksplit)
                         }
                     }
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                     __syncthreads();
                     if (tid == 0) {
                         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -256,65 +332,34 @@ fd_tc_kernel(const DevDesc d, const TcCfg cfg, const int ksplit)
                                 const uint32_t accum = (ch | s | kk) != 0;
                                 asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
                                              "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}"
-                                             :: "r"(tmem_base), "l"(da + 2 * kk), "l"(db + 2 * kk), "r"(idesc), "r"(accum) : "memory");
+                                             :: "r"(tmem_base + (uint32_t)((tile_idx & 1) * 128)), "l"(db + 2 * kk), "l"(da + 2 * kk), "r"(idesc), "r"(accum) : "memory");
                             }
                         }
                         asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
                                      :: "r"(smem_u32(&mbar)) : "memory");
                     }
-                    mbar_wait_parity(smem_u32(&mbar), phase);
-                    phase ^= 1;
-                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                }
-                b_valid = true;
-
-                // ---- epilogue: TMEM -> registers -> swizzled staging (A buffer) -> 128-byte row segments
-                {
-                    const int q = warp & 3, h = warp >> 2;
-                    unsigned char* stage = sAhi + warp * 4096;              // 32 rows x 128 B per warp
-                    #pragma unroll 1
-                    for (int c = 0; c < 2; ++c) {
-                        const int colf = 64 * h + 32 * c;                   // float column inside the tile
-                        uint32_t v[32];
-                        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)colf;
-                        asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                                     "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-                                     : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-                                       "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
-                                       "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
-                                       "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-                                     : "r"(taddr));
-                        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                        __syncwarp();                                        // previous pass's readers are done with the staging rows
-                        #pragma unroll
-                        for (int i = 0; i < 8; ++i)
-                            *reinterpret_cast<uint4*>(stage + lane * 128 + (((i ^ lane) & 7) << 4)) =
-                                make_uint4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-                        __syncwarp();
-                        // lanes 8r'..8r'+7 write one 128-byte segment of one row; 4 rows per instruction
-                        #pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            const int rl = 4 * i + (lane >> 3);             // TMEM lane of this warp's quarter
-                            const int jj = lane & 7;
-                            const uint4 val = *reinterpret_cast<const uint4*>(stage + rl * 128 + (((jj ^ rl) & 7) << 4));
-                            // M = 128: lane = row.  M = 64: rows 16q .. 16q+15 live in lanes 0..15 of quarter q.
-                            const int rt_row = (mtile == 128) ? (q * 32 + rl) : (rl < 16 ? q * 16 + rl : -1);
-                            const int m = row0 + rt_row;
-                            if (rt_row >= 0 && m < M)
-                                __stcs(reinterpret_cast<uint4*>(out_u + (long long)m * pitch + ct * kTcN + colf) + jj, val);
-                        }
+                    pending = true;
+                    if (ch == 0 && have_prev) {       // drain the previous tile while the tensor core works on this one
+                        tc_epilogue(prev, tmem_base, out_u, pitch, M, mtile, warp, lane);
+                        have_prev = false;
                     }
                 }
-                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                __syncthreads();                      // staging (A buffer) and TMEM are free for the next tile
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                b_valid = true;
+                prev.row0 = row0; prev.ct = ct; prev.acc = tile_idx & 1;
+                have_prev = true;
+                ++tile_idx;
             }
         }
+        if (pending) {
+            mbar_wait_parity(smem_u32(&mbar), phase);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        }
+        if (have_prev) tc_epilogue(prev, tmem_base, out_u, pitch, M, mtile, warp, lane);
     }
 
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"(kTcN));
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"(2 * 128));
 }
 
 }  // namespace dmk

@@ -20,10 +20,18 @@ struct PathState {
     double pw;           // power_linear_ant_gain (float64 view)
 };
 
-// Global -> local angles of one side.  geometry.py:284-310.
+// Global -> local direction of one side.  geometry.py:284-310.
+//
+// The reference goes through the angles: theta' = arccos(x), phi' = angle(re + j im), and the array response then
+// takes sin/cos of them again (geometry.py:99-101).  The steering needs only
+//     sin(theta') sin(phi') = sqrt((1-x)(1+x)) * im / hypot(re, im),      cos(theta') = x,
+// which are the same functions of (x, re, im) evaluated to a few float64 ulps, so the angles themselves (acos, atan2:
+// ~half of the prologue's dependent latency) are computed only when something consumes them -- the FoV compares
+// (geometry.py:180-193), the dipole pattern (ant_patterns.py:57-69) or the by-product kernel.
+template <bool kNeedAngles>
 __device__ __forceinline__ void rotate_side(float el_deg, float az_deg,
                                             double sx, double cx, double sy, double cy, double rz,
-                                            double& th, double& ph)
+                                            double& th, double& ph, double& sin_th_sin_ph, double& cos_th)
 {
     const float d2r = 0x1.1df46ap-6f;                       // float32(pi/180): np.deg2rad on float32 (R1)
     float th32 = __fmul_rn(el_deg, d2r);                    // :284
@@ -37,13 +45,24 @@ __device__ __forceinline__ void rotate_side(float el_deg, float az_deg,
     // :305-306  arccos(cy*cx*ct + st*(sy*cx*cd - sx*sd)), same association, no contraction
     double x = __dadd_rn(__dmul_rn(__dmul_rn(cy, cx), ct),
                          __dmul_rn(st, __dsub_rn(__dmul_rn(__dmul_rn(sy, cx), cd), __dmul_rn(sx, sd))));
-    th = acos(x);
     // :308-310  angle(cy*st*cd - sy*ct + 1j*(cy*sx*ct + st*(sy*sx*cd + cx*sd)))
     double re = __dsub_rn(__dmul_rn(__dmul_rn(cy, st), cd), __dmul_rn(sy, ct));
     double im = __dadd_rn(__dmul_rn(__dmul_rn(cy, sx), ct),
                           __dmul_rn(st, __dadd_rn(__dmul_rn(__dmul_rn(sy, sx), cd), __dmul_rn(cx, sd))));
     re = __dadd_rn(re, 0.0);                                // real + real(1j*im) = re + 0
-    ph = atan2(im, re);
+    if (kNeedAngles) {
+        th = acos(x);
+        ph = atan2(im, re);
+    } else {
+        // NaN exactly where the reference's angles are NaN (|x| > 1, NaN inputs); finite otherwise
+        th = (fabs(x) <= 1.0) ? 0.0 : __longlong_as_double(0x7ff8000000000000LL);
+        ph = (re == re && im == im) ? 0.0 : __longlong_as_double(0x7ff8000000000000LL);
+    }
+    const double sin_th = sqrt(__dmul_rn(__dsub_rn(1.0, x), __dadd_rn(1.0, x)));     // sin(arccos(x)); NaN for |x| > 1
+    const double h = sqrt(__dadd_rn(__dmul_rn(re, re), __dmul_rn(im, im)));
+    const double sin_ph = (h > 0.0) ? __ddiv_rn(im, h) : 0.0;                        // sin(atan2(im, re)); atan2(0, +0) = 0
+    sin_th_sin_ph = sin_th * sin_ph;
+    cos_th = x;
 }
 
 // geometry.py:180-193 on one side.  theta in [0, pi] so mod(theta, 2pi) == theta; phi in (-pi, pi].
@@ -64,8 +83,8 @@ __device__ __forceinline__ double dipole_gain(double th)
     return __dmul_rn(1.643, __ddiv_rn(__dmul_rn(ct, ct), s));
 }
 
-template <bool kFreqDomain>
-__device__ __forceinline__ void path_prologue(const DevDesc& d, long long user, int p, PathState& o)
+template <bool kFreqDomain, bool kNeedAngles>
+__device__ __forceinline__ void path_prologue_impl(const DevDesc& d, long long user, int p, PathState& o)
 {
     const long long off = user * (long long)d.ld + p;
     const float pw_db = d.power[off];
@@ -80,8 +99,9 @@ __device__ __forceinline__ void path_prologue(const DevDesc& d, long long user, 
         sincos(__dmul_rn(r[1], k), &syu, &cyu);
         rzu = __dmul_rn(r[2], k);
     }
-    rotate_side(d.el[0][off], d.az[0][off], d.sx[0], d.cx[0], d.sy[0], d.cy[0], d.rz[0], o.th[0], o.ph[0]);
-    rotate_side(d.el[1][off], d.az[1][off], sxu, cxu, syu, cyu, rzu, o.th[1], o.ph[1]);
+    double ss[2], cc[2];
+    rotate_side<kNeedAngles>(d.el[0][off], d.az[0][off], d.sx[0], d.cx[0], d.sy[0], d.cy[0], d.rz[0], o.th[0], o.ph[0], ss[0], cc[0]);
+    rotate_side<kNeedAngles>(d.el[1][off], d.az[1][off], sxu, cxu, syu, cyu, rzu, o.th[1], o.ph[1], ss[1], cc[1]);
 
     // ---- FoV (dataset.py:493-512)
     bool fov = true;
@@ -96,11 +116,8 @@ __device__ __forceinline__ void path_prologue(const DevDesc& d, long long user, 
     // ---- steering cycles per element step (geometry.py:99-101 with x == 0; dataset.py:393)
     #pragma unroll
     for (int s = 0; s < 2; ++s) {
-        double sth, cth, sph, cph;
-        sincos(o.th[s], &sth, &cth);
-        sincos(o.ph[s], &sph, &cph);
-        o.u[s] = d.sp[s] * (sth * sph);
-        o.v[s] = d.sp[s] * cth;
+        o.u[s] = d.sp[s] * ss[s];
+        o.v[s] = d.sp[s] * cc[s];
     }
 
     // ---- power: generator_utils.py:35 (float32 divide, float32 pow; R7), ant_patterns.py:167-168
@@ -148,6 +165,22 @@ __device__ __forceinline__ void path_prologue(const DevDesc& d, long long user, 
     // exact zeros where theta is NaN (geometry.py:65-80) or outside the FoV (dataset.py:508-511);
     // NaN gains are dropped by nansum (channel.py:283).
     o.contrib = o.valid && fov && ang_ok && c_ok && !(o.c.x == 0.0f && o.c.y == 0.0f);
+}
+
+// The angles are consumed by the FoV compares and the dipole pattern only.
+template <bool kFreqDomain>
+__device__ __forceinline__ void path_prologue(const DevDesc& d, long long user, int p, PathState& o)
+{
+    if (d.fov_any || d.pat[0] != DMK_PATTERN_ISOTROPIC || d.pat[1] != DMK_PATTERN_ISOTROPIC)
+        path_prologue_impl<kFreqDomain, true>(d, user, p, o);
+    else
+        path_prologue_impl<kFreqDomain, false>(d, user, p, o);
+}
+
+// By-product kernel: always materialise the angles.
+__device__ __forceinline__ void path_prologue_angles(const DevDesc& d, long long user, int p, PathState& o)
+{
+    path_prologue_impl<false, true>(d, user, p, o);
 }
 
 }  // namespace dmk

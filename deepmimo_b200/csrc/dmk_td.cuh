@@ -114,7 +114,7 @@ prologue_kernel(const DevDesc d, double* __restrict__ angles_rot, double* __rest
     const long long user = idx / d.P0;
     const int p = (int)(idx - user * d.P0);
     PathState st;
-    path_prologue<false>(d, user, p, st);
+    path_prologue_angles(d, user, p, st);
     if (angles_rot) {
         angles_rot[0 * total + idx] = st.th[0];
         angles_rot[1 * total + idx] = st.ph[0];
