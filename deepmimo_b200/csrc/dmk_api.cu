@@ -197,7 +197,7 @@ int dmk_channels_fd(const dmk_desc* desc, const float* power_dbw, const float* p
     // tile: the packed-FP32 kernel is faster there (profiles/README.md); DMK_FD_KERNEL=tc still forces it.
     const bool want_tc = force && !strcmp(force, "tc");
     const bool use_tc = affine && !d.has_time_axis && div_ok && (d.K % (kTcN / 2) == 0) && tc_smem <= 112 * 1024 &&
-                        !want_tile && !want_ffma && (d.M >= 128 || want_tc);
+                        !want_tile && !want_ffma && ((d.M >= 128 && !d.fov_any) || want_tc);   // FoV leaves few paths: FP32 kernel wins
     const bool use_fast = !use_tc && affine && !d.has_time_axis && div_ok && fast_smem <= 110 * 1024 && !want_tile;
     const int tile_w = use_tc ? (kTcN / 2) : (use_fast ? kTKW : kTK);
     const int n_ct = (ncols + tile_w - 1) / tile_w;

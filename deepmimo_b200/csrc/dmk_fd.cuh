@@ -27,28 +27,43 @@ struct FdShared {
     int    np;
 };
 
-// Warp 0: prologue for the P0 path columns of `user`, masks out, contributing paths compacted.
-__device__ __forceinline__ void fd_warp_prologue(const DevDesc& d, long long user, FdShared& sh, bool write_masks)
+// Prologue of one user, all threads of the CTA call this: warps 0-2 run the three float64 chains of every path
+// column (cta_prologue_chains), then warp 0 combines them, writes the masks and compacts the contributing paths.
+// Ends with a CTA barrier; sh.np is valid afterwards.
+__device__ __forceinline__ void fd_cta_prologue(const DevDesc& d, long long user, FdShared& sh, PrologueScratch& sc, bool write_masks)
 {
-    const int lane = threadIdx.x & 31;
-    PathState st;
-    bool active = lane < d.P0;
-    st.contrib = false; st.valid = false; st.fov = true; st.over = false;
-    if (active) path_prologue<true>(d, user, lane, st);
-    const unsigned ballot = __ballot_sync(0xffffffffu, active && st.contrib);
-    if (active && st.contrib) {
-        const int j = __popc(ballot & ((1u << lane) - 1u));
-        sh.c[j] = st.c; sh.wcyc[j] = st.wcyc; sh.fd[j] = st.fd;
-        sh.u[0][j] = st.u[0]; sh.v[0][j] = st.v[0];
-        sh.u[1][j] = st.u[1]; sh.v[1][j] = st.v[1];
+    cta_prologue_chains<true>(d, user, sc);
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        const int lane = threadIdx.x;
+        PathState st;
+        const bool active = lane < d.P0;
+        st.contrib = false; st.valid = false; st.fov = true; st.over = false;
+        if (active) prologue_combine<true>(d, sc.side[0][lane], sc.side[1][lane], sc.gain[lane], st);
+        const unsigned ballot = __ballot_sync(0xffffffffu, active && st.contrib);
+        if (active && st.contrib) {
+            const int j = __popc(ballot & ((1u << lane) - 1u));
+            sh.c[j] = st.c; sh.wcyc[j] = st.wcyc; sh.fd[j] = st.fd;
+            sh.u[0][j] = st.u[0]; sh.v[0][j] = st.v[0];
+            sh.u[1][j] = st.u[1]; sh.v[1][j] = st.v[1];
+        }
+        if (lane == 0) sh.np = __popc(ballot);
+        if (write_masks && active) {
+            const long long o = user * (long long)d.P0 + lane;
+            if (d.fov_mask)   d.fov_mask[o]   = st.fov ? 1 : 0;
+            if (d.valid_mask) d.valid_mask[o] = st.valid ? 1 : 0;
+            if (d.clip_mask)  d.clip_mask[o]  = (st.valid && st.over) ? 1 : 0;
+        }
     }
-    if (lane == 0) sh.np = __popc(ballot);
-    if (write_masks && active) {
-        const long long o = user * (long long)d.P0 + lane;
-        if (d.fov_mask)   d.fov_mask[o]   = st.fov ? 1 : 0;
-        if (d.valid_mask) d.valid_mask[o] = st.valid ? 1 : 0;
-        if (d.clip_mask)  d.clip_mask[o]  = (st.valid && st.over) ? 1 : 0;
-    }
+    __syncthreads();
+}
+
+// Out-of-line instance for the tensor-core kernel: inlining the three float64 chains there raises its register
+// allocation (93 -> 112) and costs ~10 % in its main loop (measured A/B on the same B200), whereas the packed-FP32
+// kernel is ~6 % faster with the inlined version.
+__device__ __noinline__ void fd_cta_prologue_outlined(const DevDesc& d, long long user, FdShared& sh, PrologueScratch& sc, bool write_masks)
+{
+    fd_cta_prologue(d, user, sh, sc, write_masks);
 }
 
 __global__ void __launch_bounds__(kFdThreads, 2)
@@ -58,13 +73,13 @@ fd_tile_kernel(const DevDesc d, const int ksplit)
     float2* sW = reinterpret_cast<float2*>(smem_raw);                    // [kMaxPaths][kTK]
     float2* sA = sW + kMaxPaths * kTK;                                   // [kMaxPaths][kTM]
     __shared__ FdShared sh;
+    __shared__ PrologueScratch psc;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const long long user = blockIdx.x / ksplit;
     const int ks = blockIdx.x % ksplit;
 
-    if (warp == 0) fd_warp_prologue(d, user, sh, ks == 0);
-    __syncthreads();
+    fd_cta_prologue(d, user, sh, psc, ks == 0);
     const int np = sh.np;
 
     const int ncols = d.K * d.T;
@@ -208,13 +223,13 @@ fd_fast_kernel(const DevDesc d, const FastCfg cfg, const int ksplit)
     float2* wA = reinterpret_cast<float2*>(smem_raw + cfg.off_wA);   // [pcap][nA]
     float2* wB = reinterpret_cast<float2*>(smem_raw + cfg.off_wB);   // [pcap][16]
     __shared__ FdShared sh;
+    __shared__ PrologueScratch psc;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const long long user = blockIdx.x / ksplit;
     const int ks = blockIdx.x % ksplit;
 
-    if (warp == 0) fd_warp_prologue(d, user, sh, ks == 0);
-    __syncthreads();
+    fd_cta_prologue(d, user, sh, psc, ks == 0);
     const int np = sh.np;
     const int ncols = d.K;
     const int n_ct = (ncols + kTKW - 1) / kTKW;

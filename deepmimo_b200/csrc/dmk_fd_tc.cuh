@@ -165,6 +165,7 @@ fd_tc_kernel(const DevDesc d, const TcCfg cfg, const int ksplit)
 {
     extern __shared__ unsigned char smem_raw[];
     __shared__ FdShared sh;
+    __shared__ PrologueScratch psc;
     __shared__ uint64_t mbar;
     __shared__ uint32_t tmem_base_s;
 
@@ -182,8 +183,7 @@ fd_tc_kernel(const DevDesc d, const TcCfg cfg, const int ksplit)
     float2* wA = reinterpret_cast<float2*>(sm + cfg.off_wA);
     float2* wB = reinterpret_cast<float2*>(sm + cfg.off_wB);
 
-    if (warp == 0) fd_warp_prologue(d, user, sh, ks == 0);
-    if (warp == 1) {
+    if (warp == 3) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(&tmem_base_s)), "r"(2 * 128));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
     }
@@ -192,7 +192,7 @@ fd_tc_kernel(const DevDesc d, const TcCfg cfg, const int ksplit)
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
+    fd_cta_prologue_outlined(d, user, sh, psc, ks == 0);      // (two CTA barriers inside)
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = tmem_base_s;
     const int np = sh.np;
@@ -259,6 +259,7 @@ fd_tc_kernel(const DevDesc d, const TcCfg cfg, const int ksplit)
         const int b_grp  = tid >> 6;                                // 0..3 -> slots 4*b_grp .. +3
         const int b_off0 = ((2 * b_col) >> 3) * 1024 + ((2 * b_col) & 7) * 128;      // row 2*b_col; row 2*b_col+1 is +128 bytes
 
+        bool a_valid = false;                         // A tile in smem is still current (single row tile, single chunk)
         for (int ct = ks; ct < n_ct; ct += ksplit) {
             const int col0 = ct * (kTcN / 2);        // first subcarrier (complex column) of the tile
             bool b_valid = false;                     // B tile of chunk 0 currently in smem (single-chunk users reuse it)
@@ -284,7 +285,7 @@ fd_tc_kernel(const DevDesc d, const TcCfg cfg, const int ksplit)
                         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     }
                     // ---- A_hi / A_lo
-                    if (a_grp < a_ngrp) {
+                    if (a_grp < a_ngrp && !(a_valid && nchunk == 1 && n_rt == 1)) {
                         const int j0 = a_grp * a_nsl;
                         const float2* tQp = tQ + (ch * kTcChunk + j0) * cfg.sQ + a_q;
                         const float2* tYp = tY + (ch * kTcChunk + j0) * cfg.sY + a_y;
@@ -345,6 +346,7 @@ fd_tc_kernel(const DevDesc d, const TcCfg cfg, const int ksplit)
                     }
                 }
                 b_valid = true;
+                a_valid = true;
                 prev.row0 = row0; prev.ct = ct; prev.acc = tile_idx & 1;
                 have_prev = true;
                 ++tile_idx;
@@ -359,7 +361,7 @@ fd_tc_kernel(const DevDesc d, const TcCfg cfg, const int ksplit)
 
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"(2 * 128));
+    if (warp == 3) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"(2 * 128));
 }
 
 }  // namespace dmk

@@ -83,104 +83,132 @@ __device__ __forceinline__ double dipole_gain(double th)
     return __dmul_rn(1.643, __ddiv_rn(__dmul_rn(ct, ct), s));
 }
 
-template <bool kFreqDomain, bool kNeedAngles>
-__device__ __forceinline__ void path_prologue_impl(const DevDesc& d, long long user, int p, PathState& o)
+// ---------------------------------------------------------------------------------------------------------
+// The prologue of one path is three independent float64 dependency chains (TX-side rotation, RX-side rotation,
+// gain/delay/phase) followed by a short combine.  One thread can run them back to back (by-product kernel); the
+// channel kernels give each chain its own warp (lanes = path columns) so the CTA's critical path is one chain.
+// ---------------------------------------------------------------------------------------------------------
+struct SideOut { double th, ph, ss, cc, gain; };           // rotated angles, sin(th)sin(ph), cos(th), element power gain
+struct GainOut { float p_lin, ec, es; double wcyc, fd; unsigned char valid, over; };
+
+template <bool kNeedAngles>
+__device__ __forceinline__ void prologue_side(const DevDesc& d, long long user, int p, int side, SideOut& o)
+{
+    const long long off = user * (long long)d.ld + p;
+    double sx = d.sx[side], cx = d.cx[side], sy = d.sy[side], cy = d.cy[side], rz = d.rz[side];
+    if (side == 1 && d.ue_rot) {                            // per-user UE rotation (dataset.py:328-338)
+        const double k = kPi / 180.0;                       // np.deg2rad float64: x * (pi/180)
+        const double* r = d.ue_rot + user * 3;
+        sincos(__dmul_rn(r[0], k), &sx, &cx);
+        sincos(__dmul_rn(r[1], k), &sy, &cy);
+        rz = __dmul_rn(r[2], k);
+    }
+    rotate_side<kNeedAngles>(d.el[side][off], d.az[side][off], sx, cx, sy, cy, rz, o.th, o.ph, o.ss, o.cc);
+    o.gain = 1.0;
+}
+
+template <bool kFreqDomain>
+__device__ __forceinline__ void prologue_gain(const DevDesc& d, long long user, int p, GainOut& g)
 {
     const long long off = user * (long long)d.ld + p;
     const float pw_db = d.power[off];
-    o.valid = (p < d.P) && !(pw_db != pw_db);
-
-    // ---- rotation (dataset.py:341-349)
-    double sxu = d.sx[1], cxu = d.cx[1], syu = d.sy[1], cyu = d.cy[1], rzu = d.rz[1];
-    if (d.ue_rot) {                                         // per-user UE rotation (dataset.py:328-338)
-        const double k = kPi / 180.0;                       // np.deg2rad float64: x * (pi/180)
-        const double* r = d.ue_rot + user * 3;
-        sincos(__dmul_rn(r[0], k), &sxu, &cxu);
-        sincos(__dmul_rn(r[1], k), &syu, &cyu);
-        rzu = __dmul_rn(r[2], k);
+    g.valid = (p < d.P) && !(pw_db != pw_db);               // channel.py:260, dataset.py:258-261
+    // generator_utils.py:35: float32 divide by 10, float32 pow (R7, <= 1 ulp)
+    g.p_lin = (float)exp10((double)__fdiv_rn(pw_db, 10.0f));
+    const float d2r = 0x1.1df46ap-6f;
+    const float ph32 = __fmul_rn(d.phase[off], d2r);        // np.deg2rad(phase) float32
+    double es64, ec64;
+    sincos((double)ph32, &es64, &ec64);                     // complex64 exp(1j*x): cosf/sinf (R10, <= 1 ulp)
+    g.ec = (float)ec64; g.es = (float)es64;
+    g.over = 0; g.wcyc = 0.0;
+    if (kFreqDomain) {
+        float dn = __fdiv_rn(d.delay[off], d.ts_f32);       // channel.py:183 (R11)
+        g.over = dn >= d.n_f32;                             // :187 (R12)
+        if (g.over) dn = d.n_f32;                           // :189
+        g.wcyc = (double)dn * d.inv_n;
     }
-    double ss[2], cc[2];
-    rotate_side<kNeedAngles>(d.el[0][off], d.az[0][off], d.sx[0], d.cx[0], d.sy[0], d.cy[0], d.rz[0], o.th[0], o.ph[0], ss[0], cc[0]);
-    rotate_side<kNeedAngles>(d.el[1][off], d.az[1][off], sxu, cxu, syu, cyu, rzu, o.th[1], o.ph[1], ss[1], cc[1]);
+    g.fd = d.doppler ? (double)d.doppler[off] : 0.0;
+}
 
+template <bool kFreqDomain>
+__device__ __forceinline__ void prologue_combine(const DevDesc& d, const SideOut& s0, const SideOut& s1, const GainOut& g, PathState& o)
+{
+    o.valid = g.valid; o.over = g.over; o.wcyc = g.wcyc; o.fd = g.fd;
+    o.th[0] = s0.th; o.ph[0] = s0.ph; o.th[1] = s1.th; o.ph[1] = s1.ph;
     // ---- FoV (dataset.py:493-512)
     bool fov = true;
     if (d.fov_any) {
-        if (d.fov_side[0]) fov = fov && in_fov(d, 0, o.th[0], o.ph[0]);
-        if (d.fov_side[1]) fov = fov && in_fov(d, 1, o.th[1], o.ph[1]);
+        if (d.fov_side[0]) fov = fov && in_fov(d, 0, s0.th, s0.ph);
+        if (d.fov_side[1]) fov = fov && in_fov(d, 1, s1.th, s1.ph);
     }
     o.fov = fov;
-    const bool ang_ok = !(o.th[0] != o.th[0]) && !(o.th[1] != o.th[1]) &&
-                        !(o.ph[0] != o.ph[0]) && !(o.ph[1] != o.ph[1]);
-
+    const bool ang_ok = !(s0.th != s0.th) && !(s1.th != s1.th) && !(s0.ph != s0.ph) && !(s1.ph != s1.ph);
     // ---- steering cycles per element step (geometry.py:99-101 with x == 0; dataset.py:393)
-    #pragma unroll
-    for (int s = 0; s < 2; ++s) {
-        o.u[s] = d.sp[s] * ss[s];
-        o.v[s] = d.sp[s] * cc[s];
-    }
-
-    // ---- power: generator_utils.py:35 (float32 divide, float32 pow; R7), ant_patterns.py:167-168
-    float  p_lin = (float)exp10((double)__fdiv_rn(pw_db, 10.0f));
+    o.u[0] = d.sp[0] * s0.ss; o.v[0] = d.sp[0] * s0.cc;
+    o.u[1] = d.sp[1] * s1.ss; o.v[1] = d.sp[1] * s1.cc;
+    // ---- power with element patterns (ant_patterns.py:167-168): float64 as soon as one side is a dipole
     const bool f64_power = (d.pat[0] != DMK_PATTERN_ISOTROPIC) || (d.pat[1] != DMK_PATTERN_ISOTROPIC);
-    double pw64 = (double)p_lin;
+    double pw64 = (double)g.p_lin;
     if (f64_power) {
         const double nan64 = __longlong_as_double(0x7ff8000000000000LL);
-        double gt = (d.pat[0] == DMK_PATTERN_HALFWAVE_DIPOLE) ? dipole_gain(fov ? o.th[0] : nan64) : 1.0;
-        double gr = (d.pat[1] == DMK_PATTERN_HALFWAVE_DIPOLE) ? dipole_gain(fov ? o.th[1] : nan64) : 1.0;
+        const double gt = (d.pat[0] == DMK_PATTERN_HALFWAVE_DIPOLE) ? dipole_gain(fov ? s0.th : nan64) : 1.0;
+        const double gr = (d.pat[1] == DMK_PATTERN_HALFWAVE_DIPOLE) ? dipole_gain(fov ? s1.th : nan64) : 1.0;
         pw64 = __dmul_rn(pw64, __dmul_rn(gt, gr));
     }
     o.pw = pw64;
-
     // ---- path gain
-    const float d2r = 0x1.1df46ap-6f;
-    const float ph32 = __fmul_rn(d.phase[off], d2r);        // np.deg2rad(phase) float32
-    const float ec = (float)cos((double)ph32);              // complex64 exp(1j*x): cosf/sinf (R10, <= 1 ulp)
-    const float es = (float)sin((double)ph32);
-    o.over = false;
     if (kFreqDomain) {
-        float dn = __fdiv_rn(d.delay[off], d.ts_f32);       // channel.py:183 (R11)
-        o.over = dn >= d.n_f32;                             // :187 (R12)
-        if (o.over) dn = d.n_f32;                           // :189
-        o.wcyc = (double)dn * d.inv_n;
         if (f64_power) {
-            double amp = o.over ? 0.0 : sqrt(__ddiv_rn(pw64, (double)d.N));   // :188, :192 (float64 branch)
-            o.c = make_float2((float)(amp * (double)ec), (float)(amp * (double)es));
+            const double amp = g.over ? 0.0 : sqrt(__ddiv_rn(pw64, (double)d.N));   // channel.py:188,:192 (float64 branch)
+            o.c = make_float2((float)(amp * (double)g.ec), (float)(amp * (double)g.es));
         } else {
-            float amp = o.over ? 0.0f : __fsqrt_rn(__fdiv_rn(p_lin, d.n_f32));  // :188, :192 (R9)
-            o.c = make_float2(__fmul_rn(amp, ec), __fmul_rn(amp, es));
+            const float amp = g.over ? 0.0f : __fsqrt_rn(__fdiv_rn(g.p_lin, d.n_f32));  // :188, :192 (R9)
+            o.c = make_float2(__fmul_rn(amp, g.ec), __fmul_rn(amp, g.es));
         }
     } else {
-        o.wcyc = 0.0;
         if (f64_power) {
-            double amp = sqrt(pw64);                        // channel.py:286
-            o.c = make_float2((float)(amp * (double)ec), (float)(amp * (double)es));
+            const double amp = sqrt(pw64);                  // channel.py:286
+            o.c = make_float2((float)(amp * (double)g.ec), (float)(amp * (double)g.es));
         } else {
-            float amp = __fsqrt_rn(p_lin);
-            o.c = make_float2(__fmul_rn(amp, ec), __fmul_rn(amp, es));
+            const float amp = __fsqrt_rn(g.p_lin);
+            o.c = make_float2(__fmul_rn(amp, g.ec), __fmul_rn(amp, g.es));
         }
     }
-    o.fd = d.doppler ? (double)d.doppler[off] : 0.0;
     const bool c_ok = (o.c.x == o.c.x) && (o.c.y == o.c.y) && (o.wcyc == o.wcyc) && (o.fd == o.fd);
     // exact zeros where theta is NaN (geometry.py:65-80) or outside the FoV (dataset.py:508-511);
     // NaN gains are dropped by nansum (channel.py:283).
     o.contrib = o.valid && fov && ang_ok && c_ok && !(o.c.x == 0.0f && o.c.y == 0.0f);
 }
 
-// The angles are consumed by the FoV compares and the dipole pattern only.
-template <bool kFreqDomain>
-__device__ __forceinline__ void path_prologue(const DevDesc& d, long long user, int p, PathState& o)
+__device__ __forceinline__ bool prologue_needs_angles(const DevDesc& d)
 {
-    if (d.fov_any || d.pat[0] != DMK_PATTERN_ISOTROPIC || d.pat[1] != DMK_PATTERN_ISOTROPIC)
-        path_prologue_impl<kFreqDomain, true>(d, user, p, o);
-    else
-        path_prologue_impl<kFreqDomain, false>(d, user, p, o);
+    return d.fov_any || d.pat[0] != DMK_PATTERN_ISOTROPIC || d.pat[1] != DMK_PATTERN_ISOTROPIC;
 }
 
-// By-product kernel: always materialise the angles.
+// Cooperative phase 1: warps 0, 1, 2 of the CTA run the three chains for path column `lane` of `user`.
+struct PrologueScratch { SideOut side[2][kMaxPaths]; GainOut gain[kMaxPaths]; };
+
+template <bool kFreqDomain>
+__device__ __forceinline__ void cta_prologue_chains(const DevDesc& d, long long user, PrologueScratch& sc)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane >= d.P0 || warp > 2) return;
+    if (warp < 2) {
+        if (prologue_needs_angles(d)) prologue_side<true>(d, user, lane, warp, sc.side[warp][lane]);
+        else                          prologue_side<false>(d, user, lane, warp, sc.side[warp][lane]);
+    } else {
+        prologue_gain<kFreqDomain>(d, user, lane, sc.gain[lane]);
+    }
+}
+
+// Single-thread version (by-product kernel): always materialises the angles.
 __device__ __forceinline__ void path_prologue_angles(const DevDesc& d, long long user, int p, PathState& o)
 {
-    path_prologue_impl<false, true>(d, user, p, o);
+    SideOut s0, s1; GainOut g;
+    prologue_side<true>(d, user, p, 0, s0);
+    prologue_side<true>(d, user, p, 1, s1);
+    prologue_gain<false>(d, user, p, g);
+    prologue_combine<false>(d, s0, s1, g, o);
 }
 
 }  // namespace dmk

@@ -22,40 +22,45 @@ struct TdShared {
     int nv;
 };
 
-__device__ __forceinline__ void td_warp_prologue(const DevDesc& d, long long user, TdShared& sh)
+__device__ __forceinline__ void td_cta_prologue(const DevDesc& d, long long user, TdShared& sh, PrologueScratch& sc)
 {
-    const int lane = threadIdx.x & 31;
-    PathState st;
-    const bool active = lane < d.P0;
-    st.contrib = false; st.valid = false; st.fov = true; st.over = false;
-    if (active) path_prologue<false>(d, user, lane, st);
-    const unsigned ballot = __ballot_sync(0xffffffffu, active && st.valid);
-    const int j = __popc(ballot & ((1u << lane) - 1u));
-    if (active && st.valid) {
-        sh.c[j] = st.c; sh.fd[j] = st.fd; sh.contrib[j] = st.contrib ? 1 : 0;
-        sh.u[0][j] = st.u[0]; sh.v[0][j] = st.v[0];
-        sh.u[1][j] = st.u[1]; sh.v[1][j] = st.v[1];
+    cta_prologue_chains<false>(d, user, sc);
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        const int lane = threadIdx.x;
+        PathState st;
+        const bool active = lane < d.P0;
+        st.contrib = false; st.valid = false; st.fov = true; st.over = false;
+        if (active) prologue_combine<false>(d, sc.side[0][lane], sc.side[1][lane], sc.gain[lane], st);
+        const unsigned ballot = __ballot_sync(0xffffffffu, active && st.valid);
+        const int j = __popc(ballot & ((1u << lane) - 1u));
+        if (active && st.valid) {
+            sh.c[j] = st.c; sh.fd[j] = st.fd; sh.contrib[j] = st.contrib ? 1 : 0;
+            sh.u[0][j] = st.u[0]; sh.v[0][j] = st.v[0];
+            sh.u[1][j] = st.u[1]; sh.v[1][j] = st.v[1];
+        }
+        if (lane == 0) sh.nv = __popc(ballot);
+        if (active) {
+            const long long o = user * (long long)d.P0 + lane;
+            if (d.fov_mask)   d.fov_mask[o]   = st.fov ? 1 : 0;
+            if (d.valid_mask) d.valid_mask[o] = st.valid ? 1 : 0;
+            if (d.path_slot)  d.path_slot[o]  = st.valid ? j : -1;
+        }
     }
-    if (lane == 0) sh.nv = __popc(ballot);
-    if (active) {
-        const long long o = user * (long long)d.P0 + lane;
-        if (d.fov_mask)   d.fov_mask[o]   = st.fov ? 1 : 0;
-        if (d.valid_mask) d.valid_mask[o] = st.valid ? 1 : 0;
-        if (d.path_slot)  d.path_slot[o]  = st.valid ? j : -1;
-    }
+    __syncthreads();
 }
 
 __global__ void __launch_bounds__(kTdThreads, 4)
 td_kernel(const DevDesc d)
 {
     __shared__ TdShared sh;
+    __shared__ PrologueScratch psc;
     __shared__ float2 sA[kTdRows * kMaxPaths];        // [row][slot] gain * steering
     __shared__ float2 sD[kMaxPaths * 64];             // [slot][it] Doppler phasors, 64 snapshots per pass
 
     const int tid = threadIdx.x;
     const long long user = blockIdx.x;
-    if (tid < 32) td_warp_prologue(d, user, sh);
-    __syncthreads();
+    td_cta_prologue(d, user, sh, psc);
     const int nv = sh.nv;
     const int P = d.P, T = d.T;
     float2* out_u = d.out + user * (long long)d.M * P * T;
