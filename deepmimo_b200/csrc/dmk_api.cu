@@ -183,8 +183,9 @@ int dmk_channels_fd(const dmk_desc* desc, const float* power_dbw, const float* p
         tcfg.pcap = pc;
         tcfg.nA = (d.K + 15) / 16;
         tcfg.mtile = d.M >= 128 ? 128 : (d.M > 32 ? 64 : (d.M > 16 ? 32 : 16));   // antenna rows per tile = tcgen05 N
-        tcfg.off_A  = take(2 * 128 * 128);                   // A_hi, A_lo (also the epilogue staging)
-        tcfg.off_B  = take(2 * kTcN * 128);                  // B_hi, B_lo
+        tcfg.nsub = tcfg.mtile <= 64 ? 2 : 1;                // keep a pipeline stage at 64 KB of output for small arrays
+        tcfg.off_A  = take((size_t)2 * tcfg.mtile * 128);    // A_hi, A_lo
+        tcfg.off_B  = take((size_t)tcfg.nsub * 2 * kTcN * 128);   // B_hi, B_lo per sub-tile
         tcfg.sY = d.bs0 | 1; tcfg.sQ = (d.Mr * d.bs1) | 1; tcfg.sA = tcfg.nA | 1; tcfg.sB = 17;   // odd strides: no bank conflicts across paths
         tcfg.off_tY = take((size_t)pc * tcfg.sY * sizeof(float2));
         tcfg.off_tQ = take((size_t)pc * tcfg.sQ * sizeof(float2));
@@ -199,7 +200,7 @@ int dmk_channels_fd(const dmk_desc* desc, const float* power_dbw, const float* p
     const bool use_tc = affine && !d.has_time_axis && div_ok && (d.K % (kTcN / 2) == 0) && tc_smem <= 112 * 1024 &&
                         !want_tile && !want_ffma && ((d.M >= 128 && !d.fov_any) || want_tc);   // FoV leaves few paths: FP32 kernel wins
     const bool use_fast = !use_tc && affine && !d.has_time_axis && div_ok && fast_smem <= 110 * 1024 && !want_tile;
-    const int tile_w = use_tc ? (kTcN / 2) : (use_fast ? kTKW : kTK);
+    const int tile_w = use_tc ? (kTcN / 2) * tcfg.nsub : (use_fast ? kTKW : kTK);
     const int n_ct = (ncols + tile_w - 1) / tile_w;
     // Few users: split each user's column tiles over several CTAs so the grid covers >= 4 waves.
     const long long want = 4LL * 2 * device_sm_count();

@@ -32,13 +32,15 @@
 
 namespace dmk {
 
-constexpr int kTcThreads = 256;
+constexpr int kTcWorkers = 256;   // 8 warps build operands and drain accumulators
+constexpr int kTcThreads = 288;   // + warp 8: issues the tcgen05.mma groups (never shares a warp with worker code)
 constexpr int kTcN       = 128;   // real output columns per tile = 64 subcarriers
 constexpr int kTcChunk   = 16;    // paths per K chunk (32 tf32 = one 128-byte swizzle row)
 
 struct TcCfg {
     int off_A, off_B, off_tY, off_tQ, off_wA, off_wB;   // byte offsets from the 1024-aligned base
     int nA, pcap, mtile;                                 // mtile = antenna rows per tile = tcgen05 N: 16, 32, 64 or 128
+    int nsub;                                            // 64-subcarrier sub-tiles per pipeline stage: 2 when mtile <= 64, else 1
     int sY, sQ, sA, sB;                                  // per-path table strides (float2 units), odd -> lanes that differ
                                                          // in the path index hit different shared-memory banks
     unsigned mul_mt, mul_bs0;
@@ -133,12 +135,16 @@ __device__ __forceinline__ void tc_store_rows(uint32_t taddr, float* out_rows, l
     uint32_t v[32];
     tmem_ld<NR>(taddr, v);
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-    #pragma unroll
-    for (int i = 0; i < NR; ++i)
-        if (r_first + i < M) __stcs(out_rows + (long long)i * pitch, __uint_as_float(v[i]));
+    if (r_first + NR <= M) {
+        #pragma unroll
+        for (int i = 0; i < NR; ++i) { __stcs(out_rows, __uint_as_float(v[i])); out_rows += pitch; }
+    } else {
+        #pragma unroll
+        for (int i = 0; i < NR; ++i) { if (r_first + i < M) __stcs(out_rows, __uint_as_float(v[i])); out_rows += pitch; }
+    }
 }
 
-struct TcTile { int row0, ct, acc; };
+struct TcTile { int row0, ct, acc; };   // ct: index of the 64-subcarrier segment, acc: first TMEM column of the accumulator
 
 __device__ __noinline__ void tc_epilogue(const TcTile& t, uint32_t tmem_base, float* out_u, long long pitch, int M, int mtile,
                                             int warp, int lane)
@@ -146,7 +152,7 @@ __device__ __noinline__ void tc_epilogue(const TcTile& t, uint32_t tmem_base, fl
     const int q = warp & 3, h = warp >> 2;                 // TMEM lane quarter (32 floats of the segment), half of the rows
     const int rows_half = mtile >> 1;                      // 64, 32, 16 or 8 antenna rows per warp
     const int r_base = t.row0 + h * rows_half;
-    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(t.acc * 128 + h * rows_half);
+    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(t.acc + h * rows_half);
     float* o = out_u + (long long)r_base * pitch + t.ct * kTcN + q * 32 + lane;
     if (rows_half == 64) {
         tc_store_rows<32>(taddr, o, pitch, r_base, M);
@@ -170,12 +176,14 @@ fd_tc_kernel(const DevDesc d, const TcCfg cfg, const int ksplit)
     __shared__ uint32_t tmem_base_s;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const bool is_worker = tid < kTcWorkers;          // warp 8 only issues MMAs
     const long long user = blockIdx.x / ksplit;
     const int ks = blockIdx.x % ksplit;
 
     unsigned char* sm = smem_raw + (((smem_u32(smem_raw) + 1023u) & ~1023u) - smem_u32(smem_raw));
-    unsigned char* sAhi = sm + cfg.off_A;                    // [mtile rows][128 B]   (also epilogue staging)
-    unsigned char* sAlo = sAhi + 128 * 128;
+    const int mtile_bytes = (cfg.mtile < 8 ? 8 : cfg.mtile) * 128;
+    unsigned char* sAhi = sm + cfg.off_A;                    // [mtile rows][128 B]
+    unsigned char* sAlo = sAhi + mtile_bytes;
     unsigned char* sBhi = sm + cfg.off_B;                    // [128 rows][128 B]
     unsigned char* sBlo = sBhi + kTcN * 128;
     float2* tY = reinterpret_cast<float2*>(sm + cfg.off_tY);
@@ -198,20 +206,25 @@ fd_tc_kernel(const DevDesc d, const TcCfg cfg, const int ksplit)
     const int np = sh.np;
     const int K = d.K, M = d.M;
     const int mtile = cfg.mtile;
-    const int n_ct = K / (kTcN / 2);
+    const int nsub = cfg.nsub;
+    const int n_seg = K / (kTcN / 2);                         // 64-subcarrier segments per row
+    const int n_ct = (n_seg + nsub - 1) / nsub;               // pipeline stages (column super-tiles) per row tile
     const int n_rt = (M + mtile - 1) / mtile;
     float* out_u = reinterpret_cast<float*>(d.out + user * (long long)M * K);
     const long long pitch = 2LL * K;                                  // floats per output row
     const int nq = d.Mr * d.bs1;
 
     if (np == 0) {
+        if (is_worker) {
         // users without contributing paths: zeros (channel.py:257,:269-271), coalesced
         float4* o = reinterpret_cast<float4*>(out_u);
         const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
         const int c4 = tid & 31, r0 = tid >> 5;                       // 32 float4 per row of a column tile, 8 rows per pass
-        for (int ct = ks; ct < n_ct; ct += ksplit) {
-            float4* ot = o + ct * (kTcN / 4) + c4;
-            for (int m = r0; m < M; m += kTcThreads / 32) __stcs(ot + (long long)m * (pitch / 4), z);
+        for (int ct = ks; ct < n_ct; ct += ksplit)
+            for (int sub = 0; sub < nsub && ct * nsub + sub < n_seg; ++sub) {
+                float4* ot = o + (ct * nsub + sub) * (kTcN / 4) + c4;
+                for (int m = r0; m < M; m += kTcWorkers / 32) __stcs(ot + (long long)m * (pitch / 4), z);
+            }
         }
     } else {
         // ---- per-user tables (phase reduced in float64 for every entry)
@@ -246,12 +259,14 @@ fd_tc_kernel(const DevDesc d, const TcCfg cfg, const int ksplit)
         uint32_t phase = 0;
         bool pending = false, have_prev = false;      // an MMA commit is outstanding / a tile waits for its epilogue
         TcTile prev = {0, 0, 0};
+        int prev_nsub = 0;
+        const int acc_stride = 128 / nsub;            // TMEM columns per accumulator; 2 * nsub accumulators in 256 columns
         int tile_idx = 0;
         // Operand builders: a thread owns one row (A) / one subcarrier (B) and a group of consecutive path slots, so
         // the row -> (rx element, z, y) decomposition is done once per tile, table reads of neighbouring lanes are
         // consecutive or broadcast, and two path slots (re,im,re,im) go out as one conflict-free 16-byte store.
         const int a_row  = tid & (mtile - 1);                       // antenna row of the tile this thread fills
-        const int a_ngrp = min(kTcThreads / mtile, 8);              // thread groups over the 16 path slots (>= 2 slots each)
+        const int a_ngrp = min(kTcWorkers / mtile, 8);              // thread groups over the 16 path slots (>= 2 slots each)
         const int a_grp  = tid / mtile;                             // threads with a_grp >= a_ngrp (mtile = 16) sit the A build out
         const int a_nsl  = kTcChunk / a_ngrp;                       // slots per thread: 8, 4, 2 or 2
         const int a_off0 = (a_row >> 3) * 1024 + (a_row & 7) * 128;
@@ -261,7 +276,8 @@ fd_tc_kernel(const DevDesc d, const TcCfg cfg, const int ksplit)
 
         bool a_valid = false;                         // A tile in smem is still current (single row tile, single chunk)
         for (int ct = ks; ct < n_ct; ct += ksplit) {
-            const int col0 = ct * (kTcN / 2);        // first subcarrier (complex column) of the tile
+            const int seg0 = ct * nsub;              // first 64-subcarrier segment of this stage
+            const int nsub_here = min(nsub, n_seg - seg0);
             bool b_valid = false;                     // B tile of chunk 0 currently in smem (single-chunk users reuse it)
             for (int rt = 0; rt < n_rt; ++rt) {
                 const int row0 = rt * mtile;
@@ -285,7 +301,7 @@ fd_tc_kernel(const DevDesc d, const TcCfg cfg, const int ksplit)
                         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     }
                     // ---- A_hi / A_lo
-                    if (a_grp < a_ngrp && !(a_valid && nchunk == 1 && n_rt == 1)) {
+                    if (is_worker && a_grp < a_ngrp && !(a_valid && nchunk == 1 && n_rt == 1)) {
                         const int j0 = a_grp * a_nsl;
                         const float2* tQp = tQ + (ch * kTcChunk + j0) * cfg.sQ + a_q;
                         const float2* tYp = tY + (ch * kTcChunk + j0) * cfg.sY + a_y;
@@ -300,9 +316,12 @@ fd_tc_kernel(const DevDesc d, const TcCfg cfg, const int ksplit)
                         }
                     }
                     // ---- B_hi / B_lo (rows 2c -> Re H, 2c+1 -> Im H)
-                    if (!(b_valid && nchunk == 1)) {
+                    if (is_worker && !(b_valid && nchunk == 1))
+                    for (int sub = 0; sub < nsub_here; ++sub) {
+                        unsigned char* sBh = sBhi + sub * (2 * kTcN * 128);
+                        unsigned char* sBl = sBh + kTcN * 128;
                         const int j0 = b_grp * 4;
-                        const int col = col0 + b_col;
+                        const int col = (seg0 + sub) * (kTcN / 2) + b_col;
                         const float2* wAp = wA + (ch * kTcChunk + j0) * cfg.sA + (col >> 4);
                         const float2* wBp = wB + (ch * kTcChunk + j0) * cfg.sB + (col & 15);
                         const int pmax = np - ch * kTcChunk - j0;
@@ -313,27 +332,32 @@ fd_tc_kernel(const DevDesc d, const TcCfg cfg, const int ksplit)
                             if (jj + 1 < pmax) w1 = cmul(wAp[(jj + 1) * cfg.sA], wBp[(jj + 1) * cfg.sB]);
                             const int sl = (j0 + jj) >> 1;
                             const int r0 = (2 * b_col) & 7;
-                            st_split_quad(sBhi, sBlo, b_off0 + (((sl ^ r0) & 7) << 4), w0.x, -w0.y, w1.x, -w1.y);
-                            st_split_quad(sBhi, sBlo, b_off0 + 128 + (((sl ^ (r0 + 1)) & 7) << 4), w0.y, w0.x, w1.y, w1.x);
+                            st_split_quad(sBh, sBl, b_off0 + (((sl ^ r0) & 7) << 4), w0.x, -w0.y, w1.x, -w1.y);
+                            st_split_quad(sBh, sBl, b_off0 + 128 + (((sl ^ (r0 + 1)) & 7) << 4), w0.y, w0.x, w1.y, w1.x);
                         }
                     }
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                     __syncthreads();
-                    if (tid == 0) {
+                    if (tid == kTcWorkers) {
                         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                         const int npc = min(kTcChunk, np - ch * kTcChunk);
                         const int ksteps = (2 * npc + 7) >> 3;
                         #pragma unroll 1
-                        for (int s = 0; s < 3; ++s) {
-                            const uint64_t da = (s == 2) ? dAlo : dAhi;
-                            const uint64_t db = (s == 1) ? dBlo : dBhi;
+                        for (int sub = 0; sub < nsub_here; ++sub) {
+                            const uint32_t acc_col = (uint32_t)((((tile_idx & 1) * nsub) + sub) * acc_stride);
+                            const uint64_t sub_off = (uint64_t)(sub * (2 * kTcN * 128) >> 4);       // descriptor address field is in 16-byte units
                             #pragma unroll 1
-                            for (int kk = 0; kk < ksteps; ++kk) {
-                                const uint32_t accum = (ch | s | kk) != 0;
-                                asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
-                                             "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}"
-                                             :: "r"(tmem_base + (uint32_t)((tile_idx & 1) * 128)), "l"(db + 2 * kk), "l"(da + 2 * kk), "r"(idesc), "r"(accum) : "memory");
+                            for (int s = 0; s < 3; ++s) {
+                                const uint64_t da = (s == 2) ? dAlo : dAhi;
+                                const uint64_t db = ((s == 1) ? dBlo : dBhi) + sub_off;
+                                #pragma unroll 1
+                                for (int kk = 0; kk < ksteps; ++kk) {
+                                    const uint32_t accum = (ch | s | kk) != 0;
+                                    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+                                                 "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}"
+                                                 :: "r"(tmem_base + acc_col), "l"(db + 2 * kk), "l"(da + 2 * kk), "r"(idesc), "r"(accum) : "memory");
+                                }
                             }
                         }
                         asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
@@ -341,13 +365,17 @@ fd_tc_kernel(const DevDesc d, const TcCfg cfg, const int ksplit)
                     }
                     pending = true;
                     if (ch == 0 && have_prev) {       // drain the previous tile while the tensor core works on this one
-                        tc_epilogue(prev, tmem_base, out_u, pitch, M, mtile, warp, lane);
+                        if (is_worker)
+                            for (int sub = 0; sub < prev_nsub; ++sub) {
+                                TcTile t = {prev.row0, prev.ct + sub, prev.acc + sub * acc_stride};
+                                tc_epilogue(t, tmem_base, out_u, pitch, M, mtile, warp, lane);
+                            }
                         have_prev = false;
                     }
                 }
                 b_valid = true;
                 a_valid = true;
-                prev.row0 = row0; prev.ct = ct; prev.acc = tile_idx & 1;
+                prev.row0 = row0; prev.ct = seg0; prev.acc = (tile_idx & 1) * nsub * acc_stride; prev_nsub = nsub_here;
                 have_prev = true;
                 ++tile_idx;
             }
@@ -356,7 +384,11 @@ fd_tc_kernel(const DevDesc d, const TcCfg cfg, const int ksplit)
             mbar_wait_parity(smem_u32(&mbar), phase);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         }
-        if (have_prev) tc_epilogue(prev, tmem_base, out_u, pitch, M, mtile, warp, lane);
+        if (have_prev && is_worker)
+            for (int sub = 0; sub < prev_nsub; ++sub) {
+                TcTile t = {prev.row0, prev.ct + sub, prev.acc + sub * acc_stride};
+                tc_epilogue(t, tmem_base, out_u, pitch, M, mtile, warp, lane);
+            }
     }
 
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
