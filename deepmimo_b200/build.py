@@ -47,7 +47,8 @@ def build_lib(force: bool = False, verbose: bool = False) -> str:
     """Compile deepmimo_b200/csrc/*.cu into deepmimo_b200/libdmk.so.  Returns the library path."""
     if not force and not is_stale():
         return LIB
-    cmd = [nvcc_path(), *NVCC_FLAGS, "-o", LIB + ".tmp", *[os.path.join(CSRC, s) for s in SOURCES]]
+    extra = os.environ.get("DMK_NVCC_EXTRA", "").split()          # e.g. -DDMK_TC_TRACE for the phase-timing debug build
+    cmd = [nvcc_path(), *NVCC_FLAGS, *extra, "-o", LIB + ".tmp", *[os.path.join(CSRC, s) for s in SOURCES]]
     proc = subprocess.run(cmd, capture_output=True, text=True)
     log = proc.stdout + proc.stderr
     with open(os.path.join(PKG, "build.log"), "w") as f:

@@ -123,6 +123,13 @@ int device_sm_count()
 
 extern "C" {
 
+#ifdef DMK_TC_TRACE
+int dmk_debug_tc_trace(long long* host_out, int n)
+{
+    return (int)cudaMemcpyFromSymbol(host_out, dmk::g_tc_trace, sizeof(long long) * n);
+}
+#endif
+
 const char* dmk_last_error(void) { return g_err; }
 int dmk_abi_version(void) { return DMK_ABI_VERSION; }
 int64_t dmk_launch_count(void) { return g_launches.load(); }
@@ -194,11 +201,11 @@ int dmk_channels_fd(const dmk_desc* desc, const float* power_dbw, const float* p
         tcfg.mul_mt = cfg.mul_mt; tcfg.mul_bs0 = cfg.mul_bs0;
         tc_smem += off;
     }
-    // Shapes with fewer than 128 rows per user leave the 128-row tensor tile half empty and rebuild B for every
-    // tile: the packed-FP32 kernel is faster there (profiles/README.md); DMK_FD_KERNEL=tc still forces it.
+    // Tiny arrays (M < 64) and FoV-sparse scenarios are per-user-overhead bound: the packed-FP32 kernel is faster there
+    // (profiles/README.md); DMK_FD_KERNEL=tc still forces the tensor-core kernel.
     const bool want_tc = force && !strcmp(force, "tc");
     const bool use_tc = affine && !d.has_time_axis && div_ok && (d.K % (kTcN / 2) == 0) && tc_smem <= 112 * 1024 &&
-                        !want_tile && !want_ffma && ((d.M >= 128 && !d.fov_any) || want_tc);   // FoV leaves few paths: FP32 kernel wins
+                        !want_tile && !want_ffma && ((d.M >= 64 && !d.fov_any) || want_tc);   // FoV leaves few paths, tiny arrays little output: FP32 kernel wins
     const bool use_fast = !use_tc && affine && !d.has_time_axis && div_ok && fast_smem <= 110 * 1024 && !want_tile;
     const int tile_w = use_tc ? (kTcN / 2) * tcfg.nsub : (use_fast ? kTKW : kTK);
     const int n_ct = (ncols + tile_w - 1) / tile_w;
@@ -221,7 +228,7 @@ int dmk_channels_fd(const dmk_desc* desc, const float* power_dbw, const float* p
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return cuda_fail(e, "fd_tc_kernel launch");
         g_launches.fetch_add(1);
-        snprintf(g_kernel, sizeof(g_kernel), "fd_tc_kernel<%dx128,3xtf32> grid=%lld ksplit=%lld smem=%zu", tcfg.mtile, grid, ksplit, tc_smem);
+        snprintf(g_kernel, sizeof(g_kernel), "fd_tc_kernel<%dx128,3xf16> grid=%lld ksplit=%lld smem=%zu", tcfg.mtile, grid, ksplit, tc_smem);
         return DMK_OK;
     }
     if (use_fast) {

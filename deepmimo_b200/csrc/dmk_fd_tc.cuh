@@ -28,6 +28,7 @@
 // The tensor pipe needs ~25-50 % of the HBM time of a tile, the operand generation a few hundred issue
 // cycles, so the kernel is bound by the output write; the second resident CTA fills the remaining bubbles.
 #pragma once
+#include <cuda_fp16.h>
 #include "dmk_fd.cuh"
 
 namespace dmk {
@@ -35,7 +36,7 @@ namespace dmk {
 constexpr int kTcWorkers = 256;   // 8 warps build operands and drain accumulators
 constexpr int kTcThreads = 288;   // + warp 8: issues the tcgen05.mma groups (never shares a warp with worker code)
 constexpr int kTcN       = 128;   // real output columns per tile = 64 subcarriers
-constexpr int kTcChunk   = 16;    // paths per K chunk (32 tf32 = one 128-byte swizzle row)
+constexpr int kTcSlots   = 32;    // path slots per operand row: 64 fp16 (re, im per path) = one 128-byte swizzle row
 
 struct TcCfg {
     int off_A, off_B, off_tY, off_tQ, off_wA, off_wB;   // byte offsets from the 1024-aligned base
@@ -81,6 +82,25 @@ __device__ __forceinline__ void st_split_pair(unsigned char* hi, unsigned char* 
     const float xl = x - __uint_as_float(xh), yl = y - __uint_as_float(yh);
     *reinterpret_cast<uint2*>(hi + off) = make_uint2(xh, yh);
     *reinterpret_cast<float2*>(lo + off) = make_float2(xl, yl);
+}
+
+// x = hi + lo in FP16: hi = fp16(x), lo = fp16(x - hi).  Operands are scaled to |x| <= 1 (unit phasors; path gains divided
+// by the user's largest |c_p|), so the absolute error per operand is <= max(2^-23 |x|, 2^-25) -- FP32-class relative to
+// the user's strongest path, which is what the per-user Frobenius criterion measures.  Four path slots (re,im x 4 =
+// 8 halves = 16 bytes) per store.
+__device__ __forceinline__ void st_split8_f16(unsigned char* hi, unsigned char* lo, int off, const float2 (&a)[4])
+{
+    uint32_t h[4], l[4];
+    #pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const __half2 hh = __floats2half2_rn(a[i].x, a[i].y);
+        const float2 back = __half22float2(hh);
+        const __half2 ll = __floats2half2_rn(a[i].x - back.x, a[i].y - back.y);
+        h[i] = *reinterpret_cast<const uint32_t*>(&hh);
+        l[i] = *reinterpret_cast<const uint32_t*>(&ll);
+    }
+    *reinterpret_cast<uint4*>(hi + off) = make_uint4(h[0], h[1], h[2], h[3]);
+    *reinterpret_cast<uint4*>(lo + off) = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
 __device__ __forceinline__ void st_split_quad(unsigned char* hi, unsigned char* lo, int off, float x0, float y0, float x1, float y1)
@@ -130,24 +150,41 @@ template <> __device__ __forceinline__ void tmem_ld<8>(uint32_t taddr, uint32_t 
 
 // Write NR antenna rows of one accumulator: register i = row (r_first + i), lanes = 32 consecutive floats of that row.
 template <int NR>
-__device__ __forceinline__ void tc_store_rows(uint32_t taddr, float* out_rows, long long pitch, int r_first, int M)
+__device__ __forceinline__ void tc_store_rows(uint32_t taddr, float* out_rows, long long pitch, int r_first, int M, float scale)
 {
     uint32_t v[32];
     tmem_ld<NR>(taddr, v);
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    #pragma unroll
+    for (int i = 0; i < NR; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * scale);      // undo the per-user operand scale
+    // explicit 64-bit pointer bump per row (2 instructions): left to itself the compiler re-derives base + i*pitch
+    const long long pitch_bytes = pitch * 4;
     if (r_first + NR <= M) {
         #pragma unroll
-        for (int i = 0; i < NR; ++i) { __stcs(out_rows, __uint_as_float(v[i])); out_rows += pitch; }
+        for (int i = 0; i < NR; ++i) {
+            asm volatile("st.global.cs.b32 [%0], %1;" :: "l"(out_rows), "r"(v[i]) : "memory");
+            asm volatile("add.s64 %0, %0, %1;" : "+l"(out_rows) : "l"(pitch_bytes));
+        }
     } else {
         #pragma unroll
-        for (int i = 0; i < NR; ++i) { if (r_first + i < M) __stcs(out_rows, __uint_as_float(v[i])); out_rows += pitch; }
+        for (int i = 0; i < NR; ++i) {
+            if (r_first + i < M) asm volatile("st.global.cs.b32 [%0], %1;" :: "l"(out_rows), "r"(v[i]) : "memory");
+            asm volatile("add.s64 %0, %0, %1;" : "+l"(out_rows) : "l"(pitch_bytes));
+        }
     }
 }
+
+#ifdef DMK_TC_TRACE
+__device__ long long g_tc_trace[4096];
+#define TC_TRACE(slot) do { if (trace_on && (slot) < 4096) g_tc_trace[(slot)] = clock64(); } while (0)
+#else
+#define TC_TRACE(slot) do { } while (0)
+#endif
 
 struct TcTile { int row0, ct, acc; };   // ct: index of the 64-subcarrier segment, acc: first TMEM column of the accumulator
 
 __device__ __noinline__ void tc_epilogue(const TcTile& t, uint32_t tmem_base, float* out_u, long long pitch, int M, int mtile,
-                                            int warp, int lane)
+                                            int warp, int lane, float scale)
 {
     const int q = warp & 3, h = warp >> 2;                 // TMEM lane quarter (32 floats of the segment), half of the rows
     const int rows_half = mtile >> 1;                      // 64, 32, 16 or 8 antenna rows per warp
@@ -155,14 +192,14 @@ __device__ __noinline__ void tc_epilogue(const TcTile& t, uint32_t tmem_base, fl
     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(t.acc + h * rows_half);
     float* o = out_u + (long long)r_base * pitch + t.ct * kTcN + q * 32 + lane;
     if (rows_half == 64) {
-        tc_store_rows<32>(taddr, o, pitch, r_base, M);
-        tc_store_rows<32>(taddr + 32, o + 32 * pitch, pitch, r_base + 32, M);
+        tc_store_rows<32>(taddr, o, pitch, r_base, M, scale);
+        tc_store_rows<32>(taddr + 32, o + 32 * pitch, pitch, r_base + 32, M, scale);
     } else if (rows_half == 32) {
-        tc_store_rows<32>(taddr, o, pitch, r_base, M);
+        tc_store_rows<32>(taddr, o, pitch, r_base, M, scale);
     } else if (rows_half == 16) {
-        tc_store_rows<16>(taddr, o, pitch, r_base, M);
+        tc_store_rows<16>(taddr, o, pitch, r_base, M, scale);
     } else {
-        tc_store_rows<8>(taddr, o, pitch, r_base, M);
+        tc_store_rows<8>(taddr, o, pitch, r_base, M, scale);
     }
 }
 
@@ -174,17 +211,18 @@ fd_tc_kernel(const DevDesc d, const TcCfg cfg, const int ksplit)
     __shared__ PrologueScratch psc;
     __shared__ uint64_t mbar;
     __shared__ uint32_t tmem_base_s;
+    __shared__ float scale_s;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const bool is_worker = tid < kTcWorkers;          // warp 8 only issues MMAs
     const long long user = blockIdx.x / ksplit;
     const int ks = blockIdx.x % ksplit;
+    const int mtile = cfg.mtile, nsub = cfg.nsub;
 
     unsigned char* sm = smem_raw + (((smem_u32(smem_raw) + 1023u) & ~1023u) - smem_u32(smem_raw));
-    const int mtile_bytes = (cfg.mtile < 8 ? 8 : cfg.mtile) * 128;
-    unsigned char* sAhi = sm + cfg.off_A;                    // [mtile rows][128 B]
-    unsigned char* sAlo = sAhi + mtile_bytes;
-    unsigned char* sBhi = sm + cfg.off_B;                    // [128 rows][128 B]
+    unsigned char* sAhi = sm + cfg.off_A;                    // [mtile rows][128 B]: 32 path slots x (re, im) fp16
+    unsigned char* sAlo = sAhi + mtile * 128;
+    unsigned char* sBhi = sm + cfg.off_B;                    // per sub-tile: [128 rows][128 B] hi, then lo
     unsigned char* sBlo = sBhi + kTcN * 128;
     float2* tY = reinterpret_cast<float2*>(sm + cfg.off_tY);
     float2* tQ = reinterpret_cast<float2*>(sm + cfg.off_tQ);
@@ -205,28 +243,36 @@ fd_tc_kernel(const DevDesc d, const TcCfg cfg, const int ksplit)
     const uint32_t tmem_base = tmem_base_s;
     const int np = sh.np;
     const int K = d.K, M = d.M;
-    const int mtile = cfg.mtile;
-    const int nsub = cfg.nsub;
     const int n_seg = K / (kTcN / 2);                         // 64-subcarrier segments per row
     const int n_ct = (n_seg + nsub - 1) / nsub;               // pipeline stages (column super-tiles) per row tile
     const int n_rt = (M + mtile - 1) / mtile;
     float* out_u = reinterpret_cast<float*>(d.out + user * (long long)M * K);
-    const long long pitch = 2LL * K;                                  // floats per output row
+    const long long pitch = 2LL * K;                          // floats per output row
     const int nq = d.Mr * d.bs1;
 
     if (np == 0) {
-        if (is_worker) {
         // users without contributing paths: zeros (channel.py:257,:269-271), coalesced
-        float4* o = reinterpret_cast<float4*>(out_u);
-        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-        const int c4 = tid & 31, r0 = tid >> 5;                       // 32 float4 per row of a column tile, 8 rows per pass
-        for (int ct = ks; ct < n_ct; ct += ksplit)
-            for (int sub = 0; sub < nsub && ct * nsub + sub < n_seg; ++sub) {
-                float4* ot = o + (ct * nsub + sub) * (kTcN / 4) + c4;
-                for (int m = r0; m < M; m += kTcWorkers / 32) __stcs(ot + (long long)m * (pitch / 4), z);
-            }
+        if (is_worker) {
+            float4* o = reinterpret_cast<float4*>(out_u);
+            const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+            const int c4 = tid & 31, r0 = tid >> 5;           // 32 float4 per row of a segment, 8 rows per pass
+            for (int ct = ks; ct < n_ct; ct += ksplit)
+                for (int sub = 0; sub < nsub && ct * nsub + sub < n_seg; ++sub) {
+                    float4* ot = o + (ct * nsub + sub) * (kTcN / 4) + c4;
+                    for (int m = r0; m < M; m += kTcWorkers / 32) __stcs(ot + (long long)m * (pitch / 4), z);
+                }
         }
     } else {
+        // ---- per-user operand scale: largest |c_p| component (FP16 operands live in [-1, 1])
+        if (warp == 0) {
+            float mx = (lane < np) ? fmaxf(fabsf(sh.c[lane].x), fabsf(sh.c[lane].y)) : 0.f;
+            #pragma unroll
+            for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+            if (lane == 0) scale_s = mx;
+        }
+        __syncthreads();
+        const float scale = scale_s;
+        const float inv_scale = 1.0f / scale;
         // ---- per-user tables (phase reduced in float64 for every entry)
         {
             const int bs0 = d.bs0, bs1 = d.bs1, nA = cfg.nA;
@@ -238,7 +284,8 @@ fd_tc_kernel(const DevDesc d, const TcCfg cfg, const int ksplit)
                 const int p = e / nq, q = e - p * nq;
                 const int r = q / bs1, z = q - r * bs1;
                 const int yr = r % d.ue0, zr = r / d.ue0;
-                tQ[p * cfg.sQ + q] = cmul(sh.c[p], phasor_cycles((double)z * sh.v[0][p] + (double)yr * sh.u[1][p] + (double)zr * sh.v[1][p]));
+                const float2 cs = make_float2(sh.c[p].x * inv_scale, sh.c[p].y * inv_scale);
+                tQ[p * cfg.sQ + q] = cmul(cs, phasor_cycles((double)z * sh.v[0][p] + (double)yr * sh.u[1][p] + (double)zr * sh.v[1][p]));
             }
             for (int e = tid; e < np * nA; e += kTcThreads) {
                 const int p = e / nA, a = e - p * nA;
@@ -251,128 +298,141 @@ fd_tc_kernel(const DevDesc d, const TcCfg cfg, const int ksplit)
         }
         __syncthreads();
 
-        const int nchunk = (np + kTcChunk - 1) / kTcChunk;
-        // instruction descriptor: D = F32, A = B = TF32, both K-major, N = antenna rows of the tile, M = 128 subcarrier floats
-        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(mtile >> 3) << 17) | ((uint32_t)(kTcN >> 4) << 24);
+        const int ksteps = (np + 7) >> 3;                     // 16 fp16 (8 path slots) per MMA
+        const int nslot = ksteps * 8;                         // slots the tensor core reads; slots >= np are written as zeros
+        // instruction descriptor: D = F32, A = B = F16 (format 0), both K-major, N = antenna rows of the tile, M = 128 floats
+        const uint32_t idesc = (1u << 4) | ((uint32_t)(mtile >> 3) << 17) | ((uint32_t)(kTcN >> 4) << 24);
         const uint64_t dAhi = umma_desc_kmajor_sw128(smem_u32(sAhi)), dAlo = umma_desc_kmajor_sw128(smem_u32(sAlo));
         const uint64_t dBhi = umma_desc_kmajor_sw128(smem_u32(sBhi)), dBlo = umma_desc_kmajor_sw128(smem_u32(sBlo));
         uint32_t phase = 0;
-        bool pending = false, have_prev = false;      // an MMA commit is outstanding / a tile waits for its epilogue
+#ifdef DMK_TC_TRACE
+        const bool trace_cta = (blockIdx.x == gridDim.x / 2);
+        const bool trace_on = trace_cta && (tid == 0 || tid == kTcWorkers);
+        const int tb = (tid == 0) ? 0 : 8;
+        int stage_no = 0;
+        if (trace_on && tid == 0) { g_tc_trace[4095] = np; }
+#endif
+        bool pending = false, have_prev = false;      // an MMA commit is outstanding / a stage waits for its epilogue
         TcTile prev = {0, 0, 0};
         int prev_nsub = 0;
         const int acc_stride = 128 / nsub;            // TMEM columns per accumulator; 2 * nsub accumulators in 256 columns
         int tile_idx = 0;
-        // Operand builders: a thread owns one row (A) / one subcarrier (B) and a group of consecutive path slots, so
-        // the row -> (rx element, z, y) decomposition is done once per tile, table reads of neighbouring lanes are
-        // consecutive or broadcast, and two path slots (re,im,re,im) go out as one conflict-free 16-byte store.
-        const int a_row  = tid & (mtile - 1);                       // antenna row of the tile this thread fills
-        const int a_ngrp = min(kTcWorkers / mtile, 8);              // thread groups over the 16 path slots (>= 2 slots each)
-        const int a_grp  = tid / mtile;                             // threads with a_grp >= a_ngrp (mtile = 16) sit the A build out
-        const int a_nsl  = kTcChunk / a_ngrp;                       // slots per thread: 8, 4, 2 or 2
-        const int a_off0 = (a_row >> 3) * 1024 + (a_row & 7) * 128;
-        const int b_col  = tid & 63;                                // subcarrier of the tile this thread fills
-        const int b_grp  = tid >> 6;                                // 0..3 -> slots 4*b_grp .. +3
-        const int b_off0 = ((2 * b_col) >> 3) * 1024 + ((2 * b_col) & 7) * 128;      // row 2*b_col; row 2*b_col+1 is +128 bytes
 
-        bool a_valid = false;                         // A tile in smem is still current (single row tile, single chunk)
+        // Operand builders: a thread owns one antenna row (A) / one subcarrier (B) and a run of consecutive path slots, so the
+        // row -> (rx element, z, y) decomposition is done once per tile, table reads of neighbouring lanes are consecutive
+        // or broadcast, and four path slots (8 halves) go out as one conflict-free 16-byte store.
+        const int a_row  = tid & (mtile - 1);
+        const int a_ngrp = min(kTcWorkers / mtile, 8);
+        const int a_grp  = tid / mtile;                       // >= a_ngrp (mtile = 16) sits the A build out
+        const int a_nsl  = kTcSlots / a_ngrp;                 // 16, 8, 4, 4 slots per thread
+        const int a_off0 = (a_row >> 3) * 1024 + (a_row & 7) * 128;
+        const int b_col  = tid & 63;
+        const int b_grp  = tid >> 6;                          // 0..3 -> slots 8*b_grp .. +7
+        const int b_row0 = 2 * b_col;                         // rows 2c (Re H) and 2c + 1 (Im H)
+        const int b_off0 = (b_row0 >> 3) * 1024 + (b_row0 & 7) * 128;
+
+        bool a_valid = false;                         // A tile in smem is still current (single row tile)
         for (int ct = ks; ct < n_ct; ct += ksplit) {
-            const int seg0 = ct * nsub;              // first 64-subcarrier segment of this stage
+            const int seg0 = ct * nsub;
             const int nsub_here = min(nsub, n_seg - seg0);
-            bool b_valid = false;                     // B tile of chunk 0 currently in smem (single-chunk users reuse it)
+            bool b_valid = false;                     // B tiles of this column stage are in smem (reused by every row tile)
             for (int rt = 0; rt < n_rt; ++rt) {
                 const int row0 = rt * mtile;
-                // row decomposition of this thread's row (once per tile)
-                const int am = row0 + a_row;
-                const bool a_ok = am < M;
-                int a_q = 0, a_y = 0;
-                if (a_ok) {
-                    const unsigned mm = (unsigned)am;
-                    const unsigned rr = cfg.mul_mt ? __umulhi(mm, cfg.mul_mt) : mm;
-                    const unsigned t = mm - rr * (unsigned)d.Mt;
-                    const unsigned zt = cfg.mul_bs0 ? __umulhi(t, cfg.mul_bs0) : t;
-                    a_y = (int)(t - zt * (unsigned)d.bs0);
-                    a_q = (int)(rr * (unsigned)d.bs1 + zt);
+                TC_TRACE(16 * stage_no + tb + 0);
+                if (pending) {                        // the previous MMA group has finished reading A/B (and writing its accumulator)
+                    if (!is_worker) mbar_wait_parity(smem_u32(&mbar), phase);
+                    asm volatile("bar.sync 1, %0;" :: "n"(kTcThreads) : "memory");
+                    phase ^= 1;
+                    pending = false;
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 }
-                for (int ch = 0; ch < nchunk; ++ch) {
-                    if (pending) {                    // the previous MMA group has finished reading A/B (and writing its accumulator)
-                        mbar_wait_parity(smem_u32(&mbar), phase);
-                        phase ^= 1;
-                        pending = false;
-                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                TC_TRACE(16 * stage_no + tb + 1);
+                // ---- A_hi / A_lo: antenna rows x path slots
+                if (is_worker && a_grp < a_ngrp && !(a_valid && n_rt == 1)) {
+                    const int am = row0 + a_row;
+                    const bool a_ok = am < M;
+                    int a_q = 0, a_y = 0;
+                    if (a_ok) {
+                        const unsigned mm = (unsigned)am;
+                        const unsigned rr = cfg.mul_mt ? __umulhi(mm, cfg.mul_mt) : mm;
+                        const unsigned t = mm - rr * (unsigned)d.Mt;
+                        const unsigned zt = cfg.mul_bs0 ? __umulhi(t, cfg.mul_bs0) : t;
+                        a_y = (int)(t - zt * (unsigned)d.bs0);
+                        a_q = (int)(rr * (unsigned)d.bs1 + zt);
                     }
-                    // ---- A_hi / A_lo
-                    if (is_worker && a_grp < a_ngrp && !(a_valid && nchunk == 1 && n_rt == 1)) {
-                        const int j0 = a_grp * a_nsl;
-                        const float2* tQp = tQ + (ch * kTcChunk + j0) * cfg.sQ + a_q;
-                        const float2* tYp = tY + (ch * kTcChunk + j0) * cfg.sY + a_y;
-                        const int pmax = np - ch * kTcChunk - j0;                      // slots < pmax hold a path
-                        #pragma unroll 2
-                        for (int jj = 0; jj < a_nsl; jj += 2) {
-                            float2 a0 = make_float2(0.f, 0.f), a1 = make_float2(0.f, 0.f);
-                            if (a_ok && jj < pmax)     a0 = cmul(tQp[jj * cfg.sQ], tYp[jj * cfg.sY]);
-                            if (a_ok && jj + 1 < pmax) a1 = cmul(tQp[(jj + 1) * cfg.sQ], tYp[(jj + 1) * cfg.sY]);
-                            const int off = a_off0 + (((((j0 + jj) >> 1) ^ (a_row & 7)) & 7) << 4);
-                            st_split_quad(sAhi, sAlo, off, a0.x, a0.y, a1.x, a1.y);
+                    const int j0 = a_grp * a_nsl;
+                    #pragma unroll 1
+                    for (int jj = 0; jj < a_nsl && j0 + jj < nslot; jj += 4) {
+                        float2 a[4];
+                        #pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const int p = j0 + jj + i;
+                            a[i] = (a_ok && p < np) ? cmul(tQ[p * cfg.sQ + a_q], tY[p * cfg.sY + a_y]) : make_float2(0.f, 0.f);
                         }
+                        st_split8_f16(sAhi, sAlo, a_off0 + (((((j0 + jj) >> 2) ^ (a_row & 7)) & 7) << 4), a);
                     }
-                    // ---- B_hi / B_lo (rows 2c -> Re H, 2c+1 -> Im H)
-                    if (is_worker && !(b_valid && nchunk == 1))
+                }
+                // ---- B_hi / B_lo per sub-tile (rows 2c -> Re H, 2c+1 -> Im H)
+                if (is_worker && !b_valid)
                     for (int sub = 0; sub < nsub_here; ++sub) {
                         unsigned char* sBh = sBhi + sub * (2 * kTcN * 128);
                         unsigned char* sBl = sBh + kTcN * 128;
-                        const int j0 = b_grp * 4;
                         const int col = (seg0 + sub) * (kTcN / 2) + b_col;
-                        const float2* wAp = wA + (ch * kTcChunk + j0) * cfg.sA + (col >> 4);
-                        const float2* wBp = wB + (ch * kTcChunk + j0) * cfg.sB + (col & 15);
-                        const int pmax = np - ch * kTcChunk - j0;
-                        #pragma unroll
-                        for (int jj = 0; jj < 4; jj += 2) {
-                            float2 w0 = make_float2(0.f, 0.f), w1 = make_float2(0.f, 0.f);
-                            if (jj < pmax)     w0 = cmul(wAp[jj * cfg.sA], wBp[jj * cfg.sB]);
-                            if (jj + 1 < pmax) w1 = cmul(wAp[(jj + 1) * cfg.sA], wBp[(jj + 1) * cfg.sB]);
-                            const int sl = (j0 + jj) >> 1;
-                            const int r0 = (2 * b_col) & 7;
-                            st_split_quad(sBh, sBl, b_off0 + (((sl ^ r0) & 7) << 4), w0.x, -w0.y, w1.x, -w1.y);
-                            st_split_quad(sBh, sBl, b_off0 + 128 + (((sl ^ (r0 + 1)) & 7) << 4), w0.y, w0.x, w1.y, w1.x);
-                        }
-                    }
-                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                    __syncthreads();
-                    if (tid == kTcWorkers) {
-                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                        const int npc = min(kTcChunk, np - ch * kTcChunk);
-                        const int ksteps = (2 * npc + 7) >> 3;
+                        const int j0 = b_grp * 8;
                         #pragma unroll 1
-                        for (int sub = 0; sub < nsub_here; ++sub) {
-                            const uint32_t acc_col = (uint32_t)((((tile_idx & 1) * nsub) + sub) * acc_stride);
-                            const uint64_t sub_off = (uint64_t)(sub * (2 * kTcN * 128) >> 4);       // descriptor address field is in 16-byte units
+                        for (int jj = 0; jj < 8 && j0 + jj < nslot; jj += 4) {
+                            float2 re[4], im[4];
+                            #pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                const int p = j0 + jj + i;
+                                float2 w = make_float2(0.f, 0.f);
+                                if (p < np) w = cmul(wA[p * cfg.sA + (col >> 4)], wB[p * cfg.sB + (col & 15)]);
+                                re[i] = make_float2(w.x, -w.y);
+                                im[i] = make_float2(w.y, w.x);
+                            }
+                            const int chunk = (j0 + jj) >> 2;
+                            st_split8_f16(sBh, sBl, b_off0 + (((chunk ^ (b_row0 & 7)) & 7) << 4), re);
+                            st_split8_f16(sBh, sBl, b_off0 + 128 + (((chunk ^ ((b_row0 + 1) & 7)) & 7) << 4), im);
+                        }
+                    }
+                TC_TRACE(16 * stage_no + tb + 2);
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncthreads();
+                TC_TRACE(16 * stage_no + tb + 3);
+                if (tid == kTcWorkers) {
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    #pragma unroll 1
+                    for (int sub = 0; sub < nsub_here; ++sub) {
+                        const uint32_t acc_col = (uint32_t)((((tile_idx & 1) * nsub) + sub) * acc_stride);
+                        const uint64_t sub_off = (uint64_t)(sub * (2 * kTcN * 128) >> 4);       // descriptor address field: 16-byte units
+                        #pragma unroll 1
+                        for (int s = 0; s < 3; ++s) {                                           // hi*hi, lo*hi, hi*lo
+                            const uint64_t da = (s == 2) ? dAlo : dAhi;
+                            const uint64_t db = ((s == 1) ? dBlo : dBhi) + sub_off;
                             #pragma unroll 1
-                            for (int s = 0; s < 3; ++s) {
-                                const uint64_t da = (s == 2) ? dAlo : dAhi;
-                                const uint64_t db = ((s == 1) ? dBlo : dBhi) + sub_off;
-                                #pragma unroll 1
-                                for (int kk = 0; kk < ksteps; ++kk) {
-                                    const uint32_t accum = (ch | s | kk) != 0;
-                                    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
-                                                 "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}"
-                                                 :: "r"(tmem_base + acc_col), "l"(db + 2 * kk), "l"(da + 2 * kk), "r"(idesc), "r"(accum) : "memory");
-                                }
+                            for (int kk = 0; kk < ksteps; ++kk) {
+                                const uint32_t accum = (s | kk) != 0;
+                                asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+                                             "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}"
+                                             :: "r"(tmem_base + acc_col), "l"(db + 2 * kk), "l"(da + 2 * kk), "r"(idesc), "r"(accum) : "memory");
                             }
                         }
-                        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
-                                     :: "r"(smem_u32(&mbar)) : "memory");
                     }
-                    pending = true;
-                    if (ch == 0 && have_prev) {       // drain the previous tile while the tensor core works on this one
-                        if (is_worker)
-                            for (int sub = 0; sub < prev_nsub; ++sub) {
-                                TcTile t = {prev.row0, prev.ct + sub, prev.acc + sub * acc_stride};
-                                tc_epilogue(t, tmem_base, out_u, pitch, M, mtile, warp, lane);
-                            }
-                        have_prev = false;
-                    }
+                    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
+                                 :: "r"(smem_u32(&mbar)) : "memory");
                 }
+                pending = true;
+                if (!is_worker) TC_TRACE(16 * stage_no + tb + 4);
+                if (have_prev && is_worker)           // drain the previous stage while the tensor core works on this one
+                    for (int sub = 0; sub < prev_nsub; ++sub) {
+                        TcTile t = {prev.row0, prev.ct + sub, prev.acc + sub * acc_stride};
+                        tc_epilogue(t, tmem_base, out_u, pitch, M, mtile, warp, lane, scale);
+                    }
+                if (is_worker) TC_TRACE(16 * stage_no + tb + 4);
+#ifdef DMK_TC_TRACE
+                ++stage_no;
+#endif
                 b_valid = true;
                 a_valid = true;
                 prev.row0 = row0; prev.ct = seg0; prev.acc = (tile_idx & 1) * nsub * acc_stride; prev_nsub = nsub_here;
@@ -381,13 +441,14 @@ fd_tc_kernel(const DevDesc d, const TcCfg cfg, const int ksplit)
             }
         }
         if (pending) {
-            mbar_wait_parity(smem_u32(&mbar), phase);
+            if (!is_worker) mbar_wait_parity(smem_u32(&mbar), phase);
+            asm volatile("bar.sync 1, %0;" :: "n"(kTcThreads) : "memory");
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         }
         if (have_prev && is_worker)
             for (int sub = 0; sub < prev_nsub; ++sub) {
                 TcTile t = {prev.row0, prev.ct + sub, prev.acc + sub * acc_stride};
-                tc_epilogue(t, tmem_base, out_u, pitch, M, mtile, warp, lane);
+                tc_epilogue(t, tmem_base, out_u, pitch, M, mtile, warp, lane, scale);
             }
     }
 

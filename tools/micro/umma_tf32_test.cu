@@ -110,6 +110,66 @@ __global__ void __launch_bounds__(128) umma_test(const float* __restrict__ A, co
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"(N));
 }
 
+template <int M, int N>
+__global__ void __launch_bounds__(128) umma_time(int nrep, long long* t_out)
+{
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ uint64_t mbar;
+    __shared__ uint32_t tmem_base_s;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* sm = smem_raw + (base - smem_u32(smem_raw));
+    for (int e = tid; e < (128 + N) * 32; e += 128) reinterpret_cast<float*>(sm)[e] = 0.001f * (e & 255);
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(&tmem_base_s)), "r"(N));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&mbar)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = tmem_base_s;
+    if (tid == 0) {
+        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+        const uint64_t da = make_kmajor_sw128_desc(smem_u32(sm)), db = make_kmajor_sw128_desc(smem_u32(sm + 128 * 128));
+        const long long t0 = clock64();
+        for (int r = 0; r < nrep; ++r)
+            for (int j = 0; j < 4; ++j) {
+                const uint32_t accum = (r | j) != 0;
+                asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+                             "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}"
+                             :: "r"(tmem_base), "l"(da + 2 * j), "l"(db + 2 * j), "r"(idesc), "r"(accum) : "memory");
+            }
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(&mbar)) : "memory");
+        const long long t1 = clock64();
+        mbar_wait(smem_u32(&mbar), 0, 1 << 24);
+        const long long t2 = clock64();
+        t_out[0] = t1 - t0; t_out[1] = t2 - t0;
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"(N));
+}
+
+template <int M, int N>
+static void run_time()
+{
+    long long* d; cudaMalloc(&d, 16);
+    const int smem = 128 * 128 + N * 128 + 1024;
+    cudaFuncSetAttribute(umma_time<M, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    for (int nrep : {1, 3, 12, 48}) {
+        long long h[2] = {0, 0};
+        for (int it = 0; it < 2; ++it) { umma_time<M, N><<<1, 128, smem>>>(nrep, d); cudaDeviceSynchronize(); }
+        cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost);
+        printf("tf32 SS MMA M=%d N=%d K=8: %3d MMAs: issue %6lld cyc, complete %6lld cyc  (%.1f cyc/MMA)\n", M, N, 4 * nrep, h[0], h[1], (double)h[1] / (4 * nrep));
+    }
+    cudaFree(d);
+}
+
 static float to_tf32(float x)
 {
     uint32_t u; memcpy(&u, &x, 4);
@@ -161,6 +221,7 @@ int main()
     rc |= run<128, 256>(4);
     rc |= run<64, 128>(4);
     rc |= run<64, 128>(1);
+    run_time<128, 128>(); run_time<128, 64>(); run_time<128, 256>(); run_time<64, 128>();
     printf(rc ? "UMMA TEST FAILED\n" : "UMMA TEST PASSED\n");
     return rc;
 }
