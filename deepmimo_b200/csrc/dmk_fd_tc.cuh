@@ -322,9 +322,8 @@ fd_tc_kernel(const DevDesc d, const TcCfg cfg, const int ksplit)
         // row -> (rx element, z, y) decomposition is done once per tile, table reads of neighbouring lanes are consecutive
         // or broadcast, and four path slots (8 halves) go out as one conflict-free 16-byte store.
         const int a_row  = tid & (mtile - 1);
-        const int a_ngrp = min(kTcWorkers / mtile, 8);
-        const int a_grp  = tid / mtile;                       // >= a_ngrp (mtile = 16) sits the A build out
-        const int a_nsl  = kTcSlots / a_ngrp;                 // 16, 8, 4, 4 slots per thread
+        const int a_ngrp = kTcWorkers / mtile;                // thread groups per antenna row: 2, 4, 8 or 16
+        const int a_grp  = tid / mtile;
         const int a_off0 = (a_row >> 3) * 1024 + (a_row & 7) * 128;
         const int b_col  = tid & 63;
         const int b_grp  = tid >> 6;                          // 0..3 -> slots 8*b_grp .. +7
@@ -348,7 +347,7 @@ fd_tc_kernel(const DevDesc d, const TcCfg cfg, const int ksplit)
                 }
                 TC_TRACE(16 * stage_no + tb + 1);
                 // ---- A_hi / A_lo: antenna rows x path slots
-                if (is_worker && a_grp < a_ngrp && !(a_valid && n_rt == 1)) {
+                if (is_worker && !(a_valid && n_rt == 1)) {
                     const int am = row0 + a_row;
                     const bool a_ok = am < M;
                     int a_q = 0, a_y = 0;
@@ -360,41 +359,42 @@ fd_tc_kernel(const DevDesc d, const TcCfg cfg, const int ksplit)
                         a_y = (int)(t - zt * (unsigned)d.bs0);
                         a_q = (int)(rr * (unsigned)d.bs1 + zt);
                     }
-                    const int j0 = a_grp * a_nsl;
+                    // slot quads are dealt round-robin to the thread groups of a row so that every thread has work
+                    // whatever the number of paths: quad = a_grp, a_grp + a_ngrp, ... < nslot / 4
                     #pragma unroll 1
-                    for (int jj = 0; jj < a_nsl && j0 + jj < nslot; jj += 4) {
+                    for (int qd = a_grp; qd * 4 < nslot; qd += a_ngrp) {
                         float2 a[4];
                         #pragma unroll
                         for (int i = 0; i < 4; ++i) {
-                            const int p = j0 + jj + i;
+                            const int p = qd * 4 + i;
                             a[i] = (a_ok && p < np) ? cmul(tQ[p * cfg.sQ + a_q], tY[p * cfg.sY + a_y]) : make_float2(0.f, 0.f);
                         }
-                        st_split8_f16(sAhi, sAlo, a_off0 + (((((j0 + jj) >> 2) ^ (a_row & 7)) & 7) << 4), a);
+                        st_split8_f16(sAhi, sAlo, a_off0 + (((qd ^ (a_row & 7)) & 7) << 4), a);
                     }
                 }
                 // ---- B_hi / B_lo per sub-tile (rows 2c -> Re H, 2c+1 -> Im H)
-                if (is_worker && !b_valid)
-                    for (int sub = 0; sub < nsub_here; ++sub) {
+                if (is_worker && !b_valid) {
+                    // (sub-tile, slot quad) pairs dealt round-robin to the four thread groups of a subcarrier
+                    const int nq4 = nslot >> 2;
+                    #pragma unroll 1
+                    for (int pi = b_grp; pi < nsub_here * nq4; pi += 4) {
+                        const int sub = pi / nq4, qd = pi - sub * nq4;
                         unsigned char* sBh = sBhi + sub * (2 * kTcN * 128);
                         unsigned char* sBl = sBh + kTcN * 128;
                         const int col = (seg0 + sub) * (kTcN / 2) + b_col;
-                        const int j0 = b_grp * 8;
-                        #pragma unroll 1
-                        for (int jj = 0; jj < 8 && j0 + jj < nslot; jj += 4) {
-                            float2 re[4], im[4];
-                            #pragma unroll
-                            for (int i = 0; i < 4; ++i) {
-                                const int p = j0 + jj + i;
-                                float2 w = make_float2(0.f, 0.f);
-                                if (p < np) w = cmul(wA[p * cfg.sA + (col >> 4)], wB[p * cfg.sB + (col & 15)]);
-                                re[i] = make_float2(w.x, -w.y);
-                                im[i] = make_float2(w.y, w.x);
-                            }
-                            const int chunk = (j0 + jj) >> 2;
-                            st_split8_f16(sBh, sBl, b_off0 + (((chunk ^ (b_row0 & 7)) & 7) << 4), re);
-                            st_split8_f16(sBh, sBl, b_off0 + 128 + (((chunk ^ ((b_row0 + 1) & 7)) & 7) << 4), im);
+                        float2 re[4], im[4];
+                        #pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const int p = qd * 4 + i;
+                            float2 w = make_float2(0.f, 0.f);
+                            if (p < np) w = cmul(wA[p * cfg.sA + (col >> 4)], wB[p * cfg.sB + (col & 15)]);
+                            re[i] = make_float2(w.x, -w.y);
+                            im[i] = make_float2(w.y, w.x);
                         }
+                        st_split8_f16(sBh, sBl, b_off0 + (((qd ^ (b_row0 & 7)) & 7) << 4), re);
+                        st_split8_f16(sBh, sBl, b_off0 + 128 + (((qd ^ ((b_row0 + 1) & 7)) & 7) << 4), im);
                     }
+                }
                 TC_TRACE(16 * stage_no + tb + 2);
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
