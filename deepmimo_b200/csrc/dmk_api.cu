@@ -190,6 +190,10 @@ int dmk_channels_fd(const dmk_desc* desc, const float* power_dbw, const float* p
         tcfg.pcap = pc;
         tcfg.nA = (d.K + 15) / 16;
         tcfg.mtile = d.M >= 128 ? 128 : (d.M > 32 ? 64 : (d.M > 16 ? 32 : 16));   // antenna rows per tile = tcgen05 N
+        if (const char* mt = getenv("DMK_TC_MTILE")) {      // experiment knob: force the antenna-row tile (16/32/64/128)
+            const int v = atoi(mt);
+            if (v == 16 || v == 32 || v == 64 || v == 128) tcfg.mtile = v;
+        }
         tcfg.nsub = tcfg.mtile <= 64 ? 2 : 1;                // keep a pipeline stage at 64 KB of output for small arrays
         tcfg.off_A  = take((size_t)2 * tcfg.mtile * 128);    // A_hi, A_lo
         tcfg.off_B  = take((size_t)tcfg.nsub * 2 * kTcN * 128);   // B_hi, B_lo per sub-tile
@@ -204,7 +208,7 @@ int dmk_channels_fd(const dmk_desc* desc, const float* power_dbw, const float* p
     // Tiny arrays (M < 64) and FoV-sparse scenarios are per-user-overhead bound: the packed-FP32 kernel is faster there
     // (profiles/README.md); DMK_FD_KERNEL=tc still forces the tensor-core kernel.
     const bool want_tc = force && !strcmp(force, "tc");
-    const bool use_tc = affine && !d.has_time_axis && div_ok && (d.K % (kTcN / 2) == 0) && tc_smem <= 112 * 1024 &&
+    const bool use_tc = affine && !d.has_time_axis && div_ok && (d.K % (kTcN / 2) == 0) && d.K <= 4096 && tc_smem <= 112 * 1024 &&
                         !want_tile && !want_ffma && ((d.M >= 64 && !d.fov_any) || want_tc);   // FoV leaves few paths, tiny arrays little output: FP32 kernel wins
     const bool use_fast = !use_tc && affine && !d.has_time_axis && div_ok && fast_smem <= 110 * 1024 && !want_tile;
     const int tile_w = use_tc ? (kTcN / 2) * tcfg.nsub : (use_fast ? kTKW : kTK);

@@ -67,7 +67,7 @@ __device__ __noinline__ void fd_cta_prologue_outlined(const DevDesc& d, long lon
 }
 
 __global__ void __launch_bounds__(kFdThreads, 2)
-fd_tile_kernel(const DevDesc d, const int ksplit)
+fd_tile_kernel(const __grid_constant__ DevDesc d, const int ksplit)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2* sW = reinterpret_cast<float2*>(smem_raw);                    // [kMaxPaths][kTK]
@@ -213,7 +213,7 @@ struct FastCfg {
 __device__ __forceinline__ float4 ldsA(const float4* p) { return *p; }
 
 __global__ void __launch_bounds__(kFdThreads, 2)
-fd_fast_kernel(const DevDesc d, const FastCfg cfg, const int ksplit)
+fd_fast_kernel(const __grid_constant__ DevDesc d, const FastCfg cfg, const int ksplit)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2* sW = reinterpret_cast<float2*>(smem_raw + cfg.off_W);    // [pcap][kTKW]

@@ -204,7 +204,7 @@ __device__ __noinline__ void tc_epilogue(const TcTile& t, uint32_t tmem_base, fl
 }
 
 __global__ void __launch_bounds__(kTcThreads, 2)
-fd_tc_kernel(const DevDesc d, const TcCfg cfg, const int ksplit)
+fd_tc_kernel(const __grid_constant__ DevDesc d, const __grid_constant__ TcCfg cfg, const int ksplit)
 {
     extern __shared__ unsigned char smem_raw[];
     __shared__ FdShared sh;
@@ -237,8 +237,16 @@ fd_tc_kernel(const DevDesc d, const TcCfg cfg, const int ksplit)
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&mbar)));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+#ifdef DMK_TC_TRACE
+    const bool trace_user = (blockIdx.x >= gridDim.x / 2 && blockIdx.x < gridDim.x / 2 + 6) && tid == 0;
+    const int tu = 4000 + 8 * (int)(blockIdx.x - gridDim.x / 2);
+    if (trace_user) g_tc_trace[tu + 0] = clock64();
+#endif
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     fd_cta_prologue_outlined(d, user, sh, psc, ks == 0);      // (two CTA barriers inside)
+#ifdef DMK_TC_TRACE
+    if (trace_user) { g_tc_trace[tu + 1] = clock64(); g_tc_trace[tu + 5] = sh.np; }
+#endif
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = tmem_base_s;
     const int np = sh.np;
@@ -275,7 +283,7 @@ fd_tc_kernel(const DevDesc d, const TcCfg cfg, const int ksplit)
         const float inv_scale = 1.0f / scale;
         // ---- per-user tables (phase reduced in float64 for every entry)
         {
-            const int bs0 = d.bs0, bs1 = d.bs1, nA = cfg.nA;
+            const int bs0 = d.bs0, bs1 = d.bs1;
             for (int e = tid; e < np * bs0; e += kTcThreads) {
                 const int p = e / bs0, y = e - p * bs0;
                 tY[p * cfg.sY + y] = phasor_cycles((double)y * sh.u[0][p]);
@@ -287,17 +295,31 @@ fd_tc_kernel(const DevDesc d, const TcCfg cfg, const int ksplit)
                 const float2 cs = make_float2(sh.c[p].x * inv_scale, sh.c[p].y * inv_scale);
                 tQ[p * cfg.sQ + q] = cmul(cs, phasor_cycles((double)z * sh.v[0][p] + (double)yr * sh.u[1][p] + (double)zr * sh.v[1][p]));
             }
-            for (int e = tid; e < np * nA; e += kTcThreads) {
-                const int p = e / nA, a = e - p * nA;
-                wA[p * cfg.sA + a] = phasor_cycles(-(sh.wcyc[p] * (double)(d.subc_start + d.subc_step * 16 * a)));
-            }
+            // delay phasors: wB[b] (16 entries) and two seed tables per path (8 fine + up to 32 coarse entries) are reduced in
+            // float64; the nA-entry table wA[a] = seed_hi[a >> 3] * seed_lo[a & 7] is then one complex multiply per entry
+            // (unit-modulus float32 product) instead of nA sincos evaluations.  K <= 4096 (host-checked).
+            float2* seed = reinterpret_cast<float2*>(sBhi);           // B operand area is free until the first build: [np][40]
+            const int n_hi = (cfg.nA + 7) >> 3;
             for (int e = tid; e < np * 16; e += kTcThreads) {
                 const int p = e >> 4, b = e & 15;
                 wB[p * cfg.sB + b] = phasor_cycles(-(sh.wcyc[p] * (double)(d.subc_step * b)));
             }
+            for (int e = tid; e < np * 40; e += kTcThreads) {
+                const int p = e / 40, b = e - p * 40;
+                if (b < 8)              seed[e] = phasor_cycles(-(sh.wcyc[p] * (double)(d.subc_step * 16 * b)));                           // seed_lo[b]
+                else if (b - 8 < n_hi)  seed[e] = phasor_cycles(-(sh.wcyc[p] * (double)(d.subc_start + d.subc_step * 128 * (b - 8))));   // seed_hi[b - 8]
+            }
         }
         __syncthreads();
-
+        for (int e = tid; e < np * cfg.nA; e += kTcThreads) {
+            const int p = e / cfg.nA, a = e - p * cfg.nA;
+            const float2* sd = reinterpret_cast<const float2*>(sBhi) + p * 40;
+            wA[p * cfg.sA + a] = cmul(sd[8 + (a >> 3)], sd[a & 7]);
+        }
+        __syncthreads();
+#ifdef DMK_TC_TRACE
+        if (trace_user) g_tc_trace[tu + 2] = clock64();
+#endif
         const int ksteps = (np + 7) >> 3;                     // 16 fp16 (8 path slots) per MMA
         const int nslot = ksteps * 8;                         // slots the tensor core reads; slots >= np are written as zeros
         // instruction descriptor: D = F32, A = B = F16 (format 0), both K-major, N = antenna rows of the tile, M = 128 floats
@@ -452,6 +474,9 @@ fd_tc_kernel(const DevDesc d, const TcCfg cfg, const int ksplit)
             }
     }
 
+#ifdef DMK_TC_TRACE
+    if (trace_user) g_tc_trace[tu + 3] = clock64();
+#endif
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 3) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"(2 * 128));

@@ -51,7 +51,7 @@ __device__ __forceinline__ void td_cta_prologue(const DevDesc& d, long long user
 }
 
 __global__ void __launch_bounds__(kTdThreads, 4)
-td_kernel(const DevDesc d)
+td_kernel(const __grid_constant__ DevDesc d)
 {
     __shared__ TdShared sh;
     __shared__ PrologueScratch psc;
@@ -111,7 +111,7 @@ td_kernel(const DevDesc d)
 
 // Per-path by-products (Dataset caches): rotated angles, power with antenna gain, FoV mask.
 __global__ void __launch_bounds__(256)
-prologue_kernel(const DevDesc d, double* __restrict__ angles_rot, double* __restrict__ power_gain)
+prologue_kernel(const __grid_constant__ DevDesc d, double* __restrict__ angles_rot, double* __restrict__ power_gain)
 {
     const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     const long long total = d.n_users * d.P0;

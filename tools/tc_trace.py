@@ -28,3 +28,9 @@ for st in range(0, 12):
     nxt = t[16 * (st + 1)]
     print(f"{st:3d} | top@{w[0]-t0:7d}  wait {w[1]-w[0]:6d}  build {w[2]-w[1]:6d}  sync {w[3]-w[2]:6d}  epi {w[4]-w[3]:6d} | "
           f"issuer: top@{u[0]-t0:7d} wait {u[1]-u[0]:6d} sync_done@{u[3]-t0:7d} issue {u[4]-u[3]:6d}")
+
+print("per-user phases (6 consecutive CTAs): np | prologue | tables | stages | total cycles")
+for i in range(6):
+    b = 4000 + 8 * i
+    if t[b] == 0: continue
+    print(f"  np {t[b+5]:2d} | prologue {t[b+1]-t[b]:6d} | tables {t[b+2]-t[b+1]:6d} | stages {t[b+3]-t[b+2]:7d} | total {t[b+3]-t[b]:7d}")
