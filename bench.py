@@ -360,7 +360,9 @@ def gpu_main(args):
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tpath):
             with open(tpath) as f:
-                traffic = json.load(f).get(args.workload)
+                rec = json.load(f).get(args.workload)
+            if rec:      # measured at rec["users"] users per launch; DRAM traffic is linear in users (every user is written once)
+                traffic = rec["dram_bytes"] * (res["plan"].n_users / rec["users"]) / n_launch
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
