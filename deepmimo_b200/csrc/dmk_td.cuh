@@ -55,8 +55,8 @@ td_kernel(const __grid_constant__ DevDesc d)
 {
     __shared__ TdShared sh;
     __shared__ PrologueScratch psc;
-    __shared__ float2 sA[kTdRows * kMaxPaths];        // [row][slot] gain * steering
-    __shared__ float2 sD[kMaxPaths * 64];             // [slot][it] Doppler phasors, 64 snapshots per pass
+    __shared__ __align__(16) float2 sA[kTdRows * kMaxPaths]; // [row][slot] gain * steering
+    __shared__ __align__(16) float2 sD[kMaxPaths * 64]; // [slot][it] Doppler phasors, 64 snapshots per pass
 
     const int tid = threadIdx.x;
     const long long user = blockIdx.x;
@@ -96,6 +96,30 @@ td_kernel(const __grid_constant__ DevDesc d)
                 // [rn, P] block is contiguous in the output
                 float2* o = out_u + (long long)row0 * P;
                 for (int e = tid; e < rn * P; e += kTdThreads) __stcs(o + e, sA[e]);
+            } else if ((tn & 1) == 0 && (T & 1) == 0 && (kTdThreads % (tn >> 1)) == 0) {
+                // fast path: a thread owns two consecutive snapshots (one 16-byte store) and walks the (row, slot) pairs with
+                // incremental indices -- no integer division per element
+                const int tpr = tn >> 1;                         // threads per (row, slot) pair
+                const int step = kTdThreads / tpr;               // (row, slot) pairs per pass
+                const int it = (tid % tpr) * 2;
+                int rj = tid / tpr;
+                int j = rj % P;
+                const int jstep = step % P;
+                float4* o = reinterpret_cast<float4*>(out_u + ((long long)row0 * P + rj) * T + it0 + it);
+                const long long ostep = (long long)step * T / 2;  // float4 units
+                for (; rj < rn * P; rj += step) {
+                    float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (j < nv) {
+                        const float2 a = sA[rj];
+                        const float4 dd = *reinterpret_cast<const float4*>(&sD[j * 64 + it]);
+                        val = make_float4(fmaf(a.x, dd.x, -a.y * dd.y), fmaf(a.x, dd.y, a.y * dd.x),
+                                          fmaf(a.x, dd.z, -a.y * dd.w), fmaf(a.x, dd.w, a.y * dd.z));
+                    }
+                    __stcs(o, val);
+                    o += ostep;
+                    j += jstep;
+                    if (j >= P) j -= P;
+                }
             } else {
                 for (int e = tid; e < rn * P * tn; e += kTdThreads) {
                     const int rj = e / tn, it = e - rj * tn;         // rj = r*P + j
