@@ -200,8 +200,12 @@ int dmk_channels_fd(const dmk_desc* desc, const float* power_dbw, const float* p
         tcfg.sY = d.bs0 | 1; tcfg.sQ = (d.Mr * d.bs1) | 1; tcfg.sA = tcfg.nA | 1; tcfg.sB = 17;   // odd strides: no bank conflicts across paths
         tcfg.off_tY = take((size_t)pc * tcfg.sY * sizeof(float2));
         tcfg.off_tQ = take((size_t)pc * tcfg.sQ * sizeof(float2));
-        tcfg.off_wA = take((size_t)pc * tcfg.sA * sizeof(float2));
+        tcfg.wa_table = d.K <= 1024;                          // larger K: coarse phasor formed on the fly from the seed tables
+        tcfg.off_wA = take(tcfg.wa_table ? (size_t)pc * tcfg.sA * sizeof(float2) : 16);
         tcfg.off_wB = take((size_t)pc * tcfg.sB * sizeof(float2));
+        // seed tables [pc][41]: temporaries in the (not yet used) B operand area when wA is materialised from them,
+        // a region of their own (instead of wA) otherwise -- the footprint must stay under two CTAs per SM
+        tcfg.off_seed = tcfg.wa_table ? tcfg.off_B : take((size_t)pc * 41 * sizeof(float2));
         tcfg.mul_mt = cfg.mul_mt; tcfg.mul_bs0 = cfg.mul_bs0;
         tc_smem += off;
     }

@@ -42,6 +42,7 @@ struct TcCfg {
     int off_A, off_B, off_tY, off_tQ, off_wA, off_wB;   // byte offsets from the 1024-aligned base
     int nA, pcap, mtile;                                 // mtile = antenna rows per tile = tcgen05 N: 16, 32, 64 or 128
     int nsub;                                            // 64-subcarrier sub-tiles per pipeline stage: 2 when mtile <= 64, else 1
+    int off_seed, wa_table;                              // seed tables [pcap][41]; wa_table = 1: coarse table wA materialised (K <= 1024)
     int sY, sQ, sA, sB;                                  // per-path table strides (float2 units), odd -> lanes that differ
                                                          // in the path index hit different shared-memory banks
     unsigned mul_mt, mul_bs0;
@@ -298,7 +299,7 @@ fd_tc_kernel(const __grid_constant__ DevDesc d, const __grid_constant__ TcCfg cf
             // delay phasors: wB[b] (16 entries) and two seed tables per path (8 fine + up to 32 coarse entries) are reduced in
             // float64; the nA-entry table wA[a] = seed_hi[a >> 3] * seed_lo[a & 7] is then one complex multiply per entry
             // (unit-modulus float32 product) instead of nA sincos evaluations.  K <= 4096 (host-checked).
-            float2* seed = reinterpret_cast<float2*>(sBhi);           // B operand area is free until the first build: [np][40]
+            float2* seed = reinterpret_cast<float2*>(sm + cfg.off_seed);  // [np][41]: 8 fine + up to 32 coarse entries
             const int n_hi = (cfg.nA + 7) >> 3;
             for (int e = tid; e < np * 16; e += kTcThreads) {
                 const int p = e >> 4, b = e & 15;
@@ -306,17 +307,19 @@ fd_tc_kernel(const __grid_constant__ DevDesc d, const __grid_constant__ TcCfg cf
             }
             for (int e = tid; e < np * 40; e += kTcThreads) {
                 const int p = e / 40, b = e - p * 40;
-                if (b < 8)              seed[e] = phasor_cycles(-(sh.wcyc[p] * (double)(d.subc_step * 16 * b)));                           // seed_lo[b]
-                else if (b - 8 < n_hi)  seed[e] = phasor_cycles(-(sh.wcyc[p] * (double)(d.subc_start + d.subc_step * 128 * (b - 8))));   // seed_hi[b - 8]
+                if (b < 8)              seed[p * 41 + b] = phasor_cycles(-(sh.wcyc[p] * (double)(d.subc_step * 16 * b)));                           // seed_lo[b]
+                else if (b - 8 < n_hi)  seed[p * 41 + b] = phasor_cycles(-(sh.wcyc[p] * (double)(d.subc_start + d.subc_step * 128 * (b - 8))));   // seed_hi[b - 8]
             }
         }
         __syncthreads();
-        for (int e = tid; e < np * cfg.nA; e += kTcThreads) {
-            const int p = e / cfg.nA, a = e - p * cfg.nA;
-            const float2* sd = reinterpret_cast<const float2*>(sBhi) + p * 40;
-            wA[p * cfg.sA + a] = cmul(sd[8 + (a >> 3)], sd[a & 7]);
+        if (cfg.wa_table) {
+            for (int e = tid; e < np * cfg.nA; e += kTcThreads) {
+                const int p = e / cfg.nA, a = e - p * cfg.nA;
+                const float2* sd = reinterpret_cast<const float2*>(sm + cfg.off_seed) + p * 41;
+                wA[p * cfg.sA + a] = cmul(sd[8 + (a >> 3)], sd[a & 7]);
+            }
+            __syncthreads();
         }
-        __syncthreads();
 #ifdef DMK_TC_TRACE
         if (trace_user) g_tc_trace[tu + 2] = clock64();
 #endif
@@ -409,7 +412,12 @@ fd_tc_kernel(const __grid_constant__ DevDesc d, const __grid_constant__ TcCfg cf
                         for (int i = 0; i < 4; ++i) {
                             const int p = qd * 4 + i;
                             float2 w = make_float2(0.f, 0.f);
-                            if (p < np) w = cmul(wA[p * cfg.sA + (col >> 4)], wB[p * cfg.sB + (col & 15)]);
+                            if (p < np) {
+                                const int a = col >> 4;
+                                const float2* sd = reinterpret_cast<const float2*>(sm + cfg.off_seed) + p * 41;
+                                const float2 wa = cfg.wa_table ? wA[p * cfg.sA + a] : cmul(sd[8 + (a >> 3)], sd[a & 7]);
+                                w = cmul(wa, wB[p * cfg.sB + (col & 15)]);
+                            }
                             re[i] = make_float2(w.x, -w.y);
                             im[i] = make_float2(w.y, w.x);
                         }

@@ -1,0 +1,80 @@
+"""Edge cases of the tensor-core FD kernel (fd_tc_kernel, forced with DMK_FD_KERNEL=tc) against the oracle:
+tile raggedness in M and K, 32 path columns, FP16 operand scaling under a 150 dB power spread, sub-tiled small arrays,
+single-path users, K split across CTAs (few users)."""
+import numpy as np
+import pytest
+
+from util import assert_channels_close, make_dataset
+
+pytestmark = pytest.mark.gpu
+
+
+def _case(n, bs, ue, n_sc, k_sel, seed, n_cols=25, bs_rot=(10, 20, 30), power_lo=-160.0, power_hi=-60.0, zero_frac=0.1):
+    from deepmimo_b200.synth import make_paths
+    d = make_paths(n, seed, n_sc=n_sc, bandwidth=50e6, n_cols=n_cols, zero_frac=zero_frac)
+    if (power_lo, power_hi) != (-160.0, -60.0):
+        rng = np.random.default_rng(seed + 1)
+        pw = -np.sort(-rng.uniform(power_lo, power_hi, d["power"].shape), axis=1).astype(np.float32)
+        pw[np.isnan(d["power"])] = np.nan
+        d["power"] = pw
+    p = {"bs_antenna": {"shape": np.array(bs), "spacing": 0.5, "rotation": np.array(bs_rot), "radiation_pattern": "isotropic"},
+         "ue_antenna": {"shape": np.array(ue), "spacing": 0.5, "rotation": np.array([0, 0, 0]), "radiation_pattern": "isotropic"},
+         "enable_doppler": 0, "enable_dual_polar": 0, "num_paths": n_cols, "freq_domain": 1,
+         "ofdm": {"subcarriers": n_sc, "selected_subcarriers": np.asarray(k_sel), "bandwidth": 50e6, "rx_filter": 0}}
+    return d, p
+
+
+def _run(d, p, monkeypatch, expect="fd_tc_kernel"):
+    import deepmimo_b200 as dmb
+    from oracle import channel_oracle as orc
+    monkeypatch.setenv("DMK_FD_KERNEL", "tc")
+    H, info = make_dataset(dmb, d).compute_channels(dmb.ChannelGenParameters(p), return_info=True, warn=False)
+    o = orc.compute_channels(d, bs_shape=p["bs_antenna"]["shape"], ue_shape=p["ue_antenna"]["shape"],
+                             bs_rotation=p["bs_antenna"]["rotation"], num_paths=p["num_paths"],
+                             subcarriers=p["ofdm"]["subcarriers"], selected_subcarriers=p["ofdm"]["selected_subcarriers"],
+                             bandwidth=p["ofdm"]["bandwidth"])
+    assert info.kernel.startswith(expect), info.kernel
+    err = assert_channels_close(H, o["H"], what=info.kernel)
+    assert np.array_equal(info.valid, o["valid"]) and np.array_equal(info.clip, o["clip"])
+    return err, info
+
+
+@pytest.mark.parametrize("bs,ue,k", [((8, 8), (1, 1), 64),          # one segment, one 64-row tile
+                                      ((12, 11), (1, 1), 128),       # M = 132: ragged second 128-row tile
+                                      ((5, 3), (3, 1), 192),         # M = 45 -> 64-row tile, 3 segments (odd count with 2 sub-tiles)
+                                      ((3, 3), (1, 1), 320),         # M = 9 -> 16-row tile
+                                      ((16, 16), (2, 2), 64)])       # M = 1024, 8 row tiles
+def test_tc_tile_raggedness(bs, ue, k, monkeypatch):
+    d, p = _case(40, bs, ue, 1024, np.arange(k), 31)
+    err, info = _run(d, p, monkeypatch)
+    print(info.kernel, f"{err:.2e}")
+
+
+def test_tc_32_path_columns_and_offset_stride_selection(monkeypatch):
+    d, p = _case(64, (8, 8), (2, 1), 2048, 5 + 3 * np.arange(128), 32, n_cols=32)      # affine selection start 5, step 3
+    err, _ = _run(d, p, monkeypatch)
+    assert err < 2e-6
+
+
+def test_tc_k4096_and_fallback_beyond(monkeypatch):
+    d, p = _case(6, (8, 8), (1, 1), 4096, np.arange(4096), 33)
+    _run(d, p, monkeypatch)
+    d, p = _case(4, (8, 8), (1, 1), 8192, np.arange(8192), 34)
+    _run(d, p, monkeypatch, expect="fd_")                 # K > 4096: the tensor-core kernel is not eligible, another FD kernel runs
+
+
+def test_tc_fp16_scaling_under_150_db_spread(monkeypatch):
+    """Path powers from -200 to -50 dBW inside one user: the per-user scale keeps the strong paths exact and the weak
+    ones cost nothing against the per-user Frobenius criterion."""
+    d, p = _case(128, (16, 8), (1, 1), 512, np.arange(512), 35, power_lo=-200.0, power_hi=-50.0, zero_frac=0.0)
+    err, _ = _run(d, p, monkeypatch)
+    assert err < 2e-6
+    d, p = _case(128, (16, 8), (1, 1), 512, np.arange(512), 36, power_lo=-300.0, power_hi=-250.0, zero_frac=0.0)   # tiny everywhere
+    err, _ = _run(d, p, monkeypatch)
+    assert err < 2e-6
+
+
+def test_tc_single_path_users_and_few_users_split_over_ctas(monkeypatch):
+    d, p = _case(3, (16, 8), (1, 1), 1024, np.arange(1024), 37, n_cols=1, zero_frac=0.0)       # ksplit > 1, np = 1
+    err, info = _run(d, p, monkeypatch)
+    assert "ksplit=" in info.kernel and int(info.kernel.split("ksplit=")[1].split()[0]) > 1
