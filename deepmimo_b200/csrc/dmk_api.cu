@@ -8,6 +8,7 @@
 
 #include "dmk_fd.cuh"
 #include "dmk_fd_tc.cuh"
+#include "dmk_fd_small.cuh"
 #include "dmk_td.cuh"
 
 namespace {
@@ -128,6 +129,10 @@ int dmk_debug_tc_trace(long long* host_out, int n)
 {
     return (int)cudaMemcpyFromSymbol(host_out, dmk::g_tc_trace, sizeof(long long) * n);
 }
+int dmk_debug_pro_trace(long long* host_out)
+{
+    return (int)cudaMemcpyFromSymbol(host_out, dmk::g_pro_trace, sizeof(long long) * 16);
+}
 #endif
 
 const char* dmk_last_error(void) { return g_err; }
@@ -224,6 +229,51 @@ int dmk_channels_fd(const dmk_desc* desc, const float* power_dbw, const float* p
     if (ksplit < 1) ksplit = 1;
     const long long grid = n_users * ksplit;
     if (grid > 0x7fffffffLL) return fail(DMK_ERR_INVALID_ARG, "grid too large: split the user range");
+    // Small arrays (M <= 16): one warp per user, see dmk_fd_small.cuh.  DMK_FD_KERNEL=small forces it where eligible.
+    {
+        const bool want_small = force && !strcmp(force, "small");
+        SmallCfg sc;
+        const int pc = d.P > 0 ? d.P : 1;
+        const int mt = d.M <= 4 ? 4 : (d.M <= 8 ? 8 : 16);
+        size_t off = 0;
+        auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 15) & ~size_t(15); return (int)o; };
+        sc.pcap = pc;
+        sc.n_hi = (((d.K + 15) / 16) + 7) / 8;
+        sc.sY = d.bs0 | 1; sc.sQ = (d.Mr * d.bs1) | 1; sc.sS = (8 + sc.n_hi) | 1;
+        sc.off_sh   = take(sizeof(FdShared));
+        sc.off_tY   = take((size_t)pc * sc.sY * sizeof(float2));
+        sc.off_tQ   = take((size_t)pc * sc.sQ * sizeof(float2));
+        sc.off_wB   = take((size_t)pc * 17 * sizeof(float2));
+        sc.off_seed = take((size_t)pc * sc.sS * sizeof(float2));
+        sc.off_A    = take((size_t)pc * mt * sizeof(float4));
+        sc.warp_bytes = (int)off;
+        sc.mul_mt = cfg.mul_mt; sc.mul_bs0 = cfg.mul_bs0;
+        const size_t small_smem = off * kSmallWarps;
+        const bool small_ok = affine && !d.has_time_axis && div_ok && d.M <= 16 && d.K <= 4096 && small_smem <= 72 * 1024;
+        const bool use_small = small_ok && !want_tile && !want_ffma && !want_tc && (want_small || true);
+        if (use_small) {
+            if (d.K == 1 && d.subc_step == 0) d.subc_step = 1;
+            const long long sgrid = (n_users + kSmallWarps - 1) / kSmallWarps;
+            if (sgrid > 0x7fffffffLL) return fail(DMK_ERR_INVALID_ARG, "grid too large: split the user range");
+            cudaError_t e = cudaSuccess;
+            static bool attr_small = false;
+            if (!attr_small) {
+                e = cudaFuncSetAttribute(fd_small_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024);
+                if (e == cudaSuccess) e = cudaFuncSetAttribute(fd_small_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024);
+                if (e == cudaSuccess) e = cudaFuncSetAttribute(fd_small_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024);
+                if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(fd_small_kernel)");
+                attr_small = true;
+            }
+            if (mt == 4)      fd_small_kernel<4><<<(unsigned)sgrid, kSmallWarps * 32, small_smem, st>>>(d, sc);
+            else if (mt == 8) fd_small_kernel<8><<<(unsigned)sgrid, kSmallWarps * 32, small_smem, st>>>(d, sc);
+            else              fd_small_kernel<16><<<(unsigned)sgrid, kSmallWarps * 32, small_smem, st>>>(d, sc);
+            e = cudaGetLastError();
+            if (e != cudaSuccess) return cuda_fail(e, "fd_small_kernel launch");
+            g_launches.fetch_add(1);
+            snprintf(g_kernel, sizeof(g_kernel), "fd_small_kernel<%d rows,warp/user> grid=%lld smem=%zu", mt, sgrid, small_smem);
+            return DMK_OK;
+        }
+    }
     if (use_tc) {
         if (d.K == 1 && d.subc_step == 0) d.subc_step = 1;
         static bool attr_tc = false;

@@ -18,6 +18,10 @@ constexpr int kFdThreads = 256;
 constexpr int kTM = 64;      // rows per CTA tile  (8 warps x 8 rows)
 constexpr int kTK = 128;     // columns per CTA tile (32 lanes x 4 columns)
 
+#ifdef DMK_TC_TRACE
+__device__ long long g_pro_trace[16];
+#endif
+
 struct FdShared {
     float2 c[kMaxPaths];
     double wcyc[kMaxPaths];
@@ -32,13 +36,24 @@ struct FdShared {
 // Ends with a CTA barrier; sh.np is valid afterwards.
 __device__ __forceinline__ void fd_cta_prologue(const DevDesc& d, long long user, FdShared& sh, PrologueScratch& sc, bool write_masks)
 {
+#ifdef DMK_TC_TRACE
+    long long pt0 = clock64();
+#endif
     cta_prologue_chains<true>(d, user, sc);
+    if (threadIdx.x >= 224) prefetch_user_rows_shifted(d, user);
+#ifdef DMK_TC_TRACE
+    long long pt1 = clock64();
+    if (blockIdx.x == gridDim.x / 2 && (threadIdx.x & 31) == 3 && threadIdx.x < 96) { g_pro_trace[(threadIdx.x >> 5) * 2] = pt0; g_pro_trace[(threadIdx.x >> 5) * 2 + 1] = pt1; }
+#endif
     __syncthreads();
     if (threadIdx.x < 32) {
         const int lane = threadIdx.x;
         PathState st;
         const bool active = lane < d.P0;
         st.contrib = false; st.valid = false; st.fov = true; st.over = false;
+#ifdef DMK_TC_TRACE
+        if (blockIdx.x == gridDim.x / 2 && lane == 3) g_pro_trace[6] = clock64();
+#endif
         if (active) prologue_combine<true>(d, sc.side[0][lane], sc.side[1][lane], sc.gain[lane], st);
         const unsigned ballot = __ballot_sync(0xffffffffu, active && st.contrib);
         if (active && st.contrib) {
@@ -54,6 +69,9 @@ __device__ __forceinline__ void fd_cta_prologue(const DevDesc& d, long long user
             if (d.valid_mask) d.valid_mask[o] = st.valid ? 1 : 0;
             if (d.clip_mask)  d.clip_mask[o]  = (st.valid && st.over) ? 1 : 0;
         }
+#ifdef DMK_TC_TRACE
+        if (blockIdx.x == gridDim.x / 2 && lane == 3) g_pro_trace[7] = clock64();
+#endif
     }
     __syncthreads();
 }

@@ -1,0 +1,160 @@
+// dmk_fd_small.cuh -- FD channel kernel for small arrays (M = M_rx * M_tx <= 16): one WARP per user.
+//
+// With a handful of antenna rows a user's whole output is a few KB (BASELINE config 1: 8 x 64 complex = 4 KB) and the
+// cost is the per-user prologue, not the accumulation.  Giving every user a CTA (fd_fast_kernel / fd_tc_kernel) leaves
+// 7 of 8 warps waiting on the prologue; here a warp does everything for its user with warp-level synchronisation only:
+//   lanes = path columns: the three float64 prologue chains back to back, combine, ballot compaction;
+//   lanes = table entries: TX y-steering, (RX x TX-z x gain), delay phasors wB[16] and the fine/coarse seed tables
+//     (phase reduced in float64 per entry);
+//   lanes = column pairs: per 64-column pass each lane owns columns 2l, 2l+1 and all M rows in registers, the W entries of its
+//     two columns are formed on the fly (seed_hi * seed_lo * wB), 2 FFMA2 per complex MAC as in fd_fast_kernel;
+//   16-byte streaming stores, 512 contiguous bytes per row per warp instruction.
+// Several warps (users) share a CTA only to share the launch; they never synchronise with each other.
+#pragma once
+#include "dmk_fd.cuh"
+
+namespace dmk {
+
+constexpr int kSmallWarps = 4;            // users per CTA
+
+struct SmallCfg {
+    int off_sh, off_tY, off_tQ, off_wB, off_seed, off_A;    // byte offsets inside a warp's shared-memory slice
+    int warp_bytes;
+    int sY, sQ, sS, n_hi, pcap;                             // odd table strides (float2 units); sS = seed stride >= 8 + n_hi
+    unsigned mul_mt, mul_bs0;
+};
+
+template <int MT>      // rows held in registers: 4, 8 or 16 (M <= MT)
+__global__ void __launch_bounds__(kSmallWarps * 32, 4)
+fd_small_kernel(const __grid_constant__ DevDesc d, const __grid_constant__ SmallCfg cfg)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long user = (long long)blockIdx.x * kSmallWarps + warp;
+    if (user >= d.n_users) return;                           // warp-uniform; no CTA-wide barrier is ever used
+
+    unsigned char* wsm = smem_raw + warp * cfg.warp_bytes;
+    FdShared& sh = *reinterpret_cast<FdShared*>(wsm + cfg.off_sh);
+    float2* tY   = reinterpret_cast<float2*>(wsm + cfg.off_tY);      // [np][sY]
+    float2* tQ   = reinterpret_cast<float2*>(wsm + cfg.off_tQ);      // [np][sQ]
+    float2* wB   = reinterpret_cast<float2*>(wsm + cfg.off_wB);      // [np][17]
+    float2* seed = reinterpret_cast<float2*>(wsm + cfg.off_seed);    // [np][sS]: 8 fine, then n_hi coarse
+    float4* sA   = reinterpret_cast<float4*>(wsm + cfg.off_A);       // [np][MT] (re, re, im, im)
+
+    // ---- prologue: lane = path column, the three chains back to back
+    {
+        PathState st;
+        const bool active = lane < d.P0;
+        st.contrib = false; st.valid = false; st.fov = true; st.over = false;
+        if (active) {
+            SideOut s0, s1; GainOut g;
+            if (prologue_needs_angles(d)) { prologue_side<true>(d, user, lane, 0, s0);  prologue_side<true>(d, user, lane, 1, s1); }
+            else                          { prologue_side<false>(d, user, lane, 0, s0); prologue_side<false>(d, user, lane, 1, s1); }
+            prologue_gain<true>(d, user, lane, g);
+            prologue_combine<true>(d, s0, s1, g, st);
+        }
+        const unsigned ballot = __ballot_sync(0xffffffffu, active && st.contrib);
+        if (active && st.contrib) {
+            const int j = __popc(ballot & ((1u << lane) - 1u));
+            sh.c[j] = st.c; sh.wcyc[j] = st.wcyc;
+            sh.u[0][j] = st.u[0]; sh.v[0][j] = st.v[0];
+            sh.u[1][j] = st.u[1]; sh.v[1][j] = st.v[1];
+        }
+        if (lane == 0) sh.np = __popc(ballot);
+        if (active) {
+            const long long o = user * (long long)d.P0 + lane;
+            if (d.fov_mask)   d.fov_mask[o]   = st.fov ? 1 : 0;
+            if (d.valid_mask) d.valid_mask[o] = st.valid ? 1 : 0;
+            if (d.clip_mask)  d.clip_mask[o]  = (st.valid && st.over) ? 1 : 0;
+        }
+    }
+    __syncwarp();
+    const int np = sh.np;
+    const int K = d.K, M = d.M;
+    float2* out_u = d.out + user * (long long)M * K;
+    const bool vec_ok = ((K & 1) == 0) && ((reinterpret_cast<uintptr_t>(d.out) & 15) == 0);
+
+    if (np == 0) {                                           // zeros (channel.py:257,:269-271)
+        const long long total = (long long)M * K;
+        if (vec_ok) { float4* o = reinterpret_cast<float4*>(out_u); for (long long e = lane; e < total / 2; e += 32) __stcs(o + e, make_float4(0.f, 0.f, 0.f, 0.f)); }
+        else        { for (long long e = lane; e < total; e += 32) __stcs(out_u + e, make_float2(0.f, 0.f)); }
+        return;
+    }
+
+    // ---- tables (phase reduced in float64 for every entry)
+    const int nq = d.Mr * d.bs1;
+    for (int e = lane; e < np * d.bs0; e += 32) {
+        const int p = e / d.bs0, y = e - p * d.bs0;
+        tY[p * cfg.sY + y] = phasor_cycles((double)y * sh.u[0][p]);
+    }
+    for (int e = lane; e < np * nq; e += 32) {
+        const int p = e / nq, q = e - p * nq;
+        const int r = q / d.bs1, z = q - r * d.bs1;
+        const int yr = r % d.ue0, zr = r / d.ue0;
+        tQ[p * cfg.sQ + q] = cmul(sh.c[p], phasor_cycles((double)z * sh.v[0][p] + (double)yr * sh.u[1][p] + (double)zr * sh.v[1][p]));
+    }
+    for (int e = lane; e < np * 16; e += 32) {
+        const int p = e >> 4, b = e & 15;
+        wB[p * 17 + b] = phasor_cycles(-(sh.wcyc[p] * (double)(d.subc_step * b)));
+    }
+    for (int e = lane; e < np * (8 + cfg.n_hi); e += 32) {
+        const int p = e / (8 + cfg.n_hi), b = e - p * (8 + cfg.n_hi);
+        const double k0 = (b < 8) ? (double)(d.subc_step * 16 * b) : (double)(d.subc_start + d.subc_step * 128 * (b - 8));
+        seed[p * cfg.sS + b] = phasor_cycles(-(sh.wcyc[p] * k0));
+    }
+    __syncwarp();
+    // ---- A[m][p] = gain * steering, stored (re, re, im, im) for the FFMA2 operand modifiers
+    for (int e = lane; e < np * MT; e += 32) {
+        const int p = e / MT, m = e - p * MT;
+        float2 a = make_float2(0.f, 0.f);
+        if (m < M) {
+            const unsigned mm = (unsigned)m;
+            const unsigned rr = cfg.mul_mt ? __umulhi(mm, cfg.mul_mt) : mm;
+            const unsigned t = mm - rr * (unsigned)d.Mt;
+            const unsigned zt = cfg.mul_bs0 ? __umulhi(t, cfg.mul_bs0) : t;
+            const unsigned yt = t - zt * (unsigned)d.bs0;
+            a = cmul(tQ[p * cfg.sQ + rr * d.bs1 + zt], tY[p * cfg.sY + yt]);
+        }
+        sA[p * MT + m] = make_float4(a.x, a.x, a.y, a.y);
+    }
+    __syncwarp();
+
+    // ---- accumulation: 64 columns per pass, lane owns columns 2l and 2l+1
+    for (int col0 = 0; col0 < K; col0 += 64) {
+        const int c0 = col0 + 2 * lane;
+        const int cc = min(c0, K - 1);                       // clamp for the table indices of idle lanes
+        const int a_idx = cc >> 4, b0 = cc & 15, b1 = (cc + 1) & 15;     // c0 is even: both columns share the coarse index
+        float2 acc[MT][2];
+        #pragma unroll
+        for (int m = 0; m < MT; ++m) { acc[m][0] = make_float2(0.f, 0.f); acc[m][1] = make_float2(0.f, 0.f); }
+        #pragma unroll 1
+        for (int p = 0; p < np; ++p) {
+            const float2* sd = seed + p * cfg.sS;
+            const float2 wa = cmul(sd[8 + (a_idx >> 3)], sd[a_idx & 7]);
+            const float2 w0 = cmul(wa, wB[p * 17 + b0]);
+            const float2 w1 = cmul(wa, wB[p * 17 + b1]);
+            const float2 w0s = make_float2(w0.y, w0.x), w1s = make_float2(w1.y, w1.x);
+            #pragma unroll
+            for (int m = 0; m < MT; ++m) {
+                const float4 a = sA[p * MT + m];
+                const float2 a1 = make_float2(a.x, a.y), a2 = make_float2(-a.z, a.w);
+                acc[m][0] = __ffma2_rn(a1, w0, acc[m][0]);
+                acc[m][0] = __ffma2_rn(a2, w0s, acc[m][0]);
+                acc[m][1] = __ffma2_rn(a1, w1, acc[m][1]);
+                acc[m][1] = __ffma2_rn(a2, w1s, acc[m][1]);
+            }
+        }
+        #pragma unroll
+        for (int m = 0; m < MT; ++m) {
+            if (m >= M) break;
+            float2* o = out_u + (long long)m * K + c0;
+            if (vec_ok && c0 + 1 < K) __stcs(reinterpret_cast<float4*>(o), make_float4(acc[m][0].x, acc[m][0].y, acc[m][1].x, acc[m][1].y));
+            else {
+                if (c0 < K)     __stcs(o, acc[m][0]);
+                if (c0 + 1 < K) __stcs(o + 1, acc[m][1]);
+            }
+        }
+    }
+}
+
+}  // namespace dmk

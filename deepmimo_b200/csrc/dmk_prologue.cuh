@@ -113,13 +113,13 @@ __device__ __forceinline__ void prologue_gain(const DevDesc& d, long long user, 
     const long long off = user * (long long)d.ld + p;
     const float pw_db = d.power[off];
     g.valid = (p < d.P) && !(pw_db != pw_db);               // channel.py:260, dataset.py:258-261
-    // generator_utils.py:35: float32 divide by 10, float32 pow (R7, <= 1 ulp)
-    g.p_lin = (float)exp10((double)__fdiv_rn(pw_db, 10.0f));
+    // generator_utils.py:35: float32 divide by 10, float32 pow.  The reference's value is itself a float32 libm/SVML result
+    // (R7: within 1 ulp of correctly rounded); exp10f is within 2 ulp, i.e. <= 1.2e-7 on the amplitude.
+    g.p_lin = exp10f(__fdiv_rn(pw_db, 10.0f));
     const float d2r = 0x1.1df46ap-6f;
     const float ph32 = __fmul_rn(d.phase[off], d2r);        // np.deg2rad(phase) float32
-    double es64, ec64;
-    sincos((double)ph32, &es64, &ec64);                     // complex64 exp(1j*x): cosf/sinf (R10, <= 1 ulp)
-    g.ec = (float)ec64; g.es = (float)es64;
+    // complex64 exp(1j*x) = (cosf(x), sinf(x)) in the reference (R10, <= 1 ulp); sincosf here is within 2 ulp for |x| <= pi
+    sincosf(ph32, &g.es, &g.ec);
     g.over = 0; g.wcyc = 0.0;
     if (kFreqDomain) {
         float dn = __fdiv_rn(d.delay[off], d.ts_f32);       // channel.py:183 (R11)
@@ -183,6 +183,17 @@ __device__ __forceinline__ void prologue_combine(const DevDesc& d, const SideOut
 __device__ __forceinline__ bool prologue_needs_angles(const DevDesc& d)
 {
     return d.fov_any || d.pat[0] != DMK_PATTERN_ISOTROPIC || d.pat[1] != DMK_PATTERN_ISOTROPIC;
+}
+
+// Called by warp 7 (threads 224..255, not part of the chains): prefetch for the user 4 waves of CTAs ahead.
+__device__ __forceinline__ void prefetch_user_rows_shifted(const DevDesc& d, long long user)
+{
+    const int t = threadIdx.x - 224;
+    const long long ahead = user + 4LL * 2 * 148;
+    if (t < 0 || t >= 7 || ahead >= d.n_users) return;
+    const float* base = (t == 0) ? d.power : (t == 1) ? d.phase : (t == 2) ? d.delay : (t == 3) ? d.az[0] : (t == 4) ? d.el[0]
+                      : (t == 5) ? d.az[1] : d.el[1];
+    asm volatile("prefetch.global.L2 [%0];" :: "l"(base + ahead * (long long)d.ld));
 }
 
 // Cooperative phase 1: warps 0, 1, 2 of the CTA run the three chains for path column `lane` of `user`.

@@ -25,6 +25,7 @@ struct TdShared {
 __device__ __forceinline__ void td_cta_prologue(const DevDesc& d, long long user, TdShared& sh, PrologueScratch& sc)
 {
     cta_prologue_chains<false>(d, user, sc);
+    if (threadIdx.x >= 224) prefetch_user_rows_shifted(d, user);
     __syncthreads();
     if (threadIdx.x < 32) {
         const int lane = threadIdx.x;

@@ -59,6 +59,14 @@ def test_fd_odd_column_counts_stay_in_bounds(sel):
     _run_guarded(_plan((7, 3), (1, 2), 1024, sel, 29))
 
 
+@pytest.mark.parametrize("bs,ue,sel", [((8, 1), (1, 1), np.arange(64)), ((3, 1), (1, 1), np.arange(7)), ((4, 2), (2, 1), np.arange(130)),
+                                        ((1, 1), (1, 1), np.arange(1)), ((5, 1), (1, 3), 2 + 5 * np.arange(33))])
+def test_small_array_kernel_stays_in_bounds(bs, ue, sel):
+    from deepmimo_b200 import _lib
+    _run_guarded(_plan(bs, ue, 2048, sel, 53))
+    assert _lib.last_kernel().startswith("fd_small_kernel"), _lib.last_kernel()
+
+
 @pytest.mark.parametrize("times", [None, np.arange(16) * 1e-3, np.arange(5) * 1e-3, np.arange(70) * 1e-4])
 def test_td_kernel_stays_in_bounds(times):
     H = _run_guarded(_plan((7, 3), (1, 2), 512, np.arange(1), 41, fd=0, times=times, n_cols=23))

@@ -216,8 +216,11 @@ def test_fd_kernel_variants_agree_with_oracle(cfg, n, monkeypatch):
     s = scenario(cfg, n)
     o = orc.compute_channels(s.data, **oracle_kwargs_from_params(s.params, s.bs_fov, s.ue_fov))
     seen = set()
-    for variant in ("tc", "ffma", "tile"):
-        monkeypatch.setenv("DMK_FD_KERNEL", variant)
+    for variant in ("tc", "ffma", "tile", "auto"):
+        if variant == "auto":
+            monkeypatch.delenv("DMK_FD_KERNEL")
+        else:
+            monkeypatch.setenv("DMK_FD_KERNEL", variant)
         ds = make_dataset(dmb, s, s.bs_fov, s.ue_fov)
         H, info = ds.compute_channels(dmb.ChannelGenParameters(s.params), return_info=True, warn=False)
         err = assert_channels_close(H, o["H"], what=f"{s.name}/{variant}")
@@ -225,3 +228,5 @@ def test_fd_kernel_variants_agree_with_oracle(cfg, n, monkeypatch):
         seen.add(info.kernel.split("<")[0])
         print(f"{s.name} {variant}: {info.kernel.split(' ')[0]} max rel. Frobenius {err:.2e}")
     assert {"fd_tc_kernel", "fd_fast_kernel", "fd_tile_kernel"} <= seen
+    if cfg == 1:
+        assert "fd_small_kernel" in seen          # small arrays default to the warp-per-user kernel

@@ -34,3 +34,9 @@ for i in range(6):
     b = 4000 + 8 * i
     if t[b] == 0: continue
     print(f"  np {t[b+5]:2d} | prologue {t[b+1]-t[b]:6d} | tables {t[b+2]-t[b+1]:6d} | stages {t[b+3]-t[b+2]:7d} | total {t[b+3]-t[b]:7d}")
+
+pb = (ctypes.c_longlong * 16)()
+lib.dmk_debug_pro_trace(pb)
+q = np.array(pb[:], dtype=np.int64)
+print("prologue of the traced CTA (lane 3): chain TX-side %d, RX-side %d, gain %d cycles; combine %d; chains start -> combine end %d"
+      % (q[1] - q[0], q[3] - q[2], q[5] - q[4], q[7] - q[6], q[7] - min(q[0], q[2], q[4])))
