@@ -21,8 +21,13 @@ ALIASES = {            # subset of deepmimo/consts.py:261-322 that touches this 
     "pwr": "power", "powers": "power", "toa": "delay", "time_of_arrival": "delay",
     "aoa_phi": "aoa_az", "aoa_theta": "aoa_el", "aod_phi": "aod_az", "aod_theta": "aod_el",
     "ue_pos": "rx_pos", "rx_loc": "rx_pos", "bs_pos": "tx_pos", "tx_loc": "tx_pos",
-    "pwr_ant_gain": "_power_linear_ant_gain",
+    "pwr_ant_gain": "_power_linear_ant_gain", "lin_pwr": "power_linear", "linear_power": "power_linear", "pwr_lin": "power_linear",
+    "pl": "pathloss", "path_loss": "pathloss", "n_paths": "num_paths", "los_status": "los",
+    "bounce_type": "inter", "interactions": "inter",
 }
+
+_HOST_BYPRODUCTS = {"power_linear": "_compute_power_linear", "pathloss": "compute_pathloss",
+                    "num_paths": "_compute_num_paths", "los": "_compute_los"}
 
 ROT_KEYS = ("_aod_el_rot", "_aod_az_rot", "_aoa_el_rot", "_aoa_az_rot")                 # consts.py:212-215
 FOV_KEYS = ("_fov_mask", "num_paths", "los", "channel", "_power_linear_ant_gain",        # dataset.py:527-532
@@ -53,6 +58,9 @@ class Dataset(DotDict):
             return self._data[key]
         if key in ROT_KEYS + FOV_KEYS[4:] + ("_fov_mask",):
             self._compute_path_byproducts()
+            return self._data[key]
+        if key in _HOST_BYPRODUCTS:
+            self._data[key] = getattr(self, _HOST_BYPRODUCTS[key])()
             return self._data[key]
         raise KeyError(key)
 
@@ -111,6 +119,44 @@ class Dataset(DotDict):
         if params is None:
             params = self._data.get("ch_params") or ChannelGenParameters()
         return _ch.compute_channels(self, params, **kwargs)
+
+    # -- per-user by-products: cheap host reductions over the path matrices and the GPU FoV mask
+    def _compute_power_linear(self) -> np.ndarray:
+        """dataset.py:694-696, generator_utils.py:35."""
+        return 10 ** (self["power"] / 10)
+
+    def compute_pathloss(self, coherent: bool = True) -> np.ndarray:
+        """Path loss in dB per user (dataset.py:541-566): -10 log10 |sum_p sqrt(p_lin) e^{j phase}|^2, NaN where no power."""
+        p_lin = 10 ** (self["power"] / 10)
+        gains = np.sqrt(p_lin).astype(np.complex64)
+        if coherent:
+            gains *= np.exp(1j * np.deg2rad(self["phase"]))
+        total = np.abs(np.nansum(gains, axis=1)) ** 2
+        pl = np.full_like(total, np.nan)
+        ok = total > 0
+        pl[ok] = -10 * np.log10(total[ok])
+        self._data["pathloss"] = pl
+        return pl
+
+    def _compute_num_paths(self) -> np.ndarray:
+        """Valid paths per user after FoV filtering (dataset.py:613-619)."""
+        return (~np.isnan(self["_aoa_az_rot_fov"])).sum(axis=1)
+
+    def _compute_los(self) -> np.ndarray:
+        """1 LoS / 0 NLoS / -1 no path: interaction code of the first in-FoV path (dataset.py:569-611)."""
+        inter = self["inter"]
+        los = np.full(inter.shape[0], -1)
+        fov = self["_fov_mask"]
+        if fov is not None:
+            has = np.any(fov, axis=1)
+            first_col = np.argmax(fov, axis=1)
+            first = np.where(has, inter[np.arange(inter.shape[0]), first_col], -1)
+        else:
+            has = self["num_paths"] > 0
+            first = inter[:, 0]
+        los[has] = 0
+        los[(first == 0) & has] = 1
+        return los
 
     def _compute_path_byproducts(self) -> None:
         """Rotated angles, FoV mask/angles and power with antenna gain (dataset.py:310-356, :461-512,

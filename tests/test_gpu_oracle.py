@@ -230,3 +230,38 @@ def test_fd_kernel_variants_agree_with_oracle(cfg, n, monkeypatch):
     assert {"fd_tc_kernel", "fd_fast_kernel", "fd_tile_kernel"} <= seen
     if cfg == 1:
         assert "fd_small_kernel" in seen          # small arrays default to the warp-per-user kernel
+
+
+def test_per_user_byproducts_match_reference_definitions():
+    """Row f2: num_paths / los / pathloss / power_linear of the Dataset mirror against the reference's definitions
+    (dataset.py:541-619, :694-696) evaluated with NumPy on the oracle's FoV mask."""
+    import deepmimo_b200 as dmb
+    from deepmimo_b200.synth import scenario
+    from oracle import channel_oracle as orc
+    s = scenario(3, 300)
+    rng = np.random.default_rng(5)
+    inter = np.where(np.isnan(s.data["power"]), np.nan, rng.choice([0, 1, 2, 11, 21], s.data["power"].shape)).astype(np.float32)
+    data = dict(s.data, inter=inter)
+    ds = make_dataset(dmb, data, s.bs_fov, s.ue_fov)
+    ds.set_channel_params(dmb.ChannelGenParameters(s.params))
+    o = orc.compute_channels(data, **oracle_kwargs_from_params(s.params, s.bs_fov, s.ue_fov))
+    fov = o["fov_mask"]
+    assert np.array_equal(ds.num_paths, fov.sum(1))                     # FoV-masked and NaN paths both drop out
+    want = np.full(300, -1)
+    for i in range(300):
+        idx = np.where(fov[i])[0]
+        if len(idx):
+            want[i] = 1 if inter[i, idx[0]] == 0 else 0
+    assert np.array_equal(ds.los, want) and set(np.unique(want)) == {-1, 0, 1}
+    p_lin = 10 ** (s.data["power"] / 10)
+    assert np.array_equal(ds.power_linear, p_lin, equal_nan=True)
+    tot = np.abs(np.nansum(np.sqrt(p_lin).astype(np.complex64) * np.exp(1j * np.deg2rad(s.data["phase"])), axis=1)) ** 2
+    pl = ds.pl
+    assert np.array_equal(np.isnan(pl), ~(tot > 0))
+    np.testing.assert_allclose(pl[tot > 0], -10 * np.log10(tot[tot > 0]), rtol=1e-6)
+    # no FoV: num_paths counts the valid paths, los looks at the first column
+    ds2 = make_dataset(dmb, data)
+    ds2.set_channel_params(dmb.ChannelGenParameters(s.params))
+    assert np.array_equal(ds2.num_paths, (~np.isnan(s.data["power"])).sum(1))
+    first = inter[:, 0]
+    assert np.array_equal(ds2.los == 1, first == 0)
