@@ -8,6 +8,7 @@
 
 #include "dmk_fd.cuh"
 #include "dmk_fd_tc.cuh"
+#include "dmk_fd_ws.cuh"
 #include "dmk_fd_small.cuh"
 #include "dmk_td.cuh"
 
@@ -216,7 +217,7 @@ int dmk_channels_fd(const dmk_desc* desc, const float* power_dbw, const float* p
     }
     // Tiny arrays (M < 64) and FoV-sparse scenarios are per-user-overhead bound: the packed-FP32 kernel is faster there
     // (profiles/README.md); DMK_FD_KERNEL=tc still forces the tensor-core kernel.
-    const bool want_tc = force && !strcmp(force, "tc");
+    const bool want_tc = force && (!strcmp(force, "tc") || !strcmp(force, "tc1") || !strcmp(force, "tcp"));
     const bool use_tc = affine && !d.has_time_axis && div_ok && (d.K % (kTcN / 2) == 0) && d.K <= 4096 && tc_smem <= 112 * 1024 &&
                         !want_tile && !want_ffma && ((d.M >= 64 && !d.fov_any) || want_tc);   // FoV leaves few paths, tiny arrays little output: FP32 kernel wins
     const bool use_fast = !use_tc && affine && !d.has_time_axis && div_ok && fast_smem <= 110 * 1024 && !want_tile;
@@ -273,6 +274,76 @@ int dmk_channels_fd(const dmk_desc* desc, const float* power_dbw, const float* p
             snprintf(g_kernel, sizeof(g_kernel), "fd_small_kernel<%d rows,warp/user> grid=%lld smem=%zu", mt, sgrid, small_smem);
             return DMK_OK;
         }
+    }
+    // Persistent tensor-core kernel with per-user look-ahead (default); DMK_FD_KERNEL=tc1 keeps the one-CTA-per-user version.
+    const bool want_tc1 = force && !strcmp(force, "tc1");
+    const bool want_tcp = force && !strcmp(force, "tcp");
+    TcCfg pcfg = tcfg;
+    size_t ptc_smem = 1024;
+    {
+        const int pc = (d.P > 0 ? d.P : 1) + 1;                  // + the zero row the builders read for padding slots
+        size_t off = 0;
+        auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 15) & ~size_t(15); return (int)o; };
+        pcfg.off_A = take((size_t)2 * pcfg.mtile * 128);
+        pcfg.off_B = take((size_t)pcfg.nsub * 2 * kTcN * 128);
+        pcfg.off_tab = (int)off;
+        size_t toff = 0;
+        auto ttake = [&](size_t bytes) { size_t o = toff; toff += (bytes + 15) & ~size_t(15); return (int)o; };
+        pcfg.wa_table = 0;
+        pcfg.sS = (8 + (pcfg.nA + 7) / 8) | 1;
+        pcfg.off_tY = ttake((size_t)pc * pcfg.sY * sizeof(float2));
+        pcfg.off_tQ = ttake((size_t)pc * pcfg.sQ * sizeof(float2));
+        pcfg.off_wB = ttake((size_t)pc * pcfg.sB * sizeof(float2));
+        pcfg.off_seed = ttake((size_t)pc * pcfg.sS * sizeof(float2));
+        pcfg.off_wA = 0;
+        pcfg.tab_bytes = (int)toff;
+        ptc_smem += off + 2 * toff;
+    }
+    const bool use_tcp = use_tc && !want_tc1 && ptc_smem <= 109600 && grid < 0xffffff00LL;   // + ~6 KB static + 1 KB reserve: two CTAs per SM
+    if (use_tcp && !want_tcp) {
+        // warp-specialised persistent kernel (dmk_fd_ws.cuh): the production tensor-core path
+        if (d.K == 1 && d.subc_step == 0) d.subc_step = 1;
+        static bool attr_ws = false;
+        if (!attr_ws) {
+            cudaError_t e = cudaFuncSetAttribute(fd_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(110 * 1024));
+            if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(fd_ws_kernel)");
+            attr_ws = true;
+        }
+        static std::atomic<unsigned> ticket_seq{0};
+        unsigned int* tickets = nullptr;
+        cudaError_t e = cudaGetSymbolAddress(reinterpret_cast<void**>(&tickets), g_tc_ticket);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaGetSymbolAddress(g_tc_ticket)");
+        const long long resident = 2LL * device_sm_count();
+        const long long pgrid = grid < resident ? grid : resident;
+        fd_ws_kernel<<<(unsigned)pgrid, kWsThreads, ptc_smem, st>>>(d, pcfg, (int)ksplit, (unsigned)grid,
+                                                                     tickets + (ticket_seq.fetch_add(1) % kTcTickets));
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return cuda_fail(e, "fd_ws_kernel launch");
+        g_launches.fetch_add(1);
+        snprintf(g_kernel, sizeof(g_kernel), "fd_ws_kernel<%dx128,3xf16> grid=%lld items=%lld ksplit=%lld smem=%zu", pcfg.mtile, pgrid, grid, ksplit, ptc_smem);
+        return DMK_OK;
+    }
+    if (use_tcp) {
+        if (d.K == 1 && d.subc_step == 0) d.subc_step = 1;
+        static bool attr_tcp = false;
+        if (!attr_tcp) {
+            cudaError_t e = cudaFuncSetAttribute(fd_tc_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(110 * 1024));
+            if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(fd_tc_persist_kernel)");
+            attr_tcp = true;
+        }
+        static std::atomic<unsigned> ticket_seq{0};
+        unsigned int* tickets = nullptr;
+        cudaError_t e = cudaGetSymbolAddress(reinterpret_cast<void**>(&tickets), g_tc_ticket);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaGetSymbolAddress(g_tc_ticket)");
+        const long long resident = 2LL * device_sm_count();
+        const long long pgrid = grid < resident ? grid : resident;
+        fd_tc_persist_kernel<<<(unsigned)pgrid, kTcPThreads, ptc_smem, st>>>(d, pcfg, (int)ksplit, (unsigned)grid,
+                                                                              tickets + (ticket_seq.fetch_add(1) % kTcTickets));
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return cuda_fail(e, "fd_tc_persist_kernel launch");
+        g_launches.fetch_add(1);
+        snprintf(g_kernel, sizeof(g_kernel), "fd_tc_persist_kernel<%dx128,3xf16> grid=%lld items=%lld ksplit=%lld smem=%zu", pcfg.mtile, pgrid, grid, ksplit, ptc_smem);
+        return DMK_OK;
     }
     if (use_tc) {
         if (d.K == 1 && d.subc_step == 0) d.subc_step = 1;
