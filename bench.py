@@ -169,7 +169,7 @@ def time_plan(plan, out_ring, chunk, steps, warmup, flush, dist, world):
         i = 0
         for a in range(0, n, chunk):
             b = min(a + chunk, n)
-            plan.run(out_ring[i % len(out_ring)][: b - a], a, b)
+            plan.run(out_ring[i % len(out_ring)][: b - a], a, b, independent=(i > 0 and len(out_ring) > 1))
             i += 1
 
     for _ in range(warmup):

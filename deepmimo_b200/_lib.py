@@ -38,10 +38,12 @@ class DmkDesc(ctypes.Structure):
         ("rx_filter", ctypes.c_int32),
         ("n_times", ctypes.c_int32),
         ("times", ctypes.c_void_p),
+        ("flags", ctypes.c_int32),
     ]
 
 
-ABI_VERSION = 1
+ABI_VERSION = 2
+FLAG_INDEPENDENT_LAUNCH = 1
 SYMBOLS = ("dmk_channels_fd", "dmk_channels_td", "dmk_path_prologue", "dmk_np_sincosf",
            "dmk_last_error", "dmk_abi_version", "dmk_launch_count", "dmk_last_kernel")
 

@@ -310,9 +310,13 @@ class ChannelPlan:
         return m
 
     # -- launch
-    def run(self, out, start: int = 0, stop: Optional[int] = None, masks: Optional[dict] = None, stream=None):
+    def run(self, out, start: int = 0, stop: Optional[int] = None, masks: Optional[dict] = None, stream=None,
+            independent: bool = False):
         """Launch the fused kernel for users [start, stop) into `out` (complex64 CUDA tensor whose
-        first dimension is stop-start).  `masks` tensors (from alloc_masks) are indexed the same way."""
+        first dimension is stop-start).  `masks` tensors (from alloc_masks) are indexed the same way.
+        `independent=True` (DMK_FLAG_INDEPENDENT_LAUNCH, include/dmk.h) tells the library that this launch does not
+        touch anything the previous kernel on the stream writes -- consecutive chunks of one user range going to
+        different buffers -- so it may start while that kernel drains its tail."""
         torch = _torch()
         stop = self.n_users if stop is None else stop
         n = stop - start
@@ -325,6 +329,7 @@ class ChannelPlan:
         ptr = lambda t, row=start: None if t is None else t.data_ptr() + row * t.stride(0) * t.element_size()
         m = masks or {}
         mp = lambda k: None if m.get(k) is None else m[k].data_ptr()
+        self.desc.flags = _lib.FLAG_INDEPENDENT_LAUNCH if independent else 0
         common = [ctypes.byref(self.desc)] + [ptr(self.t[k]) for k in PATH_KEYS] + \
                  [ptr(self.ue_rot), ptr(self.doppler), n, self.n_cols, out.data_ptr()]
         with torch.cuda.device(self.device):
@@ -407,7 +412,7 @@ def iter_channels(plan: ChannelPlan, chunk_users: Optional[int] = None, n_buffer
     for start in range(0, plan.n_users, chunk):
         stop = min(start + chunk, plan.n_users)
         buf = ring[i % len(ring)][: stop - start]
-        plan.run(buf, start, stop)
+        plan.run(buf, start, stop, independent=(i > 0 and len(ring) > 1))   # chunks of one range, different buffers
         yield start, stop, buf
         i += 1
 

@@ -315,8 +315,20 @@ int dmk_channels_fd(const dmk_desc* desc, const float* power_dbw, const float* p
         if (e != cudaSuccess) return cuda_fail(e, "cudaGetSymbolAddress(g_tc_ticket)");
         const long long resident = 2LL * device_sm_count();
         const long long pgrid = grid < resident ? grid : resident;
-        fd_ws_kernel<<<(unsigned)pgrid, kWsThreads, ptc_smem, st>>>(d, pcfg, (int)ksplit, (unsigned)grid,
-                                                                     tickets + (ticket_seq.fetch_add(1) % kTcTickets));
+        // Programmatic dependent launch: the kernel releases its dependents at once, so the next libdmk launch can fill SMs
+        // as this one's persistent CTAs retire.  Unless the caller set DMK_FLAG_INDEPENDENT_LAUNCH the kernel itself
+        // waits for the previous grid (griddepcontrol.wait) before touching memory: plain stream order.
+        const int pdl_wait = (desc->flags & DMK_FLAG_INDEPENDENT_LAUNCH) ? 0 : 1;
+        cudaLaunchConfig_t lc;
+        memset(&lc, 0, sizeof(lc));
+        lc.gridDim = dim3((unsigned)pgrid); lc.blockDim = dim3(kWsThreads); lc.dynamicSmemBytes = ptc_smem; lc.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        lc.attrs = at; lc.numAttrs = 1;
+        e = cudaLaunchKernelEx(&lc, fd_ws_kernel, d, pcfg, (int)ksplit, (unsigned)grid,
+                               tickets + (ticket_seq.fetch_add(1) % kTcTickets), pdl_wait);
+        if (e != cudaSuccess) return cuda_fail(e, "fd_ws_kernel launch");
         e = cudaGetLastError();
         if (e != cudaSuccess) return cuda_fail(e, "fd_ws_kernel launch");
         g_launches.fetch_add(1);

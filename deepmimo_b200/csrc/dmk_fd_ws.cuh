@@ -191,11 +191,13 @@ __device__ __forceinline__ void ws_drain(uint32_t tmem_base, int acc_col, float*
 
 __global__ void __launch_bounds__(kWsThreads, 2)
 fd_ws_kernel(const __grid_constant__ DevDesc d, const __grid_constant__ TcCfg cfg, const int ksplit,
-             const unsigned int n_items, unsigned int* ticket)
+             const unsigned int n_items, unsigned int* ticket, const int pdl_wait)
 {
     extern __shared__ unsigned char smem_raw[];
     __shared__ TcUserBuf ub[2];
     __shared__ WsBars bars;
+    if (pdl_wait) asm volatile("griddepcontrol.wait;" ::: "memory");     // plain stream order unless the caller declared independence
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");      // the next launch may take SMs as our CTAs retire
     __shared__ uint32_t tmem_base_s;
     __shared__ float2 sWa[kTcSlots * 9];              // stage-local coarse delay phasors [slot][8 groups of 16 subcarriers], stride 9
 

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define DMK_ABI_VERSION 1
+#define DMK_ABI_VERSION 2
 #define DMK_MAX_PATHS   32    /* path columns per user handled by one launch (reference: MAX_PATHS = 25, consts.py:180) */
 #define DMK_MAX_TIMES   4096  /* time snapshots per launch */
 
@@ -74,7 +74,16 @@ typedef struct dmk_desc {
     int32_t rx_filter;          /* must be 0 (channel.py:193-194 not implemented yet)               */
     int32_t n_times;            /* 0 = no trailing time axis; T >= 1 appends [.., T] (row a11)      */
     const double *times;        /* DEVICE pointer, [T] snapshot times in seconds                    */
+    int32_t flags;              /* DMK_FLAG_* (ABI 2); 0 = plain stream-ordered launch                   */
 } dmk_desc;
+
+/* dmk_desc.flags.
+ * DMK_FLAG_INDEPENDENT_LAUNCH: the caller asserts that this launch neither reads nor overwrites anything the
+ * kernel launched immediately before it on the same stream writes (e.g. consecutive user chunks of one
+ * compute_channels call going to different output buffers).  The persistent tensor-core kernel then starts
+ * filling SMs while the previous launch drains its tail (programmatic dependent launch without a grid
+ * dependency wait).  Without the flag every launch observes full stream order. */
+#define DMK_FLAG_INDEPENDENT_LAUNCH 1
 
 /* Frequency-domain channels (freq_domain = 1):
  *   out[u, r, t, k (, it)] = sum_p c_p a_rx[r,p] a_tx[t,p] exp(-j 2 pi k delay_n[p] / N) (* exp(+j 2 pi f_D[p] t_it))

@@ -1,4 +1,4 @@
-"""Edge cases of the tensor-core FD kernel (fd_tc_kernel, forced with DMK_FD_KERNEL=tc) against the oracle:
+"""Edge cases of the tensor-core FD kernels (fd_ws_kernel / fd_tc_kernel, forced with DMK_FD_KERNEL=tc / tc1) against the oracle:
 tile raggedness in M and K, 32 path columns, FP16 operand scaling under a 150 dB power spread, sub-tiled small arrays,
 single-path users, K split across CTAs (few users)."""
 import numpy as np
@@ -24,19 +24,23 @@ def _case(n, bs, ue, n_sc, k_sel, seed, n_cols=25, bs_rot=(10, 20, 30), power_lo
     return d, p
 
 
-def _run(d, p, monkeypatch, expect="fd_tc_kernel"):
+def _run(d, p, monkeypatch, expect=("fd_ws_kernel", "fd_tc_kernel")):
+    """Both tensor-core kernels: DMK_FD_KERNEL=tc is the warp-specialised persistent kernel (fd_ws_kernel; it hands shapes whose
+    double-buffered tables do not fit to fd_tc_kernel), tc1 the one-CTA-per-user kernel.  Returns the worst error and the last info."""
     import deepmimo_b200 as dmb
     from oracle import channel_oracle as orc
-    monkeypatch.setenv("DMK_FD_KERNEL", "tc")
-    H, info = make_dataset(dmb, d).compute_channels(dmb.ChannelGenParameters(p), return_info=True, warn=False)
     o = orc.compute_channels(d, bs_shape=p["bs_antenna"]["shape"], ue_shape=p["ue_antenna"]["shape"],
                              bs_rotation=p["bs_antenna"]["rotation"], num_paths=p["num_paths"],
                              subcarriers=p["ofdm"]["subcarriers"], selected_subcarriers=p["ofdm"]["selected_subcarriers"],
                              bandwidth=p["ofdm"]["bandwidth"])
-    assert info.kernel.startswith(expect), info.kernel
-    err = assert_channels_close(H, o["H"], what=info.kernel)
-    assert np.array_equal(info.valid, o["valid"]) and np.array_equal(info.clip, o["clip"])
-    return err, info
+    worst, info = 0.0, None
+    for variant in ("tc", "tc1"):
+        monkeypatch.setenv("DMK_FD_KERNEL", variant)
+        H, info = make_dataset(dmb, d).compute_channels(dmb.ChannelGenParameters(p), return_info=True, warn=False)
+        assert info.kernel.startswith(tuple(expect) if variant == "tc" else (expect[-1],)), info.kernel
+        worst = max(worst, assert_channels_close(H, o["H"], what=info.kernel))
+        assert np.array_equal(info.valid, o["valid"]) and np.array_equal(info.clip, o["clip"])
+    return worst, info
 
 
 @pytest.mark.parametrize("bs,ue,k", [((8, 8), (1, 1), 64),          # one segment, one 64-row tile
@@ -60,7 +64,7 @@ def test_tc_k4096_and_fallback_beyond(monkeypatch):
     d, p = _case(6, (8, 8), (1, 1), 4096, np.arange(4096), 33)
     _run(d, p, monkeypatch)
     d, p = _case(4, (8, 8), (1, 1), 8192, np.arange(8192), 34)
-    _run(d, p, monkeypatch, expect="fd_")                 # K > 4096: the tensor-core kernel is not eligible, another FD kernel runs
+    _run(d, p, monkeypatch, expect=("fd_",))                 # K > 4096: the tensor-core kernel is not eligible, another FD kernel runs
 
 
 def test_tc_fp16_scaling_under_150_db_spread(monkeypatch):
@@ -78,3 +82,29 @@ def test_tc_single_path_users_and_few_users_split_over_ctas(monkeypatch):
     d, p = _case(3, (16, 8), (1, 1), 1024, np.arange(1024), 37, n_cols=1, zero_frac=0.0)       # ksplit > 1, np = 1
     err, info = _run(d, p, monkeypatch)
     assert "ksplit=" in info.kernel and int(info.kernel.split("ksplit=")[1].split()[0]) > 1
+
+
+def test_ws_many_users_per_cta_chunked_independent_launches_and_ticket_reuse():
+    """Persistent kernel: far more users than resident CTAs (several users per CTA, zero-path users interleaved), the
+    user range streamed through iter_channels' ring (chunks after the first are launched with DMK_FLAG_INDEPENDENT_LAUNCH
+    and may overlap the previous chunk's tail), and the whole thing twice (ticket counters must return to zero)."""
+    import torch
+    import deepmimo_b200 as dmb
+    from oracle import channel_oracle as orc
+    d, p = _case(2500, (8, 8), (1, 1), 1024, np.arange(128), 41, zero_frac=0.2)
+    o = orc.compute_channels(d, bs_shape=p["bs_antenna"]["shape"], ue_shape=p["ue_antenna"]["shape"],
+                             bs_rotation=p["bs_antenna"]["rotation"], num_paths=p["num_paths"],
+                             subcarriers=p["ofdm"]["subcarriers"], selected_subcarriers=p["ofdm"]["selected_subcarriers"],
+                             bandwidth=p["ofdm"]["bandwidth"])
+    plan, _ = dmb.make_plan(make_dataset(dmb, d), dmb.ChannelGenParameters(p), warn=False)
+    for rep in range(2):
+        H = np.empty(plan.out_shape(), dtype=np.complex64)
+        chunks = list(dmb.iter_channels(plan, chunk_users=700, n_buffers=4))     # 4 chunks back to back, one buffer each
+        torch.cuda.synchronize()
+        for start, stop, buf in chunks:
+            H[start:stop] = buf.cpu().numpy()
+        from deepmimo_b200 import _lib
+        assert _lib.last_kernel().startswith("fd_ws_kernel"), _lib.last_kernel()
+        err = assert_channels_close(H, o["H"], what=f"ws chunked rep {rep}")
+        assert err < 2e-6
+    torch.cuda.synchronize()
