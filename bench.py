@@ -169,7 +169,7 @@ def time_plan(plan, out_ring, chunk, steps, warmup, flush, dist, world):
         i = 0
         for a in range(0, n, chunk):
             b = min(a + chunk, n)
-            plan.run(out_ring[i % len(out_ring)][: b - a], a, b, independent=(i > 0 and len(out_ring) > 1))
+            plan.run(out_ring[i % len(out_ring)][: b - a], a, b, independent=(i > 0 and len(out_ring) > 1 and not os.environ.get("DMK_BENCH_NO_PDL")))
             i += 1
 
     for _ in range(warmup):
@@ -207,11 +207,11 @@ def run_workload(workload, users, steps, warmup, rank, world, dist, flush, want_
     per_user = plan.spec.coefs_per_user(plan.n_cols) * 8
     total_bytes = per_user * plan.n_users
     free_b, _tot = torch.cuda.mem_get_info()
-    if total_bytes <= min(64 << 30, int(free_b * 0.6)):
+    if total_bytes <= min(64 << 30, int(free_b * 0.6)) and not os.environ.get("DMK_BENCH_FORCE_RING"):
         chunk, ring = plan.n_users, [plan.alloc_out()]
         layout = f"single [{plan.n_users} users] output tensor ({total_bytes / 2**30:.1f} GiB) rewritten every step"
     else:
-        chunk = default_chunk_users(plan, 4 << 30)          # ring of 4 GiB chunks (SURVEY.md 8d cfg 5)
+        chunk = default_chunk_users(plan, int(float(os.environ.get("DMK_BENCH_CHUNK_GIB", "4")) * (1 << 30)))   # ring of 4 GiB chunks (SURVEY.md 8d cfg 5)
         ring = [plan.alloc_out(chunk) for _ in range(3)]
         layout = f"ring of 3 x {chunk} users ({chunk * per_user / 2**30:.1f} GiB) output chunks in HBM"
     # masks once (also gives the algorithmic flop count)
@@ -225,7 +225,7 @@ def run_workload(workload, users, steps, warmup, rank, world, dist, flush, want_
     info = plan.info_from_masks(masks)
     n_coef, bytes_alg, flops, pbar = algorithmic_counts(s, plan, info)
 
-    sampler = ClockSampler(torch.cuda.current_device()) if want_clocks else None
+    sampler = ClockSampler(torch.cuda.current_device()) if (want_clocks and not os.environ.get("DMK_BENCH_NO_CLOCKS")) else None
     l0 = _lib.launch_count()
     if sampler:
         sampler.start()

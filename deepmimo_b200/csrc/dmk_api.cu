@@ -217,7 +217,7 @@ int dmk_channels_fd(const dmk_desc* desc, const float* power_dbw, const float* p
     }
     // Tiny arrays (M < 64) and FoV-sparse scenarios are per-user-overhead bound: the packed-FP32 kernel is faster there
     // (profiles/README.md); DMK_FD_KERNEL=tc still forces the tensor-core kernel.
-    const bool want_tc = force && (!strcmp(force, "tc") || !strcmp(force, "tc1") || !strcmp(force, "tcp"));
+    const bool want_tc = force && (!strcmp(force, "tc") || !strcmp(force, "tc1"));
     const bool use_tc = affine && !d.has_time_axis && div_ok && (d.K % (kTcN / 2) == 0) && d.K <= 4096 && tc_smem <= 112 * 1024 &&
                         !want_tile && !want_ffma && ((d.M >= 64 && !d.fov_any) || want_tc);   // FoV leaves few paths, tiny arrays little output: FP32 kernel wins
     const bool use_fast = !use_tc && affine && !d.has_time_axis && div_ok && fast_smem <= 110 * 1024 && !want_tile;
@@ -275,9 +275,9 @@ int dmk_channels_fd(const dmk_desc* desc, const float* power_dbw, const float* p
             return DMK_OK;
         }
     }
-    // Persistent tensor-core kernel with per-user look-ahead (default); DMK_FD_KERNEL=tc1 keeps the one-CTA-per-user version.
+    // Warp-specialised persistent tensor-core kernel (default); DMK_FD_KERNEL=tc1 keeps the one-CTA-per-user version, which also
+    // takes the shapes whose double-buffered tables do not fit next to the operand tiles.
     const bool want_tc1 = force && !strcmp(force, "tc1");
-    const bool want_tcp = force && !strcmp(force, "tcp");
     TcCfg pcfg = tcfg;
     size_t ptc_smem = 1024;
     {
@@ -300,7 +300,7 @@ int dmk_channels_fd(const dmk_desc* desc, const float* power_dbw, const float* p
         ptc_smem += off + 2 * toff;
     }
     const bool use_tcp = use_tc && !want_tc1 && ptc_smem <= 109600 && grid < 0xffffff00LL;   // + ~6 KB static + 1 KB reserve: two CTAs per SM
-    if (use_tcp && !want_tcp) {
+    if (use_tcp) {
         // warp-specialised persistent kernel (dmk_fd_ws.cuh): the production tensor-core path
         if (d.K == 1 && d.subc_step == 0) d.subc_step = 1;
         static bool attr_ws = false;
@@ -333,28 +333,6 @@ int dmk_channels_fd(const dmk_desc* desc, const float* power_dbw, const float* p
         if (e != cudaSuccess) return cuda_fail(e, "fd_ws_kernel launch");
         g_launches.fetch_add(1);
         snprintf(g_kernel, sizeof(g_kernel), "fd_ws_kernel<%dx128,3xf16> grid=%lld items=%lld ksplit=%lld smem=%zu", pcfg.mtile, pgrid, grid, ksplit, ptc_smem);
-        return DMK_OK;
-    }
-    if (use_tcp) {
-        if (d.K == 1 && d.subc_step == 0) d.subc_step = 1;
-        static bool attr_tcp = false;
-        if (!attr_tcp) {
-            cudaError_t e = cudaFuncSetAttribute(fd_tc_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(110 * 1024));
-            if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(fd_tc_persist_kernel)");
-            attr_tcp = true;
-        }
-        static std::atomic<unsigned> ticket_seq{0};
-        unsigned int* tickets = nullptr;
-        cudaError_t e = cudaGetSymbolAddress(reinterpret_cast<void**>(&tickets), g_tc_ticket);
-        if (e != cudaSuccess) return cuda_fail(e, "cudaGetSymbolAddress(g_tc_ticket)");
-        const long long resident = 2LL * device_sm_count();
-        const long long pgrid = grid < resident ? grid : resident;
-        fd_tc_persist_kernel<<<(unsigned)pgrid, kTcPThreads, ptc_smem, st>>>(d, pcfg, (int)ksplit, (unsigned)grid,
-                                                                              tickets + (ticket_seq.fetch_add(1) % kTcTickets));
-        e = cudaGetLastError();
-        if (e != cudaSuccess) return cuda_fail(e, "fd_tc_persist_kernel launch");
-        g_launches.fetch_add(1);
-        snprintf(g_kernel, sizeof(g_kernel), "fd_tc_persist_kernel<%dx128,3xf16> grid=%lld items=%lld ksplit=%lld smem=%zu", pcfg.mtile, pgrid, grid, ksplit, ptc_smem);
         return DMK_OK;
     }
     if (use_tc) {

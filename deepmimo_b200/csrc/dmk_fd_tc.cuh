@@ -492,24 +492,8 @@ fd_tc_kernel(const __grid_constant__ DevDesc d, const __grid_constant__ TcCfg cf
 }
 
 
-// =====================================================================================================================
-// Persistent variant with a per-user look-ahead (the production tensor-core kernel).
-//
-// Phase timing of fd_tc_kernel on the city-scale shape (64 rows x 1024 subcarriers = 512 KB per user; tools/tc_trace.py):
-// per user ~10 k cycles of float64 prologue (three latency-bound dependency chains) + ~6.5 k cycles of table building +
-// ~62 k cycles of stages -- 20 % of a CTA's life issues no stores at all, and with two CTAs per SM HBM sits at 61 %.
-// Here a CTA is persistent (2 per SM, users drawn from a device-side ticket counter) and owns a tenth warp, the
-// *helper*: while warps 0-8 run the stages of user i out of table buffer i & 1, the helper draws the next ticket, runs
-// the prologue of user i+1 (lanes = path columns, the three chains back to back) and builds its tables into buffer
-// (i+1) & 1.  One CTA barrier per user swaps the buffers.  The accumulator pipeline is carried across users: the last
-// stage of user i is drained under the first MMAs of user i+1 instead of behind a barrier.
-// The coarse delay table wA is never materialised here (one extra complex multiply per B entry from the seed tables):
-// two table buffers then fit next to the operand tiles with two CTAs per SM.
-// =====================================================================================================================
-constexpr int kTcPThreads = 320;   // warps 0-7 workers, warp 8 MMA issuer, warp 9 helper
-constexpr int kTcPStage   = 288;   // threads that take part in the stage barriers (named barriers 1 and 2)
-constexpr int kTcTickets  = 64;
-
+// Shared with the warp-specialised persistent kernel (dmk_fd_ws.cuh): device-side ticket counters and the per-user record.
+constexpr int kTcTickets = 64;
 __device__ unsigned int g_tc_ticket[kTcTickets];   // zero between launches: the CTA that draws the last ticket resets it
 
 struct TcUserBuf {
@@ -517,331 +501,5 @@ struct TcUserBuf {
     float scale;
     unsigned int item;
 };
-
-struct TcPrev { int row0, ct, acc, nsub; float* out_u; float scale; };
-
-// Helper warp: ticket -> prologue -> per-user tables of one buffer.  lanes = path columns, then lanes = table entries.
-__device__ __noinline__ void tc_helper_prepare(const DevDesc& d, const TcCfg& cfg, int ksplit, unsigned int n_items,
-                                               unsigned int* ticket, TcUserBuf& ub, unsigned char* tab, int lane)
-{
-    unsigned int t = 0;
-    if (lane == 0) {
-        t = atomicAdd(ticket, 1u);
-        if (t == n_items + gridDim.x - 1u) atomicExch(ticket, 0u);      // every CTA draws exactly one ticket >= n_items: this is the last draw
-        ub.item = t;
-    }
-    t = __shfl_sync(0xffffffffu, t, 0);
-    if (t >= n_items) return;
-    const long long user = t / (unsigned)ksplit;
-    const bool write_masks = (t % (unsigned)ksplit) == 0;
-    FdShared& sh = ub.sh;
-
-    PathState st;
-    const bool active = lane < d.P0;
-    st.contrib = false; st.valid = false; st.fov = true; st.over = false;
-    st.c = make_float2(0.f, 0.f);
-    if (active) {
-        SideOut s0, s1;
-        GainOut g;
-        if (prologue_needs_angles(d)) { prologue_side<true>(d, user, lane, 0, s0);  prologue_side<true>(d, user, lane, 1, s1); }
-        else                          { prologue_side<false>(d, user, lane, 0, s0); prologue_side<false>(d, user, lane, 1, s1); }
-        prologue_gain<true>(d, user, lane, g);
-        prologue_combine<true>(d, s0, s1, g, st);
-    }
-    const bool contrib = active && st.contrib;
-    const unsigned ballot = __ballot_sync(0xffffffffu, contrib);
-    const int np = __popc(ballot);
-    if (contrib) {
-        const int j = __popc(ballot & ((1u << lane) - 1u));
-        sh.c[j] = st.c; sh.wcyc[j] = st.wcyc; sh.fd[j] = st.fd;
-        sh.u[0][j] = st.u[0]; sh.v[0][j] = st.v[0];
-        sh.u[1][j] = st.u[1]; sh.v[1][j] = st.v[1];
-    }
-    if (lane == 0) sh.np = np;
-    if (write_masks && active) {
-        const long long o = user * (long long)d.P0 + lane;
-        if (d.fov_mask)   d.fov_mask[o]   = st.fov ? 1 : 0;
-        if (d.valid_mask) d.valid_mask[o] = st.valid ? 1 : 0;
-        if (d.clip_mask)  d.clip_mask[o]  = (st.valid && st.over) ? 1 : 0;
-    }
-    if (np == 0) return;
-    // per-user operand scale: largest |c_p| component (FP16 operands live in [-1, 1])
-    float mx = contrib ? fmaxf(fabsf(st.c.x), fabsf(st.c.y)) : 0.f;
-    #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    if (lane == 0) ub.scale = mx;
-    const float inv_scale = 1.0f / mx;
-    __syncwarp();
-
-    float2* tY   = reinterpret_cast<float2*>(tab + cfg.off_tY);
-    float2* tQ   = reinterpret_cast<float2*>(tab + cfg.off_tQ);
-    float2* wB   = reinterpret_cast<float2*>(tab + cfg.off_wB);
-    float2* seed = reinterpret_cast<float2*>(tab + cfg.off_seed);
-    const int bs0 = d.bs0, bs1 = d.bs1, nq = d.Mr * d.bs1;
-    for (int e = lane; e < np * bs0; e += 32) {
-        const int p = e / bs0, y = e - p * bs0;
-        tY[p * cfg.sY + y] = phasor_cycles((double)y * sh.u[0][p]);
-    }
-    for (int e = lane; e < np * nq; e += 32) {
-        const int p = e / nq, q = e - p * nq;
-        const int r = q / bs1, z = q - r * bs1;
-        const int yr = r % d.ue0, zr = r / d.ue0;
-        const float2 cs = make_float2(sh.c[p].x * inv_scale, sh.c[p].y * inv_scale);
-        tQ[p * cfg.sQ + q] = cmul(cs, phasor_cycles((double)z * sh.v[0][p] + (double)yr * sh.u[1][p] + (double)zr * sh.v[1][p]));
-    }
-    for (int e = lane; e < np * 16; e += 32) {
-        const int p = e >> 4, b = e & 15;
-        wB[p * cfg.sB + b] = phasor_cycles(-(sh.wcyc[p] * (double)(d.subc_step * b)));
-    }
-    const int n_hi = (cfg.nA + 7) >> 3, n_sd = 8 + n_hi;
-    for (int e = lane; e < np * n_sd; e += 32) {
-        const int p = e / n_sd, b = e - p * n_sd;
-        seed[p * cfg.sS + b] = (b < 8) ? phasor_cycles(-(sh.wcyc[p] * (double)(d.subc_step * 16 * b)))                             // seed_lo[b]
-                                       : phasor_cycles(-(sh.wcyc[p] * (double)(d.subc_start + d.subc_step * 128 * (b - 8))));     // seed_hi[b - 8]
-    }
-}
-
-__global__ void __launch_bounds__(kTcPThreads, 2)
-fd_tc_persist_kernel(const __grid_constant__ DevDesc d, const __grid_constant__ TcCfg cfg, const int ksplit,
-                     const unsigned int n_items, unsigned int* ticket)
-{
-    extern __shared__ unsigned char smem_raw[];
-    __shared__ TcUserBuf ub[2];
-    __shared__ uint64_t mbar;
-    __shared__ uint32_t tmem_base_s;
-
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const bool is_worker = tid < kTcWorkers;           // warps 0-7
-    const bool is_helper = warp == 9;                  // warp 8 only issues MMAs
-    const int mtile = cfg.mtile, nsub = cfg.nsub;
-
-    unsigned char* sm = smem_raw + (((smem_u32(smem_raw) + 1023u) & ~1023u) - smem_u32(smem_raw));
-    unsigned char* sAhi = sm + cfg.off_A;                    // [mtile rows][128 B]: 32 path slots x (re, im) fp16
-    unsigned char* sAlo = sAhi + mtile * 128;
-    unsigned char* sBhi = sm + cfg.off_B;                    // per sub-tile: [128 rows][128 B] hi, then lo
-    unsigned char* sBlo = sBhi + kTcN * 128;
-    unsigned char* tab0 = sm + cfg.off_tab;
-
-    if (warp == 3) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(&tmem_base_s)), "r"(2 * 128));
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
-    }
-    if (tid == 64) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&mbar)));
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    if (is_helper) tc_helper_prepare(d, cfg, ksplit, n_items, ticket, ub[0], tab0, lane);
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t tmem_base = tmem_base_s;
-    const int K = d.K, M = d.M;
-    const int n_seg = K / (kTcN / 2);                         // 64-subcarrier segments per row
-    const int n_ct = (n_seg + nsub - 1) / nsub;               // pipeline stages (column super-tiles) per row tile
-    const int n_rt = (M + mtile - 1) / mtile;
-    const long long pitch = 2LL * K;                          // floats per output row
-
-    // instruction descriptor: D = F32, A = B = F16 (format 0), both K-major, N = antenna rows of the tile, M = 128 floats
-    const uint32_t idesc = (1u << 4) | ((uint32_t)(mtile >> 3) << 17) | ((uint32_t)(kTcN >> 4) << 24);
-    const uint64_t dAhi = umma_desc_kmajor_sw128(smem_u32(sAhi)), dAlo = umma_desc_kmajor_sw128(smem_u32(sAlo));
-    const uint64_t dBhi = umma_desc_kmajor_sw128(smem_u32(sBhi)), dBlo = umma_desc_kmajor_sw128(smem_u32(sBlo));
-    const int acc_stride = 128 / nsub;            // TMEM columns per accumulator; 2 * nsub accumulators in 256 columns
-
-    // Operand builders (see fd_tc_kernel): a thread owns one antenna row (A) / one subcarrier (B) and a run of path slots.
-    const int a_row  = tid & (mtile - 1);
-    const int a_ngrp = kTcWorkers / mtile;
-    const int a_grp  = tid / mtile;
-    const int a_off0 = (a_row >> 3) * 1024 + (a_row & 7) * 128;
-    const int b_col  = tid & 63;
-    const int b_grp  = tid >> 6;
-    const int b_row0 = 2 * b_col;
-    const int b_off0 = (b_row0 >> 3) * 1024 + (b_row0 & 7) * 128;
-
-    uint32_t phase = 0;
-    bool pending = false, have_prev = false;      // an MMA commit is outstanding / a stage waits for its epilogue (carried across users)
-    TcPrev prev = {0, 0, 0, 0, nullptr, 0.f};
-    int tile_idx = 0;
-#ifdef DMK_TC_TRACE
-    const bool trace_cta = (blockIdx.x == gridDim.x / 2);
-    int stage_no = 0;
-    const int tb = (tid == 0) ? 0 : 8;
-#endif
-
-    for (int it = 0;; ++it) {
-        const int cur = it & 1;
-        const unsigned int item = ub[cur].item;
-        if (item >= n_items) break;
-#ifdef DMK_TC_TRACE
-        const bool trace_on = trace_cta && it >= 3 && stage_no < 240 && (tid == 0 || tid == kTcWorkers);
-        if (trace_cta && it >= 3 && it < 9 && (tid == 0 || tid == 288)) g_tc_trace[4000 + 8 * (it - 3) + (tid == 0 ? 0 : 2)] = clock64();
-        if (trace_cta && it >= 3 && it < 9 && tid == 0) g_tc_trace[4000 + 8 * (it - 3) + 5] = ub[cur].sh.np;
-#endif
-        if (is_helper) {
-            tc_helper_prepare(d, cfg, ksplit, n_items, ticket, ub[cur ^ 1], tab0 + (cur ^ 1) * cfg.tab_bytes, lane);
-#ifdef DMK_TC_TRACE
-            if (trace_cta && it >= 3 && it < 9 && tid == 288) g_tc_trace[4000 + 8 * (it - 3) + 3] = clock64();
-#endif
-        } else {
-            const long long user = item / (unsigned)ksplit;
-            const int ks = (int)(item % (unsigned)ksplit);
-            const FdShared& sh = ub[cur].sh;
-            const int np = sh.np;
-            float* out_u = reinterpret_cast<float*>(d.out + user * (long long)M * K);
-            if (np == 0) {
-                // users without contributing paths: zeros (channel.py:257,:269-271), coalesced
-                if (is_worker) {
-                    float4* o = reinterpret_cast<float4*>(out_u);
-                    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-                    const int c4 = tid & 31, r0 = tid >> 5;           // 32 float4 per row of a segment, 8 rows per pass
-                    for (int ct = ks; ct < n_ct; ct += ksplit)
-                        for (int sub = 0; sub < nsub && ct * nsub + sub < n_seg; ++sub) {
-                            float4* ot = o + (ct * nsub + sub) * (kTcN / 4) + c4;
-                            for (int m = r0; m < M; m += kTcWorkers / 32) __stcs(ot + (long long)m * (pitch / 4), z);
-                        }
-                }
-            } else {
-                const unsigned char* tab = tab0 + cur * cfg.tab_bytes;
-                const float2* tY   = reinterpret_cast<const float2*>(tab + cfg.off_tY);
-                const float2* tQ   = reinterpret_cast<const float2*>(tab + cfg.off_tQ);
-                const float2* wB   = reinterpret_cast<const float2*>(tab + cfg.off_wB);
-                const float2* seed = reinterpret_cast<const float2*>(tab + cfg.off_seed);
-                const float scale = ub[cur].scale;
-                const int ksteps = (np + 7) >> 3;                     // 16 fp16 (8 path slots) per MMA
-                const int nslot = ksteps * 8;                         // slots the tensor core reads; slots >= np are written as zeros
-                bool a_valid = false;                                 // A tile in smem is still current (single row tile)
-                for (int ct = ks; ct < n_ct; ct += ksplit) {
-                    const int seg0 = ct * nsub;
-                    const int nsub_here = min(nsub, n_seg - seg0);
-                    bool b_valid = false;                     // B tiles of this column stage are in smem (reused by every row tile)
-                    for (int rt = 0; rt < n_rt; ++rt) {
-                        const int row0 = rt * mtile;
-                        TC_TRACE(16 * stage_no + tb + 0);
-                        if (pending) {                        // the previous MMA group has finished reading A/B (and writing its accumulator)
-                            if (!is_worker) mbar_wait_parity(smem_u32(&mbar), phase);
-                            asm volatile("bar.sync 1, %0;" :: "n"(kTcPStage) : "memory");
-                            phase ^= 1;
-                            pending = false;
-                            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                        }
-                        TC_TRACE(16 * stage_no + tb + 1);
-                        // ---- A_hi / A_lo: antenna rows x path slots
-                        if (is_worker && !(a_valid && n_rt == 1)) {
-                            const int am = row0 + a_row;
-                            const bool a_ok = am < M;
-                            int a_q = 0, a_y = 0;
-                            if (a_ok) {
-                                const unsigned mm = (unsigned)am;
-                                const unsigned rr = cfg.mul_mt ? __umulhi(mm, cfg.mul_mt) : mm;
-                                const unsigned t = mm - rr * (unsigned)d.Mt;
-                                const unsigned zt = cfg.mul_bs0 ? __umulhi(t, cfg.mul_bs0) : t;
-                                a_y = (int)(t - zt * (unsigned)d.bs0);
-                                a_q = (int)(rr * (unsigned)d.bs1 + zt);
-                            }
-                            #pragma unroll 1
-                            for (int qd = a_grp; qd * 4 < nslot; qd += a_ngrp) {
-                                float2 a[4];
-                                #pragma unroll
-                                for (int i = 0; i < 4; ++i) {
-                                    const int p = qd * 4 + i;
-                                    a[i] = (a_ok && p < np) ? cmul(tQ[p * cfg.sQ + a_q], tY[p * cfg.sY + a_y]) : make_float2(0.f, 0.f);
-                                }
-                                st_split8_f16(sAhi, sAlo, a_off0 + (((qd ^ (a_row & 7)) & 7) << 4), a);
-                            }
-                        }
-                        // ---- B_hi / B_lo per sub-tile (rows 2c -> Re H, 2c+1 -> Im H)
-                        if (is_worker && !b_valid) {
-                            const int nq4 = nslot >> 2;
-                            #pragma unroll 1
-                            for (int pi = b_grp; pi < nsub_here * nq4; pi += 4) {
-                                const int sub = pi / nq4, qd = pi - sub * nq4;
-                                unsigned char* sBh = sBhi + sub * (2 * kTcN * 128);
-                                unsigned char* sBl = sBh + kTcN * 128;
-                                const int col = (seg0 + sub) * (kTcN / 2) + b_col;
-                                float2 re[4], im[4];
-                                #pragma unroll
-                                for (int i = 0; i < 4; ++i) {
-                                    const int p = qd * 4 + i;
-                                    float2 w = make_float2(0.f, 0.f);
-                                    if (p < np) {
-                                        const int a = col >> 4;
-                                        const float2* sd = seed + p * cfg.sS;
-                                        w = cmul(cmul(sd[8 + (a >> 3)], sd[a & 7]), wB[p * cfg.sB + (col & 15)]);
-                                    }
-                                    re[i] = make_float2(w.x, -w.y);
-                                    im[i] = make_float2(w.y, w.x);
-                                }
-                                st_split8_f16(sBh, sBl, b_off0 + (((qd ^ (b_row0 & 7)) & 7) << 4), re);
-                                st_split8_f16(sBh, sBl, b_off0 + 128 + (((qd ^ ((b_row0 + 1) & 7)) & 7) << 4), im);
-                            }
-                        }
-                        TC_TRACE(16 * stage_no + tb + 2);
-                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                        asm volatile("bar.sync 2, %0;" :: "n"(kTcPStage) : "memory");
-                        TC_TRACE(16 * stage_no + tb + 3);
-                        if (tid == kTcWorkers) {
-                            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                            #pragma unroll 1
-                            for (int sub = 0; sub < nsub_here; ++sub) {
-                                const uint32_t acc_col = (uint32_t)((((tile_idx & 1) * nsub) + sub) * acc_stride);
-                                const uint64_t sub_off = (uint64_t)(sub * (2 * kTcN * 128) >> 4);       // descriptor address field: 16-byte units
-                                #pragma unroll 1
-                                for (int s = 0; s < 3; ++s) {                                           // hi*hi, lo*hi, hi*lo
-                                    const uint64_t da = (s == 2) ? dAlo : dAhi;
-                                    const uint64_t db = ((s == 1) ? dBlo : dBhi) + sub_off;
-                                    #pragma unroll 1
-                                    for (int kk = 0; kk < ksteps; ++kk) {
-                                        const uint32_t accum = (s | kk) != 0;
-                                        asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
-                                                     "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}"
-                                                     :: "r"(tmem_base + acc_col), "l"(db + 2 * kk), "l"(da + 2 * kk), "r"(idesc), "r"(accum) : "memory");
-                                    }
-                                }
-                            }
-                            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
-                                         :: "r"(smem_u32(&mbar)) : "memory");
-                        }
-                        pending = true;
-                        if (!is_worker) TC_TRACE(16 * stage_no + tb + 4);
-                        if (have_prev && is_worker)           // drain the previous stage (possibly the previous user's last) under these MMAs
-                            for (int sub = 0; sub < prev.nsub; ++sub) {
-                                TcTile t = {prev.row0, prev.ct + sub, prev.acc + sub * acc_stride};
-                                tc_epilogue(t, tmem_base, prev.out_u, pitch, M, mtile, warp, lane, prev.scale);
-                            }
-                        if (is_worker) TC_TRACE(16 * stage_no + tb + 4);
-#ifdef DMK_TC_TRACE
-                        if (trace_cta && it >= 3) ++stage_no;
-#endif
-                        b_valid = true;
-                        a_valid = true;
-                        prev.row0 = row0; prev.ct = seg0; prev.acc = (tile_idx & 1) * nsub * acc_stride; prev.nsub = nsub_here;
-                        prev.out_u = out_u; prev.scale = scale;
-                        have_prev = true;
-                        ++tile_idx;
-                    }
-                }
-            }
-        }
-#ifdef DMK_TC_TRACE
-        if (trace_cta && it >= 3 && it < 9 && tid == 0) g_tc_trace[4000 + 8 * (it - 3) + 1] = clock64();
-#endif
-        __syncthreads();       // user i's tables are free for the helper; user i+1's are complete
-    }
-    if (!is_helper) {
-        if (pending) {
-            if (!is_worker) mbar_wait_parity(smem_u32(&mbar), phase);
-            asm volatile("bar.sync 1, %0;" :: "n"(kTcPStage) : "memory");
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        }
-        if (have_prev && is_worker)
-            for (int sub = 0; sub < prev.nsub; ++sub) {
-                TcTile t = {prev.row0, prev.ct + sub, prev.acc + sub * acc_stride};
-                tc_epilogue(t, tmem_base, prev.out_u, pitch, M, mtile, warp, lane, prev.scale);
-            }
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    if (warp == 3) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"(2 * 128));
-}
 
 }  // namespace dmk

@@ -25,6 +25,20 @@ __global__ void __launch_bounds__(256) k(float* out, long long pitch, int reps, 
                     float* p = base + (long long)(h * 32) * pitch + sub * 128 + q * 32 + lane;
                     for (int i = 0; i < 32; ++i) { asm volatile("st.global.cs.f32 [%0], %1;" :: "l"(p), "f"(1.f) : "memory"); p += pitch; }
                 }
+            } else if (MODE == 4) {        // 4 warps (q) x 2 row halves (h): per row 256 B contiguous per warp (two adjacent 128 B stores)
+                float* p = base + (long long)(h * 32) * pitch + q * 64 + lane;
+                for (int i = 0; i < 32; ++i) {
+                    asm volatile("st.global.cs.f32 [%0], %1;" :: "l"(p), "f"(1.f) : "memory");
+                    asm volatile("st.global.cs.f32 [%0], %1;" :: "l"(p + 32), "f"(1.f) : "memory");
+                    p += pitch;
+                }
+            } else if (MODE == 5) {        // like mode 1 but the two sub-tiles interleaved per row (128 B pieces 512 B apart)
+                float* p = base + (long long)(h * 32) * pitch + q * 32 + lane;
+                for (int i = 0; i < 32; ++i) {
+                    asm volatile("st.global.cs.f32 [%0], %1;" :: "l"(p), "f"(1.f) : "memory");
+                    asm volatile("st.global.cs.f32 [%0], %1;" :: "l"(p + 128), "f"(1.f) : "memory");
+                    p += pitch;
+                }
             } else if (MODE == 2) {
                 float* p = base + (long long)(warp * 8) * pitch + lane;
                 for (int i = 0; i < 8; ++i) {
@@ -49,18 +63,19 @@ int main()
     const long long total_tiles = 296LL * 512;     // 9.7 GB
     float* out; if (cudaMalloc(&out, (size_t)(total_tiles / 16 + 2) * 128 * pitch * 4) != cudaSuccess) { printf("alloc failed\n"); return 1; }
     cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
-    const char* names[4] = {"b32 128x512B tile", "b32 64x1KB stage (q,h)", "b32 64x1KB row-walk", "v4  64x1KB rows"};
-    for (int cps = 1; cps <= 6; ++cps) {
-        if (cps == 5) continue;
+    const char* names[6] = {"b32 128x512B tile", "b32 64x1KB stage (q,h)", "b32 64x1KB row-walk", "v4  64x1KB rows", "b32 64x1KB 256B/warp/row", "b32 64x1KB sub-interleaved"};
+    for (int cps = 2; cps <= 2; ++cps) {
         const int grid = 148 * cps, reps = (int)(total_tiles / grid);
-        for (int mode = 0; mode < 4; ++mode) {
+        for (int mode = 0; mode < 6; ++mode) {
             float ms = 0;
             for (int it = 0; it < 2; ++it) {
                 cudaEventRecord(a);
                 if (mode == 0) k<0><<<grid, 256>>>(out, pitch, reps, tiles_per_row);
                 else if (mode == 1) k<1><<<grid, 256>>>(out, pitch, reps, tiles_per_row);
                 else if (mode == 2) k<2><<<grid, 256>>>(out, pitch, reps, tiles_per_row);
-                else k<3><<<grid, 256>>>(out, pitch, reps, tiles_per_row);
+                else if (mode == 3) k<3><<<grid, 256>>>(out, pitch, reps, tiles_per_row);
+                else if (mode == 4) k<4><<<grid, 256>>>(out, pitch, reps, tiles_per_row);
+                else k<5><<<grid, 256>>>(out, pitch, reps, tiles_per_row);
                 cudaEventRecord(b); cudaEventSynchronize(b);
                 cudaEventElapsedTime(&ms, a, b);
             }

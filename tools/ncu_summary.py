@@ -1,48 +1,21 @@
 #!/usr/bin/env python
-"""Summarise an .ncu-rep (raw page) into the handful of metrics the roofline discussion needs.
-
-    python tools/ncu_summary.py gpurun_out/fd.ncu-rep [--all]
-"""
-import csv
-import io
-import subprocess
-import sys
-
-KEYS = [
-    "gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
-    "launch__shared_mem_per_block_dynamic", "launch__shared_mem_per_block_static", "launch__occupancy_limit_registers",
-    "launch__occupancy_limit_shared_mem", "launch__occupancy_limit_warps", "sm__warps_active.avg.pct_of_peak_sustained_active",
-    "dram__bytes_read.sum", "dram__bytes_write.sum", "dram__throughput.avg.pct_of_peak_sustained_elapsed",
-    "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_bytes.sum",
-    "sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm__inst_executed.sum", "smsp__inst_executed.sum",
-    "sm__inst_executed_pipe_fma.sum", "sm__inst_executed_pipe_fmaheavy.sum", "sm__inst_executed_pipe_fmalite.sum",
-    "sm__inst_executed_pipe_alu.sum", "sm__inst_executed_pipe_fp64.sum", "sm__inst_executed_pipe_xu.sum",
-    "sm__inst_executed_pipe_lsu.sum", "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active",
-    "sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_active", "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active",
-    "sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active", "sm__pipe_xu_cycles_active.avg.pct_of_peak_sustained_active",
-    "smsp__issue_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.avg.per_cycle_active",
-    "sm__sass_thread_inst_executed_op_ffma_pred_on.sum", "sm__sass_thread_inst_executed_op_fadd_pred_on.sum",
-    "sm__sass_thread_inst_executed_op_fmul_pred_on.sum", "sm__sass_thread_inst_executed_op_dfma_pred_on.sum",
-    "smsp__sass_thread_inst_executed_op_ffma_pred_on.sum",
-    "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
-    "smsp__cycles_active.avg", "sm__cycles_elapsed.avg", "sm__cycles_elapsed.avg.per_second",
-    "smsp__average_warp_latency_issue_stalled", "smsp__warp_issue_stalled",
-]
-
-
-def main():
-    rep = sys.argv[1]
-    show_all = "--all" in sys.argv
-    txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
-    rows = list(csv.reader(io.StringIO(txt)))
-    hdr, units = rows[0], rows[1]
-    for r in rows[2:]:
-        print("---", r[hdr.index("Kernel Name")][:80], "grid", r[hdr.index("Grid Size")] if "Grid Size" in hdr else "")
-        for i, h in enumerate(hdr):
-            if show_all or any(h.startswith(k) for k in KEYS):
-                if r[i] not in ("", "n/a"):
-                    print(f"  {h} [{units[i]}] = {r[i]}")
-
-
-if __name__ == "__main__":
-    main()
+"""Text summary of one ncu report for profiles/: key raw metrics + SASS-region sample shares.
+    python tools/ncu_summary.py gpurun_out/prof.ncu-rep > profiles/rNN_ncu_<kernel>_<workload>.txt"""
+import csv, io, subprocess, sys
+rep = sys.argv[1]
+raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+rows = list(csv.reader(io.StringIO(raw)))
+hdr, units, vals = rows[0], rows[1], rows[2]
+KEEP = ("dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct", "gpu__time_duration.sum",
+        "launch__block_size", "launch__grid_size", "launch__occupancy_limit", "launch__registers_per_thread",
+        "launch__shared_mem_per_block", "sm__cycles_elapsed.avg", "sm__inst_executed.sum.per_cycle", "sm__inst_executed_pipe_alu.sum.pct",
+        "sm__inst_executed_pipe_fma.sum.pct", "sm__inst_executed_pipe_fp64.sum.pct", "sm__inst_executed_pipe_lsu.sum.pct",
+        "sm__inst_executed_pipe_xu.sum.pct", "sm__pipe_tensor_cycles_active.avg.pct", "sm__pipe_fma_cycles_active.avg.pct",
+        "sm__throughput.avg.pct", "sm__warps_active.avg.pct", "smsp__inst_executed.sum", "smsp__issue_active.avg.pct",
+        "smsp__average_warps_issue_stalled", "lts__throughput.avg.pct", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
+        "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum")
+name = vals[hdr.index("Kernel Name")] if "Kernel Name" in hdr else "?"
+print(f"--- {name} grid {vals[hdr.index('Grid Size')] if 'Grid Size' in hdr else ''}  (ncu --set full --clock-control none; {rep})")
+for h, u, v in sorted(zip(hdr, units, vals)):
+    if any(h.startswith(k) for k in KEEP) and v not in ("", "0"):
+        print(f"  {h} [{u}] = {v}")
