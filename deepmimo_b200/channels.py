@@ -105,8 +105,9 @@ def resolve_ue_rotation(rot, n_ue: int, seed_numpy_rng: bool = True):
 
 def parse_spec(params, n_ue: int, *, bs_fov=None, ue_fov=None, times=None, seed_numpy_rng: bool = True) -> ChannelSpec:
     """Translate (validated) channel parameters into a ChannelSpec.  Raises like the reference does:
-    NotImplementedError for an unknown pattern (ant_patterns.py:119-122), and for the features this
-    path does not cover (rx_filter=1, enable_dual_polar=1)."""
+    NotImplementedError for an unknown pattern (ant_patterns.py:119-122).  `enable_dual_polar` is accepted and has no
+    effect, exactly as in the reference (the key exists in the defaults, channel.py:51, and nothing reads it);
+    `ofdm.rx_filter=1` selects the receive low-pass filter (channel.py:193-194) in the frequency-domain branch."""
     bs, ue, ofdm = params["bs_antenna"], params["ue_antenna"], params["ofdm"]
     pats = []
     for side, name in ((bs, "TX"), (ue, "RX")):
@@ -114,10 +115,6 @@ def parse_spec(params, n_ue: int, *, bs_fov=None, ue_fov=None, times=None, seed_
         if pat not in RADIATION_PATTERNS:
             raise NotImplementedError(f"The given '{pat}' antenna radiation pattern is not applicable for {name}.")
         pats.append(RADIATION_PATTERNS.index(pat))
-    if params.get("enable_dual_polar", 0):
-        raise NotImplementedError("enable_dual_polar=1 is not implemented (the reference ignores the flag)")
-    if ofdm.get("rx_filter", 0):
-        raise NotImplementedError("ofdm.rx_filter=1 (receive low-pass filter, channel.py:193-194) is not implemented")
 
     bs_shape = tuple(int(v) for v in np.asarray(bs["shape"]).ravel()[:2])
     ue_shape = tuple(int(v) for v in np.asarray(ue["shape"]).ravel()[:2])

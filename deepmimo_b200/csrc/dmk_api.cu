@@ -38,7 +38,7 @@ int build_desc(const dmk_desc* h, bool freq_domain, dmk::DevDesc& d)
 {
     using namespace dmk;
     if (!h) return fail(DMK_ERR_INVALID_ARG, "desc is NULL");
-    if (h->rx_filter) return fail(DMK_ERR_UNSUPPORTED, "ofdm.rx_filter=1 (LPF, channel.py:193-194) is not implemented");
+    if (h->rx_filter != 0 && h->rx_filter != 1) return fail(DMK_ERR_INVALID_ARG, "ofdm.rx_filter must be 0 or 1 (got %d)", h->rx_filter);
     for (int s = 0; s < 2; ++s) {
         const int32_t* shp = s == 0 ? h->bs_shape : h->ue_shape;
         if (shp[0] < 1 || shp[1] < 1) return fail(DMK_ERR_INVALID_ARG, "antenna shape must be >= 1 (got %d x %d)", shp[0], shp[1]);
@@ -83,6 +83,17 @@ int build_desc(const dmk_desc* h, bool freq_domain, dmk::DevDesc& d)
         d.h_hi[s] = 2 * M_PI - fh / 2;
         d.v_hi[s] = M_PI / 2 + fv / 2;                      // :190
         d.v_lo[s] = M_PI / 2 - fv / 2;
+    }
+    // receive low-pass filter (channel.py:193-194): only the OFDM branch reads it (the TD branch never builds path_gen gains)
+    d.rx_filter = (freq_domain && h->rx_filter) ? 1 : 0;
+    d.lpf_log2n = -1;
+    for (int b = 0; b < 31; ++b) if ((1 << b) == d.N) d.lpf_log2n = b;
+    d.lpf_batch = 1;
+    if (d.rx_filter) {
+        long long bmax = (64LL * 1024) / (8LL * d.N);        // x[B][N] float2 within 64 KB
+        if (bmax < 1) bmax = 1;
+        if (bmax > 16) bmax = 16;
+        d.lpf_batch = (int)bmax;
     }
     d.ts_f32 = (float)(1.0 / h->bandwidth);                 // channel.py:223 then float32 (NEP 50 weak scalar)
     d.n_f32 = (float)d.N;
@@ -162,7 +173,7 @@ int dmk_channels_fd(const dmk_desc* desc, const float* power_dbw, const float* p
     cudaStream_t st = reinterpret_cast<cudaStream_t>(cuda_stream);
     const int ncols = d.K * d.T;
     // Production path: affine subcarrier selection, no time axis, tables fit in shared memory.
-    const bool affine = (d.subc_step != 0) || (d.K == 1);
+    const bool affine = ((d.subc_step != 0) || (d.K == 1)) && !d.rx_filter;      // the LPF runs in the generic tile kernel
     FastCfg cfg;
     size_t fast_smem = 0;
     {
@@ -365,18 +376,23 @@ int dmk_channels_fd(const dmk_desc* desc, const float* power_dbw, const float* p
         snprintf(g_kernel, sizeof(g_kernel), "fd_fast_kernel<64x256,ffma2> grid=%lld ksplit=%lld smem=%zu", grid, ksplit, fast_smem);
         return DMK_OK;
     }
-    const size_t smem = (size_t)kMaxPaths * (kTK + kTM) * sizeof(float2);
-    static bool attr_set = false;
-    if (!attr_set) {
+    size_t smem = (size_t)kMaxPaths * (kTK + kTM) * sizeof(float2);
+    if (d.rx_filter) {
+        smem += (size_t)(1 + d.lpf_batch) * d.N * sizeof(float2);      // twiddle table + FFT batch (dmk_fd.cuh: lpf_w_tile)
+        if (smem > 200 * 1024)
+            return fail(DMK_ERR_UNSUPPORTED, "ofdm.rx_filter=1 supports ofdm.subcarriers <= 9728 (got %d)", d.N);
+    }
+    static size_t attr_set = 0;
+    if (smem > attr_set) {
         cudaError_t e = cudaFuncSetAttribute(fd_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(fd_tile_kernel)");
-        attr_set = true;
+        attr_set = smem;
     }
     fd_tile_kernel<<<(unsigned)grid, kFdThreads, smem, st>>>(d, (int)ksplit);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "fd_tile_kernel launch");
     g_launches.fetch_add(1);
-    snprintf(g_kernel, sizeof(g_kernel), "fd_tile_kernel<64x128> grid=%lld ksplit=%lld", grid, ksplit);
+    snprintf(g_kernel, sizeof(g_kernel), "fd_tile_kernel<64x128%s> grid=%lld ksplit=%lld", d.rx_filter ? (d.lpf_log2n >= 0 ? ",lpf-fft" : ",lpf-dft") : "", grid, ksplit);
     return DMK_OK;
 }
 

@@ -18,6 +18,8 @@ struct DevDesc {
     int P, P0;                    // P = min(num_paths, n_cols), P0 = n_cols
     int N, K, T;                  // OFDM size, selected subcarriers, time snapshots (T >= 1)
     int has_time_axis;            // 1 when n_times > 0
+    int rx_filter;                // 1: receive low-pass filter (channel.py:166-168, :193-194), FD only
+    int lpf_batch, lpf_log2n;     // paths per FFT batch; log2(N) when N is a power of two (FFT route), else -1 (direct DFT)
     int fov_any, fov_side[2];     // [0] = BS (AoD), [1] = UE (AoA)
     int pat[2];
     int subc_start, subc_step;    // affine selection if subc_step != 0 or K == 1

@@ -84,6 +84,110 @@ __device__ __noinline__ void fd_cta_prologue_outlined(const DevDesc& d, long lon
     fd_cta_prologue(d, user, sh, sc, write_masks);
 }
 
+// -------------------------------------------------------------------------------------------------
+// Receive low-pass filter (ofdm.rx_filter = 1; channel.py:166-168, :193-194).  The per-path frequency response is no
+// longer a pure phasor but the N-point DFT of the sampled sinc,
+//     W[p, k] = sum_{d=0}^{N-1} sinc(d - tau_p) exp(-j 2 pi d k / N),        tau_p = delay_n[p]
+// (the reference forms the [P, N] sinc matrix and multiplies it with the [N, K] DFT matrix in complex128).
+// sinc(d - tau) = sin(pi tau) (-1)^d / (pi (tau - d)): sin(pi tau) is evaluated once per path in float64 from the
+// fractional part of tau, so every sample costs one float64 subtraction, one conversion and one float32 division.
+// Per column tile and batch of `lpf_batch` paths the CTA fills x[b][d] in shared memory and transforms it:
+//   N a power of two -> in-place radix-2 FFT (bit-reversed fill, log2 N barrier-separated stages, exact twiddle table);
+//   otherwise        -> direct DFT of the selected columns only (twiddle index walks d*k mod N).
+// The [np][128] tile of W then feeds the same rank-np accumulation as the unfiltered path.
+// -------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void lpf_w_tile(const DevDesc& d, const FdShared& sh, int np, int col0, int ncols, float2* sW,
+                                           float2* lpf_mem, bool first_tile)
+{
+    __shared__ float  lpf_a[kMaxPaths];      // (-1)^k sin(pi r) / pi,  tau = k + r
+    __shared__ float  lpf_sk[kMaxPaths];     // sinc(r): the sample d == k
+    __shared__ int    lpf_k[kMaxPaths];
+    __shared__ double lpf_tau[kMaxPaths];
+    const int tid = threadIdx.x;
+    const int N = d.N, B = d.lpf_batch, lg = d.lpf_log2n;
+    float2* tw = lpf_mem;                    // [N]   exp(-j 2 pi i / N)
+    float2* x  = lpf_mem + N;                // [B][N]
+    if (first_tile) {
+        for (int i = tid; i < N; i += kFdThreads) tw[i] = phasor_cycles(-((double)i * d.inv_n));
+        if (tid < np) {
+            const double tau = sh.wcyc[tid] * (double)N;           // delay_n (wcyc = delay_n / N)
+            const double k = rint(tau), r = tau - k;
+            const double sp = sinpi(r);
+            const long long ki = (long long)k;
+            lpf_tau[tid] = tau;
+            lpf_k[tid] = (k >= 0.0 && k < (double)N) ? (int)ki : -1;
+            lpf_a[tid] = (float)(((ki & 1) ? -sp : sp) / kPi);
+            lpf_sk[tid] = (r == 0.0) ? 1.0f : (float)(sp / (kPi * r));      // np.sinc: sin(pi x)/(pi x), 1 at x == 0
+        }
+    }
+    __syncthreads();
+    for (int p0 = 0; p0 < np; p0 += B) {
+        const int nb = min(B, np - p0);
+        if (p0 > 0) __syncthreads();                               // the previous batch's gather is done with x
+        // ---- samples of the shifted sinc (bit-reversed order for the FFT route)
+        for (int e = tid; e < nb * N; e += kFdThreads) {
+            const int b = lg >= 0 ? (e >> lg) : e / N;
+            const int dd = e - b * N;
+            const int p = p0 + b;
+            float s;
+            if (dd == lpf_k[p]) s = lpf_sk[p];
+            else {
+                const float den = (float)(lpf_tau[p] - (double)dd);
+                s = __fdiv_rn((dd & 1) ? -lpf_a[p] : lpf_a[p], den);
+            }
+            const int pos = lg > 0 ? (int)(__brev((unsigned)dd) >> (32 - lg)) : dd;
+            x[b * N + pos] = make_float2(s, 0.f);
+        }
+        __syncthreads();
+        if (lg >= 0) {
+            // ---- in-place radix-2 decimation-in-time FFT of nb sequences
+            const int half_n = N >> 1;
+            for (int lh = 0; lh < lg; ++lh) {
+                const int half = 1 << lh;
+                for (int t = tid; t < nb * half_n; t += kFdThreads) {
+                    const int b = t >> (lg - 1), j = t & (half_n - 1);
+                    const int pos = j & (half - 1);
+                    const int i0 = ((j >> lh) << (lh + 1)) + pos;
+                    float2* xb = x + b * N;
+                    const float2 w = tw[pos << (lg - 1 - lh)];
+                    const float2 a = xb[i0], c = cmul(xb[i0 + half], w);
+                    xb[i0] = make_float2(a.x + c.x, a.y + c.y);
+                    xb[i0 + half] = make_float2(a.x - c.x, a.y - c.y);
+                }
+                __syncthreads();
+            }
+        }
+        // ---- the tile's columns
+        for (int e = tid; e < nb * kTK; e += kFdThreads) {
+            const int b = e / kTK, cidx = e % kTK;
+            const int col = col0 + cidx;
+            const int p = p0 + b;
+            float2 w = make_float2(0.f, 0.f);
+            if (col < ncols) {
+                const int ki = col / d.T, it = col - ki * d.T;
+                int k = subcarrier_at(d, ki) % N;
+                if (k < 0) k += N;
+                if (lg >= 0) {
+                    w = x[b * N + k];
+                } else {
+                    const float2* xb = x + b * N;
+                    float wr = 0.f, wi = 0.f;
+                    int idx = 0;
+                    for (int dd = 0; dd < N; ++dd) {
+                        const float s = xb[dd].x;
+                        const float2 t = tw[idx];
+                        wr = fmaf(s, t.x, wr); wi = fmaf(s, t.y, wi);
+                        idx += k; if (idx >= N) idx -= N;
+                    }
+                    w = make_float2(wr, wi);
+                }
+                if (d.has_time_axis) w = cmul(w, phasor_cycles(sh.fd[p] * d.times[it]));
+            }
+            sW[p * kTK + cidx] = w;
+        }
+    }
+}
+
 __global__ void __launch_bounds__(kFdThreads, 2)
 fd_tile_kernel(const __grid_constant__ DevDesc d, const int ksplit)
 {
@@ -109,6 +213,9 @@ fd_tile_kernel(const __grid_constant__ DevDesc d, const int ksplit)
     for (int ct = ks; ct < n_ct; ct += ksplit) {
         const int col0 = ct * kTK;
         __syncthreads();                                   // previous tile's readers are done with sW
+        if (d.rx_filter) {
+            lpf_w_tile(d, sh, np, col0, ncols, sW, reinterpret_cast<float2*>(smem_raw + (size_t)kMaxPaths * (kTK + kTM) * sizeof(float2)), ct == ks);
+        } else
         // ---- W tile: per-(path, column) phasor, phase reduced in float64
         for (int e = tid; e < np * kTK; e += kFdThreads) {
             const int p = e / kTK, cidx = e % kTK;

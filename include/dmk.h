@@ -39,7 +39,7 @@ extern "C" {
 typedef enum dmk_status {
     DMK_OK                =  0,
     DMK_ERR_INVALID_ARG   = -1,
-    DMK_ERR_UNSUPPORTED   = -2,   /* rx_filter=1, enable_dual_polar=1, unknown pattern (ant_patterns.py:119-122) */
+    DMK_ERR_UNSUPPORTED   = -2,   /* unknown pattern (ant_patterns.py:119-122); rx_filter=1 with more than 9728 subcarriers */
     DMK_ERR_CUDA          = -3
 } dmk_status;
 
@@ -71,7 +71,7 @@ typedef struct dmk_desc {
     int32_t subc_start;         /* if subc_step != 0 the selection is start + step*i and            */
     int32_t subc_step;          /*   `subcarriers` may be NULL                                      */
     double  bandwidth;          /* Hz (Ts = 1/bandwidth, channel.py:223)                            */
-    int32_t rx_filter;          /* must be 0 (channel.py:193-194 not implemented yet)               */
+    int32_t rx_filter;          /* 0 | 1: receive low-pass filter of the OFDM branch (channel.py:166-168, :193-194); ignored by dmk_channels_td */
     int32_t n_times;            /* 0 = no trailing time axis; T >= 1 appends [.., T] (row a11)      */
     const double *times;        /* DEVICE pointer, [T] snapshot times in seconds                    */
     int32_t flags;              /* DMK_FLAG_* (ABI 2); 0 = plain stream-ordered launch                   */
@@ -87,6 +87,7 @@ typedef struct dmk_desc {
 
 /* Frequency-domain channels (freq_domain = 1):
  *   out[u, r, t, k (, it)] = sum_p c_p a_rx[r,p] a_tx[t,p] exp(-j 2 pi k delay_n[p] / N) (* exp(+j 2 pi f_D[p] t_it))
+ * (rx_filter = 1: the delay phasor is replaced by sum_d sinc(d - delay_n[p]) exp(-j 2 pi d k / N), d = 0..N-1)
  * complex64, C-contiguous [n, M_r, M_t, K (, T)], every element written (users without paths -> zeros).
  *   ue_rot_deg : NULL or DEVICE double [n,3] per-user UE rotation (dataset.py:328-338)
  *   doppler_hz : NULL or DEVICE float  [n, n_cols] (ld) per-path Doppler shift in Hz (row a11 extension)

@@ -129,9 +129,12 @@ def pattern_gain(name: str, theta: np.ndarray):
 # --------------------------------------------------------------------------
 # per-path OFDM gains
 # --------------------------------------------------------------------------
-def ofdm_path_gains(power, toa, phase, n_sc: int, sel_sc: np.ndarray, ts: float):
-    """[P_i, K] complex path gains without LPF.  deepmimo/generator/channel.py:170-198.
+def ofdm_path_gains(power, toa, phase, n_sc: int, sel_sc: np.ndarray, ts: float, rx_filter: int = 0):
+    """[P_i, K] complex path gains.  deepmimo/generator/channel.py:155-198.
 
+    rx_filter = 0: c_p exp(-j 2 pi k delay_n / N) (:196-197).
+    rx_filter = 1: receive low-pass filter (:166-168, :193-194): (c_p sinc(d - delay_n)) @ exp(-j 2 pi d k / N), d = 0..N-1;
+    `*` and `@` have equal precedence, so the product with sinc is formed first.
     Returns (gains, over) where `over` marks paths with delay_n >= N (:187).
     """
     power = power.reshape(-1, 1)
@@ -141,7 +144,12 @@ def ofdm_path_gains(power, toa, phase, n_sc: int, sel_sc: np.ndarray, ts: float)
     power[over] = 0                                         # :188
     delay_n[over] = n_sc                                    # :189
     c = np.sqrt(power / n_sc) * np.exp(1j * np.deg2rad(phase))          # :192
-    g = c * np.exp(-1j * (2 * np.pi / n_sc) * np.outer(delay_n.ravel(), sel_sc))  # :196-197
+    if rx_filter:
+        delay_d = np.arange(n_sc)                                                               # :165
+        delay_to_ofdm = np.exp(-1j * 2 * np.pi / n_sc * np.outer(delay_d, sel_sc))              # :166-167
+        g = c * np.sinc(delay_d - delay_n) @ delay_to_ofdm                                      # :194
+    else:
+        g = c * np.exp(-1j * (2 * np.pi / n_sc) * np.outer(delay_n.ravel(), sel_sc))  # :196-197
     return g, over.ravel()
 
 
@@ -168,7 +176,7 @@ def compute_channels(data: dict, *, bs_shape=(8, 1), ue_shape=(1, 1), bs_spacing
                      bs_rotation=(0, 0, 0), ue_rotation=(0, 0, 0),
                      bs_pattern="isotropic", ue_pattern="isotropic",
                      bs_fov=None, ue_fov=None, num_paths=25, freq_domain=True,
-                     subcarriers=512, selected_subcarriers=(0,), bandwidth=10e6,
+                     subcarriers=512, selected_subcarriers=(0,), bandwidth=10e6, rx_filter=0,
                      doppler_hz=None, times=None, user_range=None) -> dict:
     """Restatement of Dataset.compute_channels (deepmimo/generator/dataset.py:224-268).
 
@@ -246,7 +254,7 @@ def compute_channels(data: dict, *, bs_shape=(8, 1), ue_shape=(1, 1), bs_spacing
         else:
             dphase = np.exp(1j * 2 * np.pi * np.outer(dop[i, m].astype(np.float64), tt))   # [P_i, T] (a11 definition)
         if freq_domain:
-            g, over = ofdm_path_gains(pw[i, m], delay[i, m], phase[i, m], int(subcarriers), sel_sc, ts)
+            g, over = ofdm_path_gains(pw[i, m], delay[i, m], phase[i, m], int(subcarriers), sel_sc, ts, int(rx_filter))
             clip[i, m] = over
             if dphase is None:
                 H[i] = np.nansum(arp[..., None, :] * g.T[None, None, :, :], axis=-1)        # channel.py:283-284

@@ -38,12 +38,12 @@ def case_list():
 
     def add(name, n, seed, n_sc, bw, sel, bs_shape=(8, 1), ue_shape=(1, 1), bs_rot=(0, 0, 0), ue_rot=(0, 0, 0),
             bs_pat="isotropic", ue_pat="isotropic", bs_fov=None, ue_fov=None, num_paths=25, fd=1,
-            bs_sp=0.5, ue_sp=0.5, holes=False, n_cols=25, zero_frac=0.10):
+            bs_sp=0.5, ue_sp=0.5, holes=False, n_cols=25, zero_frac=0.10, lpf=0):
         cases.append(dict(name=name, n=n, seed=seed, n_sc=n_sc, bw=bw, sel=np.asarray(sel), bs_shape=A(bs_shape),
                           ue_shape=A(ue_shape), bs_rot=np.asarray(bs_rot), ue_rot=np.asarray(ue_rot), bs_pat=bs_pat,
                           ue_pat=ue_pat, bs_fov=None if bs_fov is None else A(bs_fov),
                           ue_fov=None if ue_fov is None else A(ue_fov), num_paths=num_paths, fd=fd,
-                          bs_sp=bs_sp, ue_sp=ue_sp, holes=holes, n_cols=n_cols, zero_frac=zero_frac))
+                          bs_sp=bs_sp, ue_sp=ue_sp, holes=holes, n_cols=n_cols, zero_frac=zero_frac, lpf=lpf))
 
     per_user = lambda n, s, lo=0, hi=45: np.random.default_rng(s).uniform(lo, hi, (n, 3))
 
@@ -71,6 +71,12 @@ def case_list():
         bs_fov=(360, 180), ue_fov=(360, 180))
     add("np10_fd_perusr_bsrot", 32, 25, 512, 10e6, np.arange(0, 512, 100), bs_shape=(16, 1), num_paths=10,
         bs_rot=(0, 0, 90), ue_rot=per_user(32, 44, -90, 90), ue_shape=(2, 2), bs_fov=(120, 90), ue_fov=(180, 90))
+    # receive low-pass filter (ofdm.rx_filter = 1, channel.py:193-194): power-of-two N (FFT route on the device), a
+    # non-power-of-two N with a strided selection (direct DFT route), and dipole + FoV (float64 power branch)
+    add("lpf_pow2", 24, 26, 256, 20e6, np.arange(256), bs_shape=(4, 2), ue_shape=(2, 1), bs_rot=(10, 20, 30), lpf=1)
+    add("lpf_n600_sel", 24, 27, 600, 30e6, A([0, 1, 7, 64, 299, 598, 599]), bs_shape=(6, 1), ue_shape=(1, 2), lpf=1, num_paths=10)
+    add("lpf_dipole_fov", 32, 28, 128, 10e6, np.arange(0, 128, 3), bs_shape=(8, 1), bs_pat="halfwave-dipole",
+        ue_pat="halfwave-dipole", bs_fov=(140, 120), ue_fov=(180, 120), holes=True, lpf=1)
     return cases
 
 
@@ -86,7 +92,7 @@ def oracle_kwargs(c: dict) -> dict:
     return dict(bs_shape=c["bs_shape"], ue_shape=c["ue_shape"], bs_spacing=c["bs_sp"], ue_spacing=c["ue_sp"],
                 bs_rotation=c["bs_rot"], ue_rotation=c["ue_rot"], bs_pattern=c["bs_pat"], ue_pattern=c["ue_pat"],
                 bs_fov=c["bs_fov"], ue_fov=c["ue_fov"], num_paths=c["num_paths"], freq_domain=bool(c["fd"]),
-                subcarriers=c["n_sc"], selected_subcarriers=c["sel"], bandwidth=c["bw"])
+                subcarriers=c["n_sc"], selected_subcarriers=c["sel"], bandwidth=c["bw"], rx_filter=c.get("lpf", 0))
 
 
 def params_dict(c: dict) -> dict:
@@ -97,5 +103,5 @@ def params_dict(c: dict) -> dict:
         "ue_antenna": {"shape": c["ue_shape"], "spacing": c["ue_sp"], "rotation": c["ue_rot"],
                        "radiation_pattern": c["ue_pat"]},
         "enable_doppler": 0, "enable_dual_polar": 0, "num_paths": c["num_paths"], "freq_domain": c["fd"],
-        "ofdm": {"subcarriers": c["n_sc"], "selected_subcarriers": c["sel"], "bandwidth": c["bw"], "rx_filter": 0},
+        "ofdm": {"subcarriers": c["n_sc"], "selected_subcarriers": c["sel"], "bandwidth": c["bw"], "rx_filter": c.get("lpf", 0)},
     }

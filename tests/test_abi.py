@@ -51,11 +51,15 @@ def test_error_codes_without_gpu():
     d = _lib.DmkDesc()
     d.bs_shape[:] = [8, 1]; d.ue_shape[:] = [1, 1]; d.n_cols = 25; d.num_paths = 25
     d.n_subcarriers = 64; d.n_selected = 4; d.subc_step = 1; d.bandwidth = 10e6
-    d.rx_filter = 1
+    d.pattern[0] = 7
     rc = lib.dmk_channels_fd(ctypes.byref(d), *([None] * 9), 0, 25, None, None, None, None, None)
-    assert rc == -2 and b"rx_filter" in lib.dmk_last_error()
+    assert rc == -2 and b"pattern" in lib.dmk_last_error()
     with pytest.raises(NotImplementedError):
         _lib.check(rc)
+    d.pattern[0] = 0
+    d.rx_filter = 2
+    rc = lib.dmk_channels_fd(ctypes.byref(d), *([None] * 9), 0, 25, None, None, None, None, None)
+    assert rc == -1 and b"rx_filter" in lib.dmk_last_error()
     d.rx_filter = 0
     d.n_cols = 99
     rc = lib.dmk_channels_fd(ctypes.byref(d), *([None] * 9), 0, 25, None, None, None, None, None)

@@ -159,10 +159,6 @@ def test_error_paths_match_reference_behaviour():
     s = scenario(1, 16)
     ds = make_dataset(dmb, s)
     p = dmb.ChannelGenParameters(s.params)
-    p.ofdm.rx_filter = 1
-    with pytest.raises(NotImplementedError):
-        ds.compute_channels(p)
-    p = dmb.ChannelGenParameters(s.params)
     p.bs_antenna.radiation_pattern = "patch"
     with pytest.raises((AssertionError, NotImplementedError)):
         ds.compute_channels(p)
@@ -267,3 +263,41 @@ def test_per_user_byproducts_match_reference_definitions():
     assert np.array_equal(ds2.num_paths, (~np.isnan(s.data["power"])).sum(1))
     first = inter[:, 0]
     assert np.array_equal(ds2.los == 1, first == 0)
+
+
+@pytest.mark.parametrize("n_sc,sel,bs,ue", [(1024, np.arange(1024), (8, 4), (2, 1)),          # FFT route, 8 paths per batch, 8 column tiles
+                                              (4096, np.arange(0, 4096, 16), (4, 4), (1, 1)),   # FFT route, 2 paths per batch
+                                              (300, np.arange(0, 300, 2), (4, 2), (1, 2)),      # direct-DFT route
+                                              (64, np.arange(64), (8, 1), (1, 1))])             # small array + LPF -> tile kernel, 16 paths per batch
+def test_rx_filter_lowpass_matches_oracle(n_sc, sel, bs, ue):
+    """ofdm.rx_filter = 1 (channel.py:166-168, :193-194): W[p,k] = sum_d sinc(d - delay_n) exp(-j 2 pi d k / N).
+    Oracle = NumPy restatement, bit-identical to the live reference on the lpf_* golden cases."""
+    import deepmimo_b200 as dmb
+    from deepmimo_b200.synth import make_paths
+    from oracle import channel_oracle as orc
+    d = make_paths(40, 77 + n_sc, n_sc=n_sc, bandwidth=50e6, n_cols=25, zero_frac=0.1, clip_frac=0.02)
+    p = {"bs_antenna": {"shape": np.array(bs), "spacing": 0.5, "rotation": np.array([5, 10, 20]), "radiation_pattern": "isotropic"},
+         "ue_antenna": {"shape": np.array(ue), "spacing": 0.5, "rotation": np.array([0, 0, 0]), "radiation_pattern": "isotropic"},
+         "enable_doppler": 0, "enable_dual_polar": 0, "num_paths": 25, "freq_domain": 1,
+         "ofdm": {"subcarriers": n_sc, "selected_subcarriers": sel, "bandwidth": 50e6, "rx_filter": 1}}
+    H, info = make_dataset(dmb, d).compute_channels(dmb.ChannelGenParameters(p), return_info=True, warn=False)
+    o = orc.compute_channels(d, **oracle_kwargs_from_params(p))
+    err = assert_channels_close(H, o["H"], what=f"lpf N={n_sc}")
+    assert np.array_equal(info.valid, o["valid"]) and np.array_equal(info.clip, o["clip"])
+    assert "lpf" in info.kernel
+    print(f"lpf N={n_sc} K={len(sel)}: {info.kernel.split(' ')[0]} max rel. Frobenius {err:.2e}")
+    # the filter must actually change the result (it is not the unfiltered channel)
+    p["ofdm"]["rx_filter"] = 0
+    H0 = make_dataset(dmb, d).compute_channels(dmb.ChannelGenParameters(p), warn=False)
+    assert np.abs(H - H0).max() > 1e-3 * np.abs(H0).max()
+
+
+def test_rx_filter_is_ignored_in_time_domain_like_the_reference():
+    import deepmimo_b200 as dmb
+    from deepmimo_b200.synth import scenario
+    s = scenario(4, 32)
+    p = dmb.ChannelGenParameters(s.params)
+    H0 = make_dataset(dmb, s).compute_channels(p, warn=False)
+    p.ofdm.rx_filter = 1                              # channel.py:285-287: the TD branch never calls path_gen.generate
+    H1 = make_dataset(dmb, s).compute_channels(p, warn=False)
+    assert np.array_equal(H0.view(np.float32), H1.view(np.float32))

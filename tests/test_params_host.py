@@ -73,9 +73,9 @@ def test_parse_spec_fov_rules_and_subcarriers():
     p.freq_domain = 0
     p.num_paths = 10
     assert parse_spec(p, 10, times=[0, 1e-3]).out_shape(10, 25) == (10, 1, 8, 10, 2)
-    p.ofdm.rx_filter = 1
-    with pytest.raises(NotImplementedError):
-        parse_spec(p, 10)
+    p.ofdm.rx_filter = 1                                      # receive LPF (channel.py:193-194) is carried to the kernel
+    p.enable_dual_polar = 1                                   # present in the defaults, read by nothing in the reference
+    assert parse_spec(p, 10).rx_filter == 1
 
 
 def test_random_ue_rotation_matches_reference_draw():

@@ -46,4 +46,4 @@ def oracle_kwargs_from_params(p: dict, bs_fov=None, ue_fov=None) -> dict:
                 bs_pattern=p["bs_antenna"]["radiation_pattern"], ue_pattern=p["ue_antenna"]["radiation_pattern"],
                 bs_fov=bs_fov, ue_fov=ue_fov, num_paths=p["num_paths"], freq_domain=bool(p["freq_domain"]),
                 subcarriers=p["ofdm"]["subcarriers"], selected_subcarriers=p["ofdm"]["selected_subcarriers"],
-                bandwidth=p["ofdm"]["bandwidth"])
+                bandwidth=p["ofdm"]["bandwidth"], rx_filter=int(p["ofdm"].get("rx_filter", 0)))
