@@ -42,6 +42,11 @@ CPU_BASELINE_USERS = {1: 80000, 2: 128, 3: 256, 4: 20000, 5: 1024}
 FP32_LANES_PER_SM = 128
 
 
+def _lib_last_kernel():
+    from deepmimo_b200 import _lib
+    return _lib.last_kernel()
+
+
 def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
@@ -344,6 +349,31 @@ def gpu_main(args):
                 torch.cuda.empty_cache()
             except Exception as e:  # noqa: BLE001
                 extra[w] = {"error": str(e)[:200]}
+
+        # row f3: fused beam amplitude map (16-beam steering_vec codebook) on the headline shape -- H is never written
+        try:
+            import deepmimo_b200 as dmb
+            plan = res["plan"]
+            if plan.spec.freq_domain and plan.spec.times is None:
+                F = np.array([dmb.steering_vec(list(plan.spec.bs_shape), phi=a, spacing=plan.spec.bs_spacing).squeeze()
+                              for a in np.around(np.linspace(-60, 60, 16), 2)]).astype(np.complex64)
+                Fd = torch.from_numpy(F).cuda()
+                amp = torch.empty((plan.n_users, 16), dtype=torch.float32, device="cuda")
+                for _ in range(3):
+                    plan.run_beams(Fd, amp)
+                evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(5)]
+                for a, b in evs:
+                    flush.fill_(3)
+                    a.record(); plan.run_beams(Fd, amp); b.record()
+                torch.cuda.synchronize()
+                ms = sum(a.elapsed_time(b) for a, b in evs) / len(evs)
+                extra["beams16_" + args.workload] = {
+                    "ms_per_step": ms, "users": plan.n_users, "users_per_s": plan.n_users / (ms / 1e3),
+                    "beamformed_coef_per_s": plan.n_users * plan.spec.m_rx * 16 * len(plan.spec.selected) / (ms / 1e3),
+                    "equivalent_H_coef_per_s": res["n_coef"] / (ms / 1e3), "kernel": _lib_last_kernel().split(" ")[0],
+                    "what": "mean_{r,k} |F @ H| for a 16-beam codebook straight from the path matrices (dmk_beam_amplitude_fd)"}
+        except Exception as e:  # noqa: BLE001
+            extra["beams16_" + args.workload] = {"error": str(e)[:200]}
 
     if rank == 0:
         ms_step = total_ms / args.steps

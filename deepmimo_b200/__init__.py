@@ -9,10 +9,11 @@ from .params import ChannelGenParameters, ChannelParameters, DotDict
 from .dataset import Dataset, MacroDataset
 from .channels import (ChannelInfo, ChannelPlan, ChannelSpec, compute_channels, iter_channels, make_plan,
                        parse_spec)
+from .beams import beam_amplitude, steering_vec
 from .install import install, uninstall
 from .loader import load_scenario, load_tx_rx_raydata, save_scenario
 
 __version__ = "0.1.0"
 __all__ = ["ChannelGenParameters", "ChannelParameters", "DotDict", "Dataset", "MacroDataset", "ChannelInfo",
            "ChannelPlan", "ChannelSpec", "compute_channels", "iter_channels", "make_plan", "parse_spec",
-           "install", "uninstall", "load_scenario", "load_tx_rx_raydata", "save_scenario"]
+           "beam_amplitude", "steering_vec", "install", "uninstall", "load_scenario", "load_tx_rx_raydata", "save_scenario"]

@@ -44,7 +44,7 @@ class DmkDesc(ctypes.Structure):
 
 ABI_VERSION = 2
 FLAG_INDEPENDENT_LAUNCH = 1
-SYMBOLS = ("dmk_channels_fd", "dmk_channels_td", "dmk_path_prologue", "dmk_np_sincosf",
+SYMBOLS = ("dmk_channels_fd", "dmk_channels_td", "dmk_beam_amplitude_fd", "dmk_path_prologue", "dmk_np_sincosf",
            "dmk_last_error", "dmk_abi_version", "dmk_launch_count", "dmk_last_kernel")
 
 
@@ -60,6 +60,8 @@ def _declare(lib: ctypes.CDLL) -> None:
     lib.dmk_channels_fd.restype = ctypes.c_int
     lib.dmk_channels_td.argtypes = common + [vp, vp, vp, vp]
     lib.dmk_channels_td.restype = ctypes.c_int
+    lib.dmk_beam_amplitude_fd.argtypes = [desc_p] + [vp] * 7 + [vp, i64, i32, vp, i32, vp, vp, vp, vp, vp]
+    lib.dmk_beam_amplitude_fd.restype = ctypes.c_int
     lib.dmk_path_prologue.argtypes = [desc_p] + [vp] * 5 + [vp, i64, i32, vp, vp, vp, vp]
     lib.dmk_path_prologue.restype = ctypes.c_int
     lib.dmk_np_sincosf.argtypes = [vp, vp, vp, i64, vp]

@@ -337,6 +337,27 @@ class ChannelPlan:
         _lib.check(rc)
         return out
 
+    def run_beams(self, beams_dev, out, masks: Optional[dict] = None, stream=None):
+        """Fused beam amplitude map (dmk_beam_amplitude_fd): `beams_dev` complex64 CUDA [n_beams, M_t], `out` float32 CUDA
+        [n_users, n_beams] = mean over RX elements and subcarriers of |beams @ H|.  H is never written."""
+        torch = _torch()
+        nb = int(beams_dev.shape[0])
+        if tuple(beams_dev.shape) != (nb, self.spec.m_tx) or beams_dev.dtype != torch.complex64 or not beams_dev.is_contiguous():
+            raise ValueError(f"beams must be a contiguous complex64 CUDA tensor [n_beams, {self.spec.m_tx}]")
+        if tuple(out.shape) != (self.n_users, nb) or out.dtype != torch.float32 or not out.is_contiguous():
+            raise ValueError(f"out must be a contiguous float32 CUDA tensor [{self.n_users}, {nb}]")
+        st = torch.cuda.current_stream(self.device) if stream is None else stream
+        m = masks or {}
+        mp = lambda k: None if m.get(k) is None else m[k].data_ptr()
+        self.desc.flags = 0
+        with torch.cuda.device(self.device):
+            rc = self.lib.dmk_beam_amplitude_fd(
+                ctypes.byref(self.desc), *[self.t[k].data_ptr() for k in PATH_KEYS],
+                None if self.ue_rot is None else self.ue_rot.data_ptr(), self.n_users, self.n_cols,
+                beams_dev.data_ptr(), nb, out.data_ptr(), mp("fov"), mp("valid"), mp("clip"), st.cuda_stream)
+        _lib.check(rc)
+        return out
+
     def info_from_masks(self, masks: dict) -> ChannelInfo:
         p = self.spec.n_paths_eff(self.n_cols)
         info = ChannelInfo(kernel=_lib.last_kernel(), launches=_lib.launch_count())

@@ -11,6 +11,7 @@
 #include "dmk_fd_ws.cuh"
 #include "dmk_fd_small.cuh"
 #include "dmk_td.cuh"
+#include "dmk_bf.cuh"
 
 namespace {
 
@@ -419,6 +420,55 @@ int dmk_channels_td(const dmk_desc* desc, const float* power_dbw, const float* p
     if (e != cudaSuccess) return cuda_fail(e, "td_kernel launch");
     g_launches.fetch_add(1);
     snprintf(g_kernel, sizeof(g_kernel), "td_kernel grid=%lld", (long long)n_users);
+    return DMK_OK;
+}
+
+int dmk_beam_amplitude_fd(const dmk_desc* desc, const float* power_dbw, const float* phase_deg, const float* delay_s,
+                          const float* aoa_az_deg, const float* aoa_el_deg, const float* aod_az_deg, const float* aod_el_deg,
+                          const double* ue_rot_deg, int64_t n_users, int32_t ld, const void* beams_c64, int32_t n_beams,
+                          float* mean_abs, uint8_t* fov_mask, uint8_t* valid_mask, uint8_t* clip_mask, void* cuda_stream)
+{
+    using namespace dmk;
+    DevDesc d;
+    int rc = build_desc(desc, true, d);
+    if (rc) return rc;
+    rc = check_arrays(power_dbw, phase_deg, delay_s, aoa_az_deg, aoa_el_deg, aod_az_deg, aod_el_deg, n_users, ld, d.P0);
+    if (rc) return rc;
+    if (n_beams < 1 || n_beams > 4096) return fail(DMK_ERR_INVALID_ARG, "n_beams=%d outside [1, 4096]", n_beams);
+    if (d.has_time_axis) return fail(DMK_ERR_UNSUPPORTED, "beam amplitude maps take no time axis");
+    if (d.rx_filter) return fail(DMK_ERR_UNSUPPORTED, "beam amplitude maps do not apply the receive low-pass filter");
+    if (n_users == 0) return DMK_OK;
+    if (d.K == 0) return fail(DMK_ERR_INVALID_ARG, "no selected subcarriers: the mean over subcarriers is undefined");
+    if (!beams_c64 || !mean_abs) return fail(DMK_ERR_INVALID_ARG, "beams or output is NULL");
+    if (n_users > 0x7fffffffLL) return fail(DMK_ERR_INVALID_ARG, "grid too large: split the user range");
+    bind_arrays(d, power_dbw, phase_deg, delay_s, aoa_az_deg, aoa_el_deg, aod_az_deg, aod_el_deg, ue_rot_deg, nullptr, n_users, ld);
+    d.fov_mask = fov_mask; d.valid_mask = valid_mask; d.clip_mask = clip_mask;
+    if (d.K == 1 && d.subc_step == 0 && !d.subc) d.subc_step = 1;
+    BfCfg c;
+    c.n_beams = n_beams;
+    c.F = reinterpret_cast<const float2*>(beams_c64);
+    c.out = mean_abs;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 15) & ~size_t(15); return (int)o; };
+    c.off_G    = take((size_t)n_beams * kMaxPaths * sizeof(float2));
+    c.off_rows = take((size_t)d.Mr * n_beams * sizeof(float));
+    c.off_tY   = take((size_t)kMaxPaths * d.bs0 * sizeof(float2));
+    c.off_tZ   = take((size_t)kMaxPaths * d.bs1 * sizeof(float2));
+    c.off_aR   = take((size_t)kMaxPaths * d.Mr * sizeof(float2));
+    const size_t smem = (size_t)kMaxPaths * (kTK + kTM) * sizeof(float2) + off;
+    if (smem > 200 * 1024) return fail(DMK_ERR_UNSUPPORTED, "beam tables need %zu bytes of shared memory (> 200 KB): fewer beams or a smaller panel", smem);
+    static size_t attr_bf = 0;
+    if (smem > attr_bf) {
+        cudaError_t e = cudaFuncSetAttribute(bf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(bf_kernel)");
+        attr_bf = smem;
+    }
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(cuda_stream);
+    bf_kernel<<<(unsigned)n_users, kFdThreads, smem, st>>>(d, c);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "bf_kernel launch");
+    g_launches.fetch_add(1);
+    snprintf(g_kernel, sizeof(g_kernel), "bf_kernel<64x128> grid=%lld beams=%d smem=%zu", (long long)n_users, n_beams, smem);
     return DMK_OK;
 }
 

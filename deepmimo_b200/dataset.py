@@ -120,6 +120,15 @@ class Dataset(DotDict):
             params = self._data.get("ch_params") or ChannelGenParameters()
         return _ch.compute_channels(self, params, **kwargs)
 
+    # -- first consumer of H
+    def beam_amplitude(self, beams, params: Optional[ChannelGenParameters] = None, **kwargs):
+        """Beam amplitude map `np.abs(beams @ channel).mean(axis=1).mean(axis=-1)` without materialising the channel
+        (docs/manual.ipynb cell 105; deepmimo_b200/beams.py)."""
+        from .beams import beam_amplitude
+        if params is None:
+            params = self._data.get("ch_params") or ChannelGenParameters()
+        return beam_amplitude(self, beams, params, **kwargs)
+
     # -- per-user by-products (SURVEY.md 8f row f2): cheap host reductions over the path matrices and the GPU FoV mask
     def _compute_power_linear(self) -> np.ndarray:
         """dataset.py:694-696, generator_utils.py:35."""

@@ -121,6 +121,25 @@ int dmk_channels_td(const dmk_desc *desc,
                     uint8_t *fov_mask, uint8_t *valid_mask, int32_t *path_slot,
                     void *cuda_stream);
 
+/* Beam amplitude map, fused (docs/manual.ipynb cell 105 of the reference):
+ *   mean_abs[u, b] = mean over RX elements r and selected subcarriers k of | sum_t beams[b, t] H[u, r, t, k] |
+ * == np.abs(F1 @ dataset.channel).mean(axis=1).mean(axis=-1) with F1 = beams (rows e.g. from steering_vec,
+ * deepmimo/generator/geometry.py:322-339).  H is never written: the codebook is folded into the TX steering of
+ * every path and the [n, M_r, n_beams, K] product is reduced in registers.  Frequency domain, no time axis, rx_filter = 0.
+ *   beams_c64 : DEVICE complex64 [n_beams, M_t], row-major (M_t = bs_shape[0] * bs_shape[1], element order y fastest)
+ *   mean_abs  : DEVICE float32 [n, n_beams]
+ * masks as in dmk_channels_fd. */
+int dmk_beam_amplitude_fd(const dmk_desc *desc,
+                          const float *power_dbw, const float *phase_deg, const float *delay_s,
+                          const float *aoa_az_deg, const float *aoa_el_deg,
+                          const float *aod_az_deg, const float *aod_el_deg,
+                          const double *ue_rot_deg,
+                          int64_t n_users, int32_t ld,
+                          const void *beams_c64, int32_t n_beams,
+                          float *mean_abs,
+                          uint8_t *fov_mask, uint8_t *valid_mask, uint8_t *clip_mask,
+                          void *cuda_stream);
+
 /* Per-path by-products of the prologue (the Dataset caches the reference fills lazily):
  *   angles_rot : NULL or DEVICE double [4, n, n_cols] = _aod_el_rot, _aod_az_rot, _aoa_el_rot, _aoa_az_rot
  *                (radians, before FoV NaN-ing; dataset.py:351-356)

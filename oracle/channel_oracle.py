@@ -268,3 +268,26 @@ def compute_channels(data: dict, *, bs_shape=(8, 1), ue_shape=(1, 1), bs_spacing
             else:
                 H[i, :, :, :n_i, :] = (arp * pg[None, None, :])[..., None] * dphase[None, None, :, :]
     return dict(H=H, fov_mask=fov_mask, valid=valid, clip=clip, path_slot=path_slot)
+
+
+# --------------------------------------------------------------------------
+# row f3: beamforming codebooks and beam amplitude maps (adjacent consumer of H)
+# --------------------------------------------------------------------------
+def steering_vec(array, phi: float = 0, theta: float = 0, spacing: float = 0.5) -> np.ndarray:
+    """Normalised steering vector [M, 1] complex128.  deepmimo/generator/geometry.py:322-339.
+
+    The reference passes (phi*pi/180, theta*pi/180 + pi/2) to `_array_response(ant_ind, theta, phi, kd)`
+    (geometry.py:338, :19), i.e. the azimuth lands in the `theta` slot and the shifted elevation in the `phi`
+    slot; the phases follow geometry.py:99-101 with those arguments.  Restated as is.
+    """
+    idx = element_grid(array)                                   # :337
+    th, ph, kd = phi * np.pi / 180, theta * np.pi / 180 + np.pi / 2, 2 * np.pi * spacing
+    gamma = np.vstack([1j * kd * np.sin(th) * np.cos(ph), 1j * kd * np.sin(th) * np.sin(ph), 1j * kd * np.cos(th)]).T   # :99-102
+    resp = np.exp(idx @ gamma.T)                                # :35
+    return resp / np.linalg.norm(resp)                          # :339
+
+
+def beam_amplitude(H: np.ndarray, F: np.ndarray) -> np.ndarray:
+    """Mean amplitude per (user, beam) of the beamformed channel, docs/manual.ipynb cell 105:
+    `np.abs(F1 @ channel).mean(axis=1).mean(axis=-1)` with F1 [n_beams, M_t], channel [n, M_r, M_t, K]."""
+    return np.abs(F @ H).mean(axis=1).mean(axis=-1)
