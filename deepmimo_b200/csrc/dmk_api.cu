@@ -444,6 +444,49 @@ int dmk_beam_amplitude_fd(const dmk_desc* desc, const float* power_dbw, const fl
     bind_arrays(d, power_dbw, phase_deg, delay_s, aoa_az_deg, aoa_el_deg, aod_az_deg, aod_el_deg, ue_rot_deg, nullptr, n_users, ld);
     d.fov_mask = fov_mask; d.valid_mask = valid_mask; d.clip_mask = clip_mask;
     if (d.K == 1 && d.subc_step == 0 && !d.subc) d.subc_step = 1;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(cuda_stream);
+    // Production route: the packed-FP32 kernel in beam mode (virtual TX panel 1 x n_beams, dmk_fd.cuh: fd_fast_body<true>).
+    // Needs an affine subcarrier selection and tables that fit; otherwise the generic tile version below runs.
+    {
+        const bool affine = (d.subc_step != 0) || (d.K == 1);
+        DevDesc db = d;
+        db.bs0 = 1; db.bs1 = n_beams; db.Mt = n_beams; db.M = d.Mr * n_beams;
+        FastCfg cfg;
+        BeamCfg bc;
+        size_t fast_smem = 0;
+        const int pc = d.P > 0 ? d.P : 1;
+        auto take = [&](size_t bytes) { size_t o = fast_smem; fast_smem += (bytes + 15) & ~size_t(15); return (int)o; };
+        cfg.pcap = pc;
+        cfg.nA = (d.K + 15) / 16;
+        cfg.off_W  = take((size_t)pc * kTKW * sizeof(float2));
+        cfg.off_A  = take((size_t)8 * pc * 8 * sizeof(float4));
+        cfg.off_tY = take((size_t)pc * sizeof(float2));
+        cfg.off_tQ = take((size_t)pc * db.M * sizeof(float2));
+        cfg.off_wA = take((size_t)pc * cfg.nA * sizeof(float2));
+        cfg.off_wB = take((size_t)pc * 16 * sizeof(float2));
+        bc.off_rows = take((size_t)db.M * sizeof(float));
+        cfg.mul_mt  = db.Mt > 1 ? (unsigned)((0x100000000ULL + db.Mt - 1) / db.Mt) : 0u;
+        cfg.mul_bs0 = 0u;
+        bc.n_beams = n_beams; bc.bs0 = d.bs0; bc.bs1 = d.bs1;
+        bc.F = reinterpret_cast<const float2*>(beams_c64);
+        bc.out = mean_abs;
+        const bool div_ok = (unsigned long long)db.M * (unsigned long long)db.Mt < 0xffffffffULL;
+        const char* force = getenv("DMK_BF_KERNEL");
+        if (affine && div_ok && fast_smem <= 110 * 1024 && d.bs0 + d.bs1 + d.Mr <= kTKW && !(force && !strcmp(force, "tile"))) {
+            static size_t attr_bff = 0;
+            if (fast_smem > attr_bff) {
+                cudaError_t e = cudaFuncSetAttribute(bf_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(110 * 1024));
+                if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(bf_fast_kernel)");
+                attr_bff = 110 * 1024;
+            }
+            bf_fast_kernel<<<(unsigned)n_users, kFdThreads, fast_smem, st>>>(db, cfg, bc);
+            cudaError_t e = cudaGetLastError();
+            if (e != cudaSuccess) return cuda_fail(e, "bf_fast_kernel launch");
+            g_launches.fetch_add(1);
+            snprintf(g_kernel, sizeof(g_kernel), "bf_fast_kernel<64x256,ffma2> grid=%lld beams=%d smem=%zu", (long long)n_users, n_beams, fast_smem);
+            return DMK_OK;
+        }
+    }
     BfCfg c;
     c.n_beams = n_beams;
     c.F = reinterpret_cast<const float2*>(beams_c64);
@@ -463,7 +506,6 @@ int dmk_beam_amplitude_fd(const dmk_desc* desc, const float* power_dbw, const fl
         if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(bf_kernel)");
         attr_bf = smem;
     }
-    cudaStream_t st = reinterpret_cast<cudaStream_t>(cuda_stream);
     bf_kernel<<<(unsigned)n_users, kFdThreads, smem, st>>>(d, c);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "bf_kernel launch");

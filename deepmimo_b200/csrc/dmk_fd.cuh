@@ -337,8 +337,19 @@ struct FastCfg {
 
 __device__ __forceinline__ float4 ldsA(const float4* p) { return *p; }
 
-__global__ void __launch_bounds__(kFdThreads, 2)
-fd_fast_kernel(const __grid_constant__ DevDesc d, const FastCfg cfg, const int ksplit)
+// Beam mode (row f3, dmk_beam_amplitude_fd): the same contraction with the M_t antenna rows replaced by n_beams beam rows.
+// The host hands the kernel a descriptor whose TX panel is the "virtual array" 1 x n_beams (bs0 = 1, bs1 = Mt = n_beams), the
+// table tQ[p][r * n_beams + b] = c_p a_rx[r,p] G[b,p] with G[b,p] = sum_t F[b,t] a_tx[t,p] is built from the true panel, and
+// the epilogue reduces |acc| over the columns instead of storing it: 4 bytes per (user, beam) leave the SM.
+struct BeamCfg {
+    int n_beams, bs0, bs1;            // codebook rows; the true TX panel
+    int off_rows;                     // byte offset of rows[Mr * n_beams] (float) in dynamic shared memory
+    const float2* F;                  // DEVICE [n_beams, bs0 * bs1] complex64
+    float* out;                       // DEVICE [n_users, n_beams] float32
+};
+
+template <bool kBeams>
+__device__ __forceinline__ void fd_fast_body(const DevDesc& d, const FastCfg& cfg, const int ksplit, const BeamCfg& bf)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2* sW = reinterpret_cast<float2*>(smem_raw + cfg.off_W);    // [pcap][kTKW]
@@ -359,13 +370,53 @@ fd_fast_kernel(const __grid_constant__ DevDesc d, const FastCfg cfg, const int k
     const int ncols = d.K;
     const int n_ct = (ncols + kTKW - 1) / kTKW;
     const int n_rt = (d.M + kTM - 1) / kTM;
-    float2* out_u = d.out + user * (long long)d.M * ncols;
+    float2* out_u = kBeams ? nullptr : d.out + user * (long long)d.M * ncols;
     const bool vec_ok = ((ncols & 1) == 0) && ((reinterpret_cast<uintptr_t>(d.out) & 15) == 0);
     const int nq = d.Mr * d.bs1;
+    float* rows = reinterpret_cast<float*>(smem_raw + bf.off_rows);     // beam mode: sum over columns of |Y| per (rx element, beam)
+    if (kBeams && np == 0) {                                            // no contributing path: H == 0 -> amplitude 0
+        for (int b = tid; b < bf.n_beams; b += kFdThreads) bf.out[user * (long long)bf.n_beams + b] = 0.f;
+        return;
+    }
 
     // ---- per-user tables (phase reduced in float64 for every entry)
     {
         const int bs0 = d.bs0, bs1 = d.bs1, nA = cfg.nA;
+        if (kBeams) {
+            // TX steering of the true panel and gain * RX steering go to scratch tables in the (still unused) W tile area
+            const int tb0 = bf.bs0, tb1 = bf.bs1, Mr = d.Mr, B = bf.n_beams;
+            float2* xY = sW;                              // [np][tb0]
+            float2* xZ = xY + np * tb0;                   // [np][tb1]
+            float2* xR = xZ + np * tb1;                   // [np][Mr]
+            for (int e = tid; e < np * tb0; e += kFdThreads) { const int p = e / tb0, y = e - p * tb0; xY[e] = phasor_cycles((double)y * sh.u[0][p]); }
+            for (int e = tid; e < np * tb1; e += kFdThreads) { const int p = e / tb1, z = e - p * tb1; xZ[e] = phasor_cycles((double)z * sh.v[0][p]); }
+            for (int e = tid; e < np * Mr; e += kFdThreads) {
+                const int p = e / Mr, r = e - p * Mr;
+                const int yr = r % d.ue0, zr = r / d.ue0;
+                xR[e] = cmul(sh.c[p], phasor_cycles((double)yr * sh.u[1][p] + (double)zr * sh.v[1][p]));
+            }
+            for (int e = tid; e < Mr * B; e += kFdThreads) rows[e] = 0.f;
+            for (int e = tid; e < np; e += kFdThreads) tY[e] = make_float2(1.f, 0.f);          // virtual panel: bs0 == 1
+            __syncthreads();
+            // G[b][p] = sum_t F[b,t] a_tx[t,p] (a_tx separable: y fastest), then tQ[p][r * B + b] = c_p a_rx[r,p] G[b,p]
+            for (int e = tid; e < B * np; e += kFdThreads) {
+                const int b = e / np, p = e - b * np;
+                const float2* f = bf.F + (long long)b * (tb0 * tb1);
+                float2 g = make_float2(0.f, 0.f);
+                for (int z = 0; z < tb1; ++z) {
+                    float2 gz = make_float2(0.f, 0.f);
+                    for (int y = 0; y < tb0; ++y) {
+                        const float2 fv = __ldg(f + z * tb0 + y), ty = xY[p * tb0 + y];
+                        gz.x = fmaf(fv.x, ty.x, gz.x); gz.x = fmaf(-fv.y, ty.y, gz.x);
+                        gz.y = fmaf(fv.x, ty.y, gz.y); gz.y = fmaf(fv.y, ty.x, gz.y);
+                    }
+                    const float2 tz = xZ[p * tb1 + z];
+                    g.x = fmaf(gz.x, tz.x, g.x); g.x = fmaf(-gz.y, tz.y, g.x);
+                    g.y = fmaf(gz.x, tz.y, g.y); g.y = fmaf(gz.y, tz.x, g.y);
+                }
+                for (int r = 0; r < Mr; ++r) tQ[p * nq + r * B + b] = cmul(xR[p * Mr + r], g);
+            }
+        } else {
         for (int e = tid; e < np * bs0; e += kFdThreads) {
             const int p = e / bs0, y = e - p * bs0;
             tY[p * bs0 + y] = phasor_cycles((double)y * sh.u[0][p]);
@@ -375,6 +426,7 @@ fd_fast_kernel(const __grid_constant__ DevDesc d, const FastCfg cfg, const int k
             const int r = q / bs1, z = q - r * bs1;
             const int yr = r % d.ue0, zr = r / d.ue0;
             tQ[p * nq + q] = cmul(sh.c[p], phasor_cycles((double)z * sh.v[0][p] + (double)yr * sh.u[1][p] + (double)zr * sh.v[1][p]));
+        }
         }
         for (int e = tid; e < np * nA; e += kFdThreads) {
             const int p = e / nA, a = e - p * nA;
@@ -454,6 +506,19 @@ fd_fast_kernel(const __grid_constant__ DevDesc d, const FastCfg cfg, const int k
                     }
                 }
 
+                if (kBeams) {
+                    // ---- |Y| summed over the pass's columns (W is zero beyond ncols); the warp owns its 8 rows: no atomics
+                    #pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        float sa = 0.f;
+                        #pragma unroll
+                        for (int j = 0; j < 4; ++j) sa += sqrtf(fmaf(acc[i][j].x, acc[i][j].x, acc[i][j].y * acc[i][j].y));
+                        #pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) sa += __shfl_xor_sync(0xffffffffu, sa, o);
+                        if (lane == 0 && row0 + i < d.M) rows[row0 + i] += sa;
+                    }
+                    continue;
+                }
                 // ---- store: lane owns columns {2l, 2l+1} and {64+2l, 64+2l+1} of this 128-column pass
                 const int colp = col0 + pass * kTK;
                 float2* obase = out_u + (long long)row0 * ncols + colp + 2 * lane;
@@ -480,6 +545,28 @@ fd_fast_kernel(const __grid_constant__ DevDesc d, const FastCfg cfg, const int k
             }
         }
     }
+    if (kBeams) {
+        __syncthreads();
+        const int B = bf.n_beams;
+        const float inv = 1.0f / ((float)d.Mr * (float)ncols);
+        for (int b = tid; b < B; b += kFdThreads) {
+            float sa = 0.f;
+            for (int r = 0; r < d.Mr; ++r) sa += rows[r * B + b];
+            bf.out[user * (long long)B + b] = sa * inv;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kFdThreads, 2)
+fd_fast_kernel(const __grid_constant__ DevDesc d, const FastCfg cfg, const int ksplit)
+{
+    fd_fast_body<false>(d, cfg, ksplit, BeamCfg{});
+}
+
+__global__ void __launch_bounds__(kFdThreads, 2)
+bf_fast_kernel(const __grid_constant__ DevDesc d, const FastCfg cfg, const __grid_constant__ BeamCfg bf)
+{
+    fd_fast_body<true>(d, cfg, 1, bf);
 }
 
 }  // namespace dmk

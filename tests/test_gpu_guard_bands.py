@@ -9,7 +9,7 @@ GUARD = 1 << 16          # complex64 elements on each side (512 KiB)
 CANARY = np.complex64(complex(-7.0e33, 3.0e-33))
 
 
-def _plan(bs, ue, n_sc, sel, n, fd=1, times=None, n_cols=25, seed=5):
+def _plan(bs, ue, n_sc, sel, n, fd=1, times=None, n_cols=25, seed=5, rx_filter=0):
     import deepmimo_b200 as dmb
     from deepmimo_b200.synth import doppler_from_velocity, make_paths
     d = make_paths(n, seed, n_sc=n_sc, bandwidth=50e6, n_cols=n_cols)
@@ -17,7 +17,7 @@ def _plan(bs, ue, n_sc, sel, n, fd=1, times=None, n_cols=25, seed=5):
     p.bs_antenna.shape = np.array(bs); p.ue_antenna.shape = np.array(ue)
     p.bs_antenna.rotation = np.array([5, 10, 15])
     p.ofdm.subcarriers = n_sc; p.ofdm.selected_subcarriers = np.asarray(sel); p.ofdm.bandwidth = 50e6
-    p.freq_domain = fd; p.num_paths = n_cols
+    p.freq_domain = fd; p.num_paths = n_cols; p.ofdm.rx_filter = rx_filter
     dop = doppler_from_velocity(d, 1, 3.5e9) if times is not None else None
     plan, _ = dmb.make_plan(dmb.Dataset(d), p, times=times, doppler=dop, warn=False)
     return plan
@@ -46,7 +46,7 @@ def _run_guarded(plan):
     return inner.reshape(shape)
 
 
-@pytest.mark.parametrize("variant", ["tc", "ffma", "tile"])
+@pytest.mark.parametrize("variant", ["tc", "tc1", "ffma", "tile"])
 @pytest.mark.parametrize("bs,ue,k", [((12, 11), (1, 1), 192), ((5, 3), (3, 1), 64), ((3, 3), (1, 1), 320), ((9, 8), (2, 1), 128)])
 def test_fd_kernels_stay_in_bounds(variant, bs, ue, k, monkeypatch):
     monkeypatch.setenv("DMK_FD_KERNEL", variant)
@@ -75,3 +75,9 @@ def test_td_kernel_stays_in_bounds(times):
 
 def test_fd_time_axis_stays_in_bounds():
     _run_guarded(_plan((4, 2), (1, 1), 256, np.arange(48), 19, times=np.arange(3) * 1e-3))
+
+
+@pytest.mark.parametrize("n_sc,sel", [(256, np.arange(256)), (600, np.arange(0, 600, 7)), (1024, np.arange(130))])
+def test_fd_lowpass_filter_stays_in_bounds(n_sc, sel):
+    H = _run_guarded(_plan((5, 3), (2, 1), n_sc, sel, 21, rx_filter=1))
+    assert H.shape == (21, 2, 15, len(sel))
