@@ -472,7 +472,11 @@ int dmk_beam_amplitude_fd(const dmk_desc* desc, const float* power_dbw, const fl
         bc.out = mean_abs;
         const bool div_ok = (unsigned long long)db.M * (unsigned long long)db.Mt < 0xffffffffULL;
         const char* force = getenv("DMK_BF_KERNEL");
-        if (affine && div_ok && fast_smem <= 110 * 1024 && d.bs0 + d.bs1 + d.Mr <= kTKW && !(force && !strcmp(force, "tile"))) {
+        // scratch tables [np][bs0|1], [np][bs1|1], [np][Mr] live in the W tile area, one staged codebook row [n_beams][bs0] in the
+        // A strip area, and a thread accumulates at most 8 (beam, path) pairs
+        const bool scratch_ok = (d.bs0 | 1) + (d.bs1 | 1) + d.Mr <= kTKW && (size_t)n_beams * d.bs0 * sizeof(float2) <= (size_t)8 * pc * 8 * sizeof(float4) &&
+                                (long long)n_beams * pc <= 8LL * kFdThreads;
+        if (affine && div_ok && fast_smem <= 110 * 1024 && scratch_ok && !(force && !strcmp(force, "tile"))) {
             static size_t attr_bff = 0;
             if (fast_smem > attr_bff) {
                 cudaError_t e = cudaFuncSetAttribute(bf_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(110 * 1024));

@@ -383,13 +383,17 @@ __device__ __forceinline__ void fd_fast_body(const DevDesc& d, const FastCfg& cf
     {
         const int bs0 = d.bs0, bs1 = d.bs1, nA = cfg.nA;
         if (kBeams) {
-            // TX steering of the true panel and gain * RX steering go to scratch tables in the (still unused) W tile area
+            // TX steering of the true panel and gain * RX steering go to scratch tables in the (still unused) W tile area;
+            // the codebook is staged one panel row (tb0 entries of every beam) at a time in the (still unused) A strip area,
+            // so its loads are coalesced and off the dependent path.  Odd table strides: lanes that differ in p hit different banks.
             const int tb0 = bf.bs0, tb1 = bf.bs1, Mr = d.Mr, B = bf.n_beams;
-            float2* xY = sW;                              // [np][tb0]
-            float2* xZ = xY + np * tb0;                   // [np][tb1]
-            float2* xR = xZ + np * tb1;                   // [np][Mr]
-            for (int e = tid; e < np * tb0; e += kFdThreads) { const int p = e / tb0, y = e - p * tb0; xY[e] = phasor_cycles((double)y * sh.u[0][p]); }
-            for (int e = tid; e < np * tb1; e += kFdThreads) { const int p = e / tb1, z = e - p * tb1; xZ[e] = phasor_cycles((double)z * sh.v[0][p]); }
+            const int sy = tb0 | 1, sz = tb1 | 1;
+            float2* xY = sW;                              // [np][sy]
+            float2* xZ = xY + np * sy;                    // [np][sz]
+            float2* xR = xZ + np * sz;                    // [np][Mr]
+            float2* fS = reinterpret_cast<float2*>(sA);   // [B][tb0]
+            for (int e = tid; e < np * tb0; e += kFdThreads) { const int p = e / tb0, y = e - p * tb0; xY[p * sy + y] = phasor_cycles((double)y * sh.u[0][p]); }
+            for (int e = tid; e < np * tb1; e += kFdThreads) { const int p = e / tb1, z = e - p * tb1; xZ[p * sz + z] = phasor_cycles((double)z * sh.v[0][p]); }
             for (int e = tid; e < np * Mr; e += kFdThreads) {
                 const int p = e / Mr, r = e - p * Mr;
                 const int yr = r % d.ue0, zr = r / d.ue0;
@@ -397,24 +401,46 @@ __device__ __forceinline__ void fd_fast_body(const DevDesc& d, const FastCfg& cf
             }
             for (int e = tid; e < Mr * B; e += kFdThreads) rows[e] = 0.f;
             for (int e = tid; e < np; e += kFdThreads) tY[e] = make_float2(1.f, 0.f);          // virtual panel: bs0 == 1
-            __syncthreads();
-            // G[b][p] = sum_t F[b,t] a_tx[t,p] (a_tx separable: y fastest), then tQ[p][r * B + b] = c_p a_rx[r,p] G[b,p]
-            for (int e = tid; e < B * np; e += kFdThreads) {
-                const int b = e / np, p = e - b * np;
-                const float2* f = bf.F + (long long)b * (tb0 * tb1);
-                float2 g = make_float2(0.f, 0.f);
-                for (int z = 0; z < tb1; ++z) {
-                    float2 gz = make_float2(0.f, 0.f);
-                    for (int y = 0; y < tb0; ++y) {
-                        const float2 fv = __ldg(f + z * tb0 + y), ty = xY[p * tb0 + y];
-                        gz.x = fmaf(fv.x, ty.x, gz.x); gz.x = fmaf(-fv.y, ty.y, gz.x);
-                        gz.y = fmaf(fv.x, ty.y, gz.y); gz.y = fmaf(fv.y, ty.x, gz.y);
-                    }
-                    const float2 tz = xZ[p * tb1 + z];
-                    g.x = fmaf(gz.x, tz.x, g.x); g.x = fmaf(-gz.y, tz.y, g.x);
-                    g.y = fmaf(gz.x, tz.y, g.y); g.y = fmaf(gz.y, tz.x, g.y);
+            // G[b][p] = sum_z xZ[p][z] sum_y F[b, z*tb0 + y] xY[p][y]; a thread owns up to kBeamAcc (beam, path) pairs
+            constexpr int kBeamAcc = 8;
+            float2 g[kBeamAcc];
+            #pragma unroll
+            for (int k = 0; k < kBeamAcc; ++k) g[k] = make_float2(0.f, 0.f);
+            const int n_bp = B * np;
+            for (int z = 0; z < tb1; ++z) {
+                __syncthreads();                          // tables written (z == 0) / the previous row's readers are done with fS
+                for (int e = tid; e < B * tb0; e += kFdThreads) {
+                    const int b = e / tb0, y = e - b * tb0;
+                    fS[e] = __ldg(bf.F + (long long)b * (tb0 * tb1) + z * tb0 + y);
                 }
-                for (int r = 0; r < Mr; ++r) tQ[p * nq + r * B + b] = cmul(xR[p * Mr + r], g);
+                __syncthreads();
+                #pragma unroll
+                for (int k = 0; k < kBeamAcc; ++k) {
+                    const int e = tid + k * kFdThreads;
+                    if (e < n_bp) {
+                        const int b = e / np, p = e - b * np;
+                        const float2* f = fS + b * tb0;
+                        const float2* ty = xY + p * sy;
+                        float2 gz = make_float2(0.f, 0.f);
+                        for (int y = 0; y < tb0; ++y) {
+                            const float2 fv = f[y], t = ty[y];
+                            gz.x = fmaf(fv.x, t.x, gz.x); gz.x = fmaf(-fv.y, t.y, gz.x);
+                            gz.y = fmaf(fv.x, t.y, gz.y); gz.y = fmaf(fv.y, t.x, gz.y);
+                        }
+                        const float2 tz = xZ[p * sz + z];
+                        g[k].x = fmaf(gz.x, tz.x, g[k].x); g[k].x = fmaf(-gz.y, tz.y, g[k].x);
+                        g[k].y = fmaf(gz.x, tz.y, g[k].y); g[k].y = fmaf(gz.y, tz.x, g[k].y);
+                    }
+                }
+            }
+            // tQ[p][r * B + b] = c_p a_rx[r,p] G[b,p]
+            #pragma unroll
+            for (int k = 0; k < kBeamAcc; ++k) {
+                const int e = tid + k * kFdThreads;
+                if (e < n_bp) {
+                    const int b = e / np, p = e - b * np;
+                    for (int r = 0; r < Mr; ++r) tQ[p * nq + r * B + b] = cmul(xR[p * Mr + r], g[k]);
+                }
             }
         } else {
         for (int e = tid; e < np * bs0; e += kFdThreads) {
@@ -512,7 +538,10 @@ __device__ __forceinline__ void fd_fast_body(const DevDesc& d, const FastCfg& cf
                     for (int i = 0; i < 8; ++i) {
                         float sa = 0.f;
                         #pragma unroll
-                        for (int j = 0; j < 4; ++j) sa += sqrtf(fmaf(acc[i][j].x, acc[i][j].x, acc[i][j].y * acc[i][j].y));
+                        for (int j = 0; j < 4; ++j) {
+                            const float q = fmaf(acc[i][j].x, acc[i][j].x, acc[i][j].y * acc[i][j].y);
+                            sa = fmaf(q, rsqrtf(fmaxf(q, 1e-37f)), sa);          // |y| = q * rsqrt(q) (2 ulp; exact 0 for q == 0)
+                        }
                         #pragma unroll
                         for (int o = 16; o > 0; o >>= 1) sa += __shfl_xor_sync(0xffffffffu, sa, o);
                         if (lane == 0 && row0 + i < d.M) rows[row0 + i] += sa;
