@@ -299,6 +299,31 @@ def cpu_baseline(s, workload, cores=1):
                       f"(NumPy {np.__version__}, single thread like the reference's per-user loop)"}
 
 
+def bind_to_gpu_cpus(device_index: int):
+    """Pin this rank to the CPUs NVML reports as local to its GPU (same NUMA node / PCIe root) before any pinned host
+    buffer is allocated: with one process per GPU the D2H copies of the e2e leg then land in node-local memory instead
+    of crossing the socket interconnect.  Returns the CPU count used, or None if NVML / the syscall is unavailable."""
+    try:
+        import pynvml
+        import torch
+        pynvml.nvmlInit()
+        uuid = str(torch.cuda.get_device_properties(device_index).uuid)
+        try:
+            h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid).encode())
+        except Exception:  # noqa: BLE001
+            h = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (int(m) >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception as e:  # noqa: BLE001
+        log(f"[bench] CPU affinity not set ({e})")
+    return None
+
+
 def gpu_main(args):
     # stdout must carry exactly one JSON line: libraries (NCCL prints its version banner) write to fd 1, so
     # fd 1 is pointed at stderr for the run and the JSON line goes to the saved descriptor.
@@ -313,6 +338,7 @@ def gpu_main(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device; there is no CPU fallback for the b200 arm")
     torch.cuda.set_device(local)
+    n_local_cpus = bind_to_gpu_cpus(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     hbm_peak, sm_max_mhz, peak_src = measured_peaks()
@@ -413,6 +439,7 @@ def gpu_main(args):
                          "t_min_bound": "fp32" if t_fma > t_write else "hbm"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"],
                     "users_per_gpu": e2e["users"], "steps": e2e["steps"],
+                    "cpu_affinity": (f"rank pinned to the {n_local_cpus} CPUs NVML reports local to its GPU" if n_local_cpus else "not set"),
                     "path": "deepmimo_b200.compute_channels(dataset, params, host_out=pinned): pinned H2D + fused kernel "
                             "(1 GiB chunks, 2 device buffers) + D2H overlapped on a copy stream"},
             "gpu_launches": res["launches"],

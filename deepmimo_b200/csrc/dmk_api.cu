@@ -291,7 +291,8 @@ int dmk_channels_fd(const dmk_desc* desc, const float* power_dbw, const float* p
     // takes the shapes whose double-buffered tables do not fit next to the operand tiles.
     const bool want_tc1 = force && !strcmp(force, "tc1");
     TcCfg pcfg = tcfg;
-    size_t ptc_smem = 1024;
+    size_t ptc_smem = 0;
+    int n_helpers = 1;
     {
         const int pc = (d.P > 0 ? d.P : 1) + 1;                  // + the zero row the builders read for padding slots
         size_t off = 0;
@@ -308,16 +309,25 @@ int dmk_channels_fd(const dmk_desc* desc, const float* power_dbw, const float* p
         pcfg.off_wB = ttake((size_t)pc * pcfg.sB * sizeof(float2));
         pcfg.off_seed = ttake((size_t)pc * pcfg.sS * sizeof(float2));
         pcfg.off_wA = 0;
-        pcfg.tab_bytes = (int)toff;
-        ptc_smem += off + 2 * toff;
+        const size_t buf_bytes = ((sizeof(TcUserBuf) + 15) & ~size_t(15)) + toff;      // [user record][tables]
+        pcfg.tab_bytes = (int)buf_bytes;
+        // One helper warp prepares a user in ~30-45 k cycles (float64 prologue + tables, latency-bound).  Users whose output is
+        // written faster than that (< ~400 KB) make the kernel helper-bound: they get four helper warps and eight buffers in a
+        // single CTA per SM (shared memory and registers allow it because only one CTA is resident).
+        const size_t per_user_bytes = (size_t)d.M * d.K * sizeof(float2);
+        const size_t smem4 = 1024 + off + 8 * buf_bytes;
+        const char* hf = getenv("DMK_WS_HELPERS");
+        if ((per_user_bytes <= 384 * 1024 || (hf && atoi(hf) == 4)) && smem4 <= 220 * 1024 && !(hf && atoi(hf) == 1)) n_helpers = 4;
+        ptc_smem = 1024 + off + 2 * n_helpers * buf_bytes;
     }
-    const bool use_tcp = use_tc && !want_tc1 && ptc_smem <= 109600 && grid < 0xffffff00LL;   // + ~6 KB static + 1 KB reserve: two CTAs per SM
+    const bool use_tcp = use_tc && !want_tc1 && (n_helpers == 4 || ptc_smem <= 113200) && grid < 0xffffff00LL;   // H = 1: + ~2.6 KB static + 1 KB reserve, two CTAs per SM
     if (use_tcp) {
         // warp-specialised persistent kernel (dmk_fd_ws.cuh): the production tensor-core path
         if (d.K == 1 && d.subc_step == 0) d.subc_step = 1;
         static bool attr_ws = false;
         if (!attr_ws) {
-            cudaError_t e = cudaFuncSetAttribute(fd_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(110 * 1024));
+            cudaError_t e = cudaFuncSetAttribute(fd_ws_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(114 * 1024));
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(fd_ws_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024));
             if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(fd_ws_kernel)");
             attr_ws = true;
         }
@@ -325,7 +335,7 @@ int dmk_channels_fd(const dmk_desc* desc, const float* power_dbw, const float* p
         unsigned int* tickets = nullptr;
         cudaError_t e = cudaGetSymbolAddress(reinterpret_cast<void**>(&tickets), g_tc_ticket);
         if (e != cudaSuccess) return cuda_fail(e, "cudaGetSymbolAddress(g_tc_ticket)");
-        const long long resident = 2LL * device_sm_count();
+        const long long resident = (n_helpers == 1 ? 2LL : 1LL) * device_sm_count();
         const long long pgrid = grid < resident ? grid : resident;
         // Programmatic dependent launch: the kernel releases its dependents at once, so the next libdmk launch can fill SMs
         // as this one's persistent CTAs retire.  Unless the caller set DMK_FLAG_INDEPENDENT_LAUNCH the kernel itself
@@ -333,18 +343,18 @@ int dmk_channels_fd(const dmk_desc* desc, const float* power_dbw, const float* p
         const int pdl_wait = (desc->flags & DMK_FLAG_INDEPENDENT_LAUNCH) ? 0 : 1;
         cudaLaunchConfig_t lc;
         memset(&lc, 0, sizeof(lc));
-        lc.gridDim = dim3((unsigned)pgrid); lc.blockDim = dim3(kWsThreads); lc.dynamicSmemBytes = ptc_smem; lc.stream = st;
+        lc.gridDim = dim3((unsigned)pgrid); lc.blockDim = dim3((9 + n_helpers) * 32); lc.dynamicSmemBytes = ptc_smem; lc.stream = st;
         cudaLaunchAttribute at[1];
         at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         at[0].val.programmaticStreamSerializationAllowed = 1;
         lc.attrs = at; lc.numAttrs = 1;
-        e = cudaLaunchKernelEx(&lc, fd_ws_kernel, d, pcfg, (int)ksplit, (unsigned)grid,
-                               tickets + (ticket_seq.fetch_add(1) % kTcTickets), pdl_wait);
-        if (e != cudaSuccess) return cuda_fail(e, "fd_ws_kernel launch");
-        e = cudaGetLastError();
+        unsigned int* tk = tickets + (ticket_seq.fetch_add(1) % kTcTickets);
+        if (n_helpers == 1) e = cudaLaunchKernelEx(&lc, fd_ws_kernel<1>, d, pcfg, (int)ksplit, (unsigned)grid, tk, pdl_wait);
+        else                e = cudaLaunchKernelEx(&lc, fd_ws_kernel<4>, d, pcfg, (int)ksplit, (unsigned)grid, tk, pdl_wait);
         if (e != cudaSuccess) return cuda_fail(e, "fd_ws_kernel launch");
         g_launches.fetch_add(1);
-        snprintf(g_kernel, sizeof(g_kernel), "fd_ws_kernel<%dx128,3xf16> grid=%lld items=%lld ksplit=%lld smem=%zu", pcfg.mtile, pgrid, grid, ksplit, ptc_smem);
+        snprintf(g_kernel, sizeof(g_kernel), "fd_ws_kernel<%dx128,3xf16,%d helper%s> grid=%lld items=%lld ksplit=%lld smem=%zu", pcfg.mtile, n_helpers,
+                 n_helpers > 1 ? "s" : "", pgrid, grid, ksplit, ptc_smem);
         return DMK_OK;
     }
     if (use_tc) {

@@ -15,7 +15,7 @@
 
 namespace dmk {
 
-constexpr int kSmallWarps = 4;            // users per CTA
+constexpr int kSmallWarps = 3;            // users per CTA: 6 CTAs = 18 warps per SM fit the 12 KB-per-warp tables and 112 registers (4 x 4 = 16 did)
 
 struct SmallCfg {
     int off_sh, off_tY, off_tQ, off_wB, off_seed, off_A;    // byte offsets inside a warp's shared-memory slice
@@ -25,7 +25,7 @@ struct SmallCfg {
 };
 
 template <int MT>      // rows held in registers: 4, 8 or 16 (M <= MT)
-__global__ void __launch_bounds__(kSmallWarps * 32, 4)
+__global__ void __launch_bounds__(kSmallWarps * 32, 6)
 fd_small_kernel(const __grid_constant__ DevDesc d, const __grid_constant__ SmallCfg cfg)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];

@@ -21,15 +21,16 @@
 
 namespace dmk {
 
-constexpr int kWsThreads  = 320;
+constexpr int kWsConsumers = 288;  // warps 0-8: threads that read a user record (and arrive on ub_empty)
 constexpr int kWsDrain0   = 0;     // warps 0-3
 constexpr int kWsBuild0   = 4;     // warps 4-7
 constexpr int kWsIssuer   = 8;
-constexpr int kWsHelper   = 9;
+constexpr int kWsHelper0  = 9;     // warps 9 .. 9 + H - 1
 constexpr int kWsBuilders = 128;
+constexpr int kWsMaxHelpers = 4;
 
 struct WsBars {
-    uint64_t ub_full[2], ub_empty[2];   // helper -> everyone (1 arrival) ; everyone -> helper (288 arrivals)
+    uint64_t ub_full[2 * kWsMaxHelpers], ub_empty[2 * kWsMaxHelpers];   // helper -> everyone (1 arrival) ; everyone -> helper (288 arrivals)
     uint64_t op_full;                   // builders -> issuer (128 arrivals): operand tiles of the next stage are in smem
     uint64_t mma_done[2];               // tcgen05.commit: accumulator g & 1 complete, operand tiles free again
     uint64_t acc_empty[2];              // drain warps -> issuer (128 arrivals): accumulator g & 1 has been read out
@@ -89,13 +90,13 @@ __device__ __forceinline__ void st_split8_f16_rowpair(unsigned char* hi, unsigne
 
 // Helper warp: ticket -> prologue -> per-user tables of one buffer.  lanes = path columns, then lanes = table entries.
 // Row np of every table is zero-filled: the operand builders read it (index min(p, np)) for the padding slots.
-__device__ __noinline__ void ws_helper_prepare(const DevDesc& d, const TcCfg& cfg, int ksplit, unsigned int n_items,
+__device__ __noinline__ void ws_helper_prepare(const DevDesc& d, const TcCfg& cfg, int ksplit, unsigned int n_items, unsigned int n_draw_last,
                                                unsigned int* ticket, TcUserBuf& ub, unsigned char* tab, int lane)
 {
     unsigned int t = 0;
     if (lane == 0) {
         t = atomicAdd(ticket, 1u);
-        if (t == n_items + gridDim.x - 1u) atomicExch(ticket, 0u);      // every CTA draws exactly one ticket >= n_items: this is the last draw
+        if (t == n_draw_last) atomicExch(ticket, 0u);      // every helper warp of every CTA draws exactly one ticket >= n_items: this is the last draw
         ub.item = t;
     }
     t = __shfl_sync(0xffffffffu, t, 0);
@@ -189,12 +190,33 @@ __device__ __forceinline__ void ws_drain(uint32_t tmem_base, int acc_col, float*
     }
 }
 
-__global__ void __launch_bounds__(kWsThreads, 2)
+// Consumers (drain, builders, issuer) walk the users in the order it = 0, 1, 2, ...: user `it` is prepared by helper it % H into
+// buffer it % (2H) (every helper owns two buffers).  A helper that draws a ticket >= n_items publishes it as a sentinel and stops;
+// its slots are skipped from then on, and the walk ends when every helper of the CTA has stopped.
+template <int H>
+__device__ __forceinline__ bool ws_next_user(WsBars& bars, const unsigned char* bufs, int buf_stride, unsigned n_items,
+                                             unsigned& it, unsigned& done, int& b)
+{
+    constexpr unsigned R = 2 * H, kAll = (1u << H) - 1u;
+    for (;;) {
+        if (done == kAll) return false;
+        const unsigned h = it % H;
+        if (!((done >> h) & 1u)) {
+            b = (int)(it % R);
+            mbar_wait(&bars.ub_full[b], (it / R) & 1u);
+            if (reinterpret_cast<const TcUserBuf*>(bufs + (size_t)b * buf_stride)->item < n_items) return true;
+            done |= 1u << h;
+        }
+        ++it;
+    }
+}
+
+template <int H>        // helper warps per CTA: 1 (two CTAs per SM, large per-user outputs) or 4 (one CTA per SM, helper-bound shapes)
+__global__ void __launch_bounds__((9 + H) * 32, H == 1 ? 2 : 1)
 fd_ws_kernel(const __grid_constant__ DevDesc d, const __grid_constant__ TcCfg cfg, const int ksplit,
              const unsigned int n_items, unsigned int* ticket, const int pdl_wait)
 {
     extern __shared__ unsigned char smem_raw[];
-    __shared__ TcUserBuf ub[2];
     __shared__ WsBars bars;
     if (pdl_wait) asm volatile("griddepcontrol.wait;" ::: "memory");     // plain stream order unless the caller declared independence
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");      // the next launch may take SMs as our CTAs retire
@@ -209,15 +231,17 @@ fd_ws_kernel(const __grid_constant__ DevDesc d, const __grid_constant__ TcCfg cf
     unsigned char* sAlo = sAhi + mtile * 128;
     unsigned char* sBhi = sm + cfg.off_B;                    // per sub-tile: [128 rows][128 B] hi, then lo
     unsigned char* sBlo = sBhi + kTcN * 128;
-    unsigned char* tab0 = sm + cfg.off_tab;
+    unsigned char* bufs = sm + cfg.off_tab;                  // 2H buffers of cfg.tab_bytes: [TcUserBuf][tables]
+    constexpr int kUb = (int)((sizeof(TcUserBuf) + 15) & ~size_t(15));
+    auto user_buf = [&](int b) -> TcUserBuf& { return *reinterpret_cast<TcUserBuf*>(bufs + (size_t)b * cfg.tab_bytes); };
+    auto user_tab = [&](int b) -> unsigned char* { return bufs + (size_t)b * cfg.tab_bytes + kUb; };
 
     if (warp == 3) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(&tmem_base_s)), "r"(2 * 128));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
     }
     if (tid == 64) {
-        mbar_init(&bars.ub_full[0], 1);   mbar_init(&bars.ub_full[1], 1);
-        mbar_init(&bars.ub_empty[0], kWsThreads - 32); mbar_init(&bars.ub_empty[1], kWsThreads - 32);
+        for (int b = 0; b < 2 * H; ++b) { mbar_init(&bars.ub_full[b], 1); mbar_init(&bars.ub_empty[b], kWsConsumers); }
         mbar_init(&bars.op_full, kWsBuilders);
         mbar_init(&bars.mma_done[0], 1);  mbar_init(&bars.mma_done[1], 1);
         mbar_init(&bars.acc_empty[0], 128); mbar_init(&bars.acc_empty[1], 128);
@@ -234,14 +258,16 @@ fd_ws_kernel(const __grid_constant__ DevDesc d, const __grid_constant__ TcCfg cf
     const long long pitch = 2LL * K;                          // floats per output row
     const int acc_stride = 128 / nsub;                        // TMEM columns per accumulator; 2 * nsub accumulators in 256 columns
 
-    if (warp == kWsHelper) {
-        // ------------------------------------------------------------------------------------------ helper
-        for (unsigned it = 0;; ++it) {
-            const int b = it & 1;
-            mbar_wait(&bars.ub_empty[b], ((it >> 1) & 1u) ^ 1u);        // users it-2's readers are done with buffer b
-            ws_helper_prepare(d, cfg, ksplit, n_items, ticket, ub[b], tab0 + b * cfg.tab_bytes, lane);
+    if (warp >= kWsHelper0) {
+        // ------------------------------------------------------------------------------------------ helpers
+        const int h = warp - kWsHelper0;
+        const unsigned int n_draw_last = n_items + gridDim.x * (unsigned)H - 1u;
+        for (unsigned k = 0;; ++k) {
+            const int b = h + (int)(k & 1u) * H;                          // this helper's two buffers, alternately
+            mbar_wait(&bars.ub_empty[b], ((k >> 1) & 1u) ^ 1u);          // the readers of this buffer's previous user are done
+            ws_helper_prepare(d, cfg, ksplit, n_items, n_draw_last, ticket, user_buf(b), user_tab(b), lane);
             __syncwarp();
-            const unsigned int item = ub[b].item;
+            const unsigned int item = user_buf(b).item;
             if (lane == 0) mbar_arrive(&bars.ub_full[b]);
             if (item >= n_items) break;
         }
@@ -258,15 +284,15 @@ fd_ws_kernel(const __grid_constant__ DevDesc d, const __grid_constant__ TcCfg cf
         const int b_off0 = (b_row0 >> 3) * 1024 + (b_row0 & 7) * 128;
         const int b_sw0 = b_row0 & 7, b_sw1 = (b_row0 + 1) & 7;
         unsigned g = 0;                                       // global stage counter (identical in every role)
-        for (unsigned it = 0;; ++it) {
-            const int cur = it & 1;
-            mbar_wait(&bars.ub_full[cur], (it >> 1) & 1u);
-            const unsigned int item = ub[cur].item;
-            if (item >= n_items) break;
+        unsigned it = 0, done = 0;
+        int cur = 0;
+        for (; ws_next_user<H>(bars, bufs, cfg.tab_bytes, n_items, it, done, cur); ++it) {
+            const TcUserBuf& ub = user_buf(cur);
+            const unsigned int item = ub.item;
             const int ks = (int)(item % (unsigned)ksplit);
-            const int np = ub[cur].sh.np;
+            const int np = ub.sh.np;
             if (np > 0) {
-                const unsigned char* tab = tab0 + cur * cfg.tab_bytes;
+                const unsigned char* tab = user_tab(cur);
                 const float2* tY   = reinterpret_cast<const float2*>(tab + cfg.off_tY);
                 const float2* tQ   = reinterpret_cast<const float2*>(tab + cfg.off_tQ);
                 const float2* wB   = reinterpret_cast<const float2*>(tab + cfg.off_wB);
@@ -355,13 +381,13 @@ fd_ws_kernel(const __grid_constant__ DevDesc d, const __grid_constant__ TcCfg cf
         const uint64_t dAhi = umma_desc_kmajor_sw128(smem_u32(sAhi)), dAlo = umma_desc_kmajor_sw128(smem_u32(sAlo));
         const uint64_t dBhi = umma_desc_kmajor_sw128(smem_u32(sBhi)), dBlo = umma_desc_kmajor_sw128(smem_u32(sBlo));
         unsigned g = 0;
-        for (unsigned it = 0;; ++it) {
-            const int cur = it & 1;
-            mbar_wait(&bars.ub_full[cur], (it >> 1) & 1u);
-            const unsigned int item = ub[cur].item;
-            if (item >= n_items) break;
+        unsigned it = 0, done = 0;
+        int cur = 0;
+        for (; ws_next_user<H>(bars, bufs, cfg.tab_bytes, n_items, it, done, cur); ++it) {
+            const TcUserBuf& ub = user_buf(cur);
+            const unsigned int item = ub.item;
             const int ks = (int)(item % (unsigned)ksplit);
-            const int np = ub[cur].sh.np;
+            const int np = ub.sh.np;
             if (np > 0) {
                 const int ksteps = (np + 7) >> 3;                     // 16 fp16 (8 path slots) per MMA
                 for (int ct = ks; ct < n_ct; ct += ksplit) {
@@ -404,15 +430,15 @@ fd_ws_kernel(const __grid_constant__ DevDesc d, const __grid_constant__ TcCfg cf
         // ------------------------------------------------------------------------------------------ drain warps 0-3
         const int q = warp;                                   // TMEM lane quarter = 32 floats (128 bytes) of every row segment
         unsigned g = 0;
-        for (unsigned it = 0;; ++it) {
-            const int cur = it & 1;
-            mbar_wait(&bars.ub_full[cur], (it >> 1) & 1u);
-            const unsigned int item = ub[cur].item;
-            if (item >= n_items) break;
+        unsigned it = 0, done = 0;
+        int cur = 0;
+        for (; ws_next_user<H>(bars, bufs, cfg.tab_bytes, n_items, it, done, cur); ++it) {
+            const TcUserBuf& ub = user_buf(cur);
+            const unsigned int item = ub.item;
             const long long user = item / (unsigned)ksplit;
             const int ks = (int)(item % (unsigned)ksplit);
-            const int np = ub[cur].sh.np;
-            const float scale = ub[cur].scale;
+            const int np = ub.sh.np;
+            const float scale = ub.scale;
             float* out_u = reinterpret_cast<float*>(d.out + user * (long long)M * K);
             if (np == 0) {
                 // users without contributing paths: zeros (channel.py:257,:269-271), one 512-byte row segment per warp store

@@ -108,3 +108,22 @@ def test_ws_many_users_per_cta_chunked_independent_launches_and_ticket_reuse():
         err = assert_channels_close(H, o["H"], what=f"ws chunked rep {rep}")
         assert err < 2e-6
     torch.cuda.synchronize()
+
+
+@pytest.mark.parametrize("helpers", ["1", "4"])
+def test_ws_helper_counts_agree(helpers, monkeypatch):
+    """The persistent kernel runs with one helper warp (two CTAs per SM) or four (one CTA per SM, eight user buffers);
+    DMK_WS_HELPERS pins the choice.  Both must meet the bar on a shape that streams many users through every CTA."""
+    monkeypatch.setenv("DMK_WS_HELPERS", helpers)
+    d, p = _case(1500, (8, 8), (1, 1), 1024, np.arange(192), 43, zero_frac=0.15)
+    import deepmimo_b200 as dmb
+    from deepmimo_b200 import _lib
+    from oracle import channel_oracle as orc
+    monkeypatch.setenv("DMK_FD_KERNEL", "tc")
+    H = make_dataset(dmb, d).compute_channels(dmb.ChannelGenParameters(p), warn=False)
+    assert f"{helpers} helper" in _lib.last_kernel(), _lib.last_kernel()
+    o = orc.compute_channels(d, bs_shape=p["bs_antenna"]["shape"], ue_shape=p["ue_antenna"]["shape"],
+                             bs_rotation=p["bs_antenna"]["rotation"], num_paths=p["num_paths"],
+                             subcarriers=p["ofdm"]["subcarriers"], selected_subcarriers=p["ofdm"]["selected_subcarriers"],
+                             bandwidth=p["ofdm"]["bandwidth"])
+    assert assert_channels_close(H, o["H"], what=_lib.last_kernel()) < 2e-6
