@@ -421,7 +421,8 @@ def gpu_main(args):
                 traffic = rec["dram_bytes"] * (res["plan"].n_users / rec["users"]) / n_launch
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms_step, "ms_step_min_median_max": [min(res["ms"]), statistics.median(res["ms"]), max(res["ms"])],
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"{args.workload}: {res['scenario'].notes}", "users_per_gpu": res["plan"].n_users,
                        "out_shape_per_gpu": list(res["plan"].out_shape()), "mean_active_paths_per_user": res["pbar"],
