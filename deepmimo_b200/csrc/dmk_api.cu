@@ -194,7 +194,7 @@ int dmk_channels_fd(const dmk_desc* desc, const float* power_dbw, const float* p
         cfg.mul_bs0 = d.bs0 > 1 ? (unsigned)((0x100000000ULL + d.bs0 - 1) / d.bs0) : 0u;
     }
     const bool div_ok = (unsigned long long)d.M * (unsigned long long)(d.Mt > d.bs0 ? d.Mt : d.bs0) < 0xffffffffULL;
-    // Kernel choice: tensor-core (3xTF32 tcgen05) > packed-FP32 CUDA-core > generic tile kernel.
+    // Kernel choice: tensor-core (tcgen05, FP16 hi/lo split) > packed-FP32 CUDA-core > generic tile kernel.
     // DMK_FD_KERNEL=tc|ffma|tile overrides it (parity tests and A/B timing use this).
     const char* force = getenv("DMK_FD_KERNEL");
     const bool want_tile = force && !strcmp(force, "tile");

@@ -1,4 +1,6 @@
-// dmk_fd_tc.cuh -- FD channel kernel on the 5th-generation tensor cores (tcgen05, kind::tf32, TMEM).
+// dmk_fd_tc.cuh -- FD channel contraction on the 5th-generation tensor cores (tcgen05, kind::f16, TMEM): the arithmetic, the
+// operand layouts and the one-CTA-per-user kernel.  The production kernel (persistent, warp-specialised) is in dmk_fd_ws.cuh and
+// reuses everything here except the kernel body.
 //
 // Why: with P ~ 12 contributing paths per user the FP32 FMA pipe, not HBM, bounds the CUDA-core kernel
 // (profiles/r01_ncu_fd_fast_kernel_*.txt: top stall math_pipe_throttle, DRAM = algorithmic bytes).  The
@@ -11,22 +13,23 @@
 // register i of a tcgen05.ld holds, across the 32 lanes of a warp, 32 consecutive floats of output row m_i, so every
 // warp-wide 4-byte store is one full 128-byte line -- no shared-memory staging -- and the MMA N dimension adapts to
 // small arrays (M = 64 -> N = 64, M = 8 -> N = 16) without idle tensor rows.
-// TF32 keeps 11 significant bits, so every operand is split x = hi + lo (hi = tf32(x), lo = tf32(x - hi)) and
-// D = A_hi B_hi + A_hi B_lo + A_lo B_hi accumulates in FP32 in tensor memory: relative error ~2^-21 per term
-// (measured per-user relative Frobenius error vs the reference: see tests), far inside the 1e-5 budget.
+// Precision: FP16 operands keep 11 significant bits, so every operand is split x = hi + lo (hi = fp16(x), lo = fp16(x - hi)) and
+// D = B_hi A_hi + B_lo A_hi + B_hi A_lo accumulates in FP32 in tensor memory.  Operands are scaled into [-1, 1] (unit phasors;
+// path gains divided by the user's largest |c_p| component, undone in the epilogue), so the absolute operand error is
+// <= 2^-23 relative to the user's strongest path -- measured per-user relative Frobenius error <= 4.3e-7 (tests), far inside
+// the 1e-5 budget.  All 32 path slots (re, im) of a row are one 128-byte K-major SWIZZLE_128B row; one MMA covers 8 slots (K = 16).
+// (A first version used 3xTF32, K = 8 per MMA: same accuracy, twice the MMAs and operand bytes.)
 //
-// Structure (one CTA = one user or a slice of its column tiles, 256 threads, 2 CTAs per SM):
-//   warp 0: per-path prologue (float64) -> compacted path records;  all threads: separable phasor tables
-//   per 128-float (64-subcarrier) column tile, per row tile of 128 (or 64) rows, per chunk of 16 paths:
-//     all threads write A_hi/A_lo (rows x 32 tf32) and B_hi/B_lo (128 x 32 tf32) straight into shared memory
-//     in the K-major SWIZZLE_128B UMMA layout (one complex multiply of table entries + split per entry);
-//     fence.proxy.async; barrier; one thread issues 3 x ksteps tcgen05.mma (M x 128 x 8) and commits to an
-//     mbarrier; everyone waits on it.
-//   epilogue: every warp pulls its TMEM lane quarter with tcgen05.ld 32x32b.xN and writes each register as one
+// fd_tc_kernel (one CTA = one user or a slice of its column stages, 288 threads, 2 CTAs per SM):
+//   warps 0-2: per-path float64 prologue chains -> warp 0 combines and compacts;  all threads: separable phasor tables
+//   per stage (64 or 2 x 64 subcarriers) and row tile of mtile rows:
+//     workers write A_hi/A_lo (mtile x 64 halves) and B_hi/B_lo (128 x 64 halves) straight into shared memory in the
+//     K-major SWIZZLE_128B UMMA layout (one complex multiply of table entries + split per entry);
+//     fence.proxy.async; barrier; warp 8 issues 3 x ksteps tcgen05.mma (128 x mtile x 16) and commits to an mbarrier.
+//   epilogue: every worker warp pulls its TMEM lane quarter with tcgen05.ld 32x32b.xN and writes each register as one
 //   128-byte row segment (streaming stores).  The accumulator is double-buffered in TMEM (2 x 128 columns): the
-//   epilogue of tile t-1 runs while the tensor core works on tile t.
-// The tensor pipe needs ~25-50 % of the HBM time of a tile, the operand generation a few hundred issue
-// cycles, so the kernel is bound by the output write; the second resident CTA fills the remaining bubbles.
+//   epilogue of stage s-1 runs while the tensor core works on stage s.
+// Used for shapes whose double-buffered tables do not fit next to the operand tiles, and as DMK_FD_KERNEL=tc1.
 #pragma once
 #include <cuda_fp16.h>
 #include "dmk_fd.cuh"
@@ -62,30 +65,6 @@ __device__ __forceinline__ uint64_t umma_desc_kmajor_sw128(uint32_t saddr)
     return d;
 }
 
-__device__ __forceinline__ uint32_t tf32_rna(float x)
-{
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-    return r;
-}
-
-// byte offset of element pair (row, path slot j: k = 2j, 2j+1) in a K-major SWIZZLE_128B tile of 32 tf32 per row
-__device__ __forceinline__ int sw128_pair_offset(int row, int j)
-{
-    return (row >> 3) * 1024 + (row & 7) * 128 + ((((j >> 1) ^ (row & 7)) & 7) << 4) + (j & 1) * 8;
-}
-
-// x = hi + lo with hi = tf32(x) (round to nearest, ties away: integer add on the sign-magnitude pattern) and
-// lo = x - hi exact in FP32; the tensor core reads the top 19 bits of lo (|lo| <= 2^-11 |x| -> error <= 2^-22 |x|).
-__device__ __forceinline__ void st_split_pair(unsigned char* hi, unsigned char* lo, int off, float x, float y)
-{
-    const uint32_t xh = (__float_as_uint(x) + 0x1000u) & 0xffffe000u;
-    const uint32_t yh = (__float_as_uint(y) + 0x1000u) & 0xffffe000u;
-    const float xl = x - __uint_as_float(xh), yl = y - __uint_as_float(yh);
-    *reinterpret_cast<uint2*>(hi + off) = make_uint2(xh, yh);
-    *reinterpret_cast<float2*>(lo + off) = make_float2(xl, yl);
-}
-
 // x = hi + lo in FP16: hi = fp16(x), lo = fp16(x - hi).  Operands are scaled to |x| <= 1 (unit phasors; path gains divided
 // by the user's largest |c_p|), so the absolute error per operand is <= max(2^-23 |x|, 2^-25) -- FP32-class relative to
 // the user's strongest path, which is what the per-user Frobenius criterion measures.  Four path slots (re,im x 4 =
@@ -103,15 +82,6 @@ __device__ __forceinline__ void st_split8_f16(unsigned char* hi, unsigned char* 
     }
     *reinterpret_cast<uint4*>(hi + off) = make_uint4(h[0], h[1], h[2], h[3]);
     *reinterpret_cast<uint4*>(lo + off) = make_uint4(l[0], l[1], l[2], l[3]);
-}
-
-__device__ __forceinline__ void st_split_quad(unsigned char* hi, unsigned char* lo, int off, float x0, float y0, float x1, float y1)
-{
-    const uint32_t a = (__float_as_uint(x0) + 0x1000u) & 0xffffe000u, b = (__float_as_uint(y0) + 0x1000u) & 0xffffe000u;
-    const uint32_t c = (__float_as_uint(x1) + 0x1000u) & 0xffffe000u, e = (__float_as_uint(y1) + 0x1000u) & 0xffffe000u;
-    *reinterpret_cast<uint4*>(hi + off) = make_uint4(a, b, c, e);
-    *reinterpret_cast<float4*>(lo + off) = make_float4(x0 - __uint_as_float(a), y0 - __uint_as_float(b),
-                                                        x1 - __uint_as_float(c), y1 - __uint_as_float(e));
 }
 
 __device__ __forceinline__ void mbar_wait_parity(uint32_t bar, uint32_t parity)
