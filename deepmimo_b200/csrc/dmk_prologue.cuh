@@ -41,7 +41,7 @@ __device__ __forceinline__ void rotate_side(float el_deg, float az_deg,
     double st = (double)st32, ct = (double)ct32;
     double dphi = __dsub_rn((double)ph32, rz);              // :294 float32 - float64 -> float64 (R3)
     double sd, cd;
-    sincos(dphi, &sd, &cd);
+    dsincos_bf(dphi, sd, cd);
     // :305-306  arccos(cy*cx*ct + st*(sy*cx*cd - sx*sd)), same association, no contraction
     double x = __dadd_rn(__dmul_rn(__dmul_rn(cy, cx), ct),
                          __dmul_rn(st, __dsub_rn(__dmul_rn(__dmul_rn(sy, cx), cd), __dmul_rn(sx, sd))));
@@ -99,8 +99,8 @@ __device__ __forceinline__ void prologue_side(const DevDesc& d, long long user, 
     if (side == 1 && d.ue_rot) {                            // per-user UE rotation (dataset.py:328-338)
         const double k = kPi / 180.0;                       // np.deg2rad float64: x * (pi/180)
         const double* r = d.ue_rot + user * 3;
-        sincos(__dmul_rn(r[0], k), &sx, &cx);
-        sincos(__dmul_rn(r[1], k), &sy, &cy);
+        dsincos_bf(__dmul_rn(r[0], k), sx, cx);
+        dsincos_bf(__dmul_rn(r[1], k), sy, cy);
         rz = __dmul_rn(r[2], k);
     }
     rotate_side<kNeedAngles>(d.el[side][off], d.az[side][off], sx, cx, sy, cy, rz, o.th, o.ph, o.ss, o.cc);
