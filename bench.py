@@ -115,7 +115,7 @@ class ClockSampler(threading.Thread):
     REASONS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
                0x80: "hw_power_brake_slowdown", 0x2: "applications_clocks_setting", 0x10: "sync_boost"}
 
-    def __init__(self, device_index: int, interval=0.01):
+    def __init__(self, device_index: int, interval=0.02):
         super().__init__(daemon=True)
         self.interval, self.samples, self.reasons, self.power = interval, [], set(), []
         self.stop_flag = threading.Event()
@@ -131,6 +131,12 @@ class ClockSampler(threading.Thread):
             except Exception:  # noqa: BLE001
                 self.h = pynvml.nvmlDeviceGetHandleByIndex(device_index)
             self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            # prime every query once here, outside the timed region: the first call of an NVML query can take milliseconds
+            # and was seen to stretch one timed step from 2.9 to 6.2 ms
+            pynvml.nvmlDeviceGetClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            pynvml.nvmlDeviceGetPowerUsage(self.h)
+            (pynvml.nvmlDeviceGetCurrentClocksEventReasons if hasattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons")
+             else pynvml.nvmlDeviceGetCurrentClocksThrottleReasons)(self.h)
             self.ok = True
         except Exception as e:  # noqa: BLE001
             log(f"[bench] NVML unavailable ({e}); clocks not sampled")
