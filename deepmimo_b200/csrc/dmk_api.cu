@@ -91,7 +91,7 @@ int build_desc(const dmk_desc* h, bool freq_domain, dmk::DevDesc& d)
     for (int b = 0; b < 31; ++b) if ((1 << b) == d.N) d.lpf_log2n = b;
     d.lpf_batch = 1;
     if (d.rx_filter) {
-        long long bmax = (64LL * 1024) / (8LL * d.N);        // x[B][N] float2 within 64 KB
+        long long bmax = (32LL * 1024) / (8LL * d.N);        // x[B][N] float2 within 32 KB
         if (bmax < 1) bmax = 1;
         if (bmax > 16) bmax = 16;
         d.lpf_batch = (int)bmax;
@@ -392,6 +392,10 @@ int dmk_channels_fd(const dmk_desc* desc, const float* power_dbw, const float* p
         smem += (size_t)(1 + d.lpf_batch) * d.N * sizeof(float2);      // twiddle table + FFT batch (dmk_fd.cuh: lpf_w_tile)
         if (smem > 200 * 1024)
             return fail(DMK_ERR_UNSUPPORTED, "ofdm.rx_filter=1 supports ofdm.subcarriers <= 9728 (got %d)", d.N);
+        // what is left of 200 KB caches the transformed paths of a user (np * K complex values) across its column tiles
+        d.lpf_cache = (int)((200 * 1024 - smem) / sizeof(float2));
+        if ((long long)d.lpf_cache > (long long)kMaxPaths * d.K) d.lpf_cache = kMaxPaths * d.K;
+        smem += (size_t)d.lpf_cache * sizeof(float2);
     }
     static size_t attr_set = 0;
     if (smem > attr_set) {

@@ -20,6 +20,7 @@ struct DevDesc {
     int has_time_axis;            // 1 when n_times > 0
     int rx_filter;                // 1: receive low-pass filter (channel.py:166-168, :193-194), FD only
     int lpf_batch, lpf_log2n;     // paths per FFT batch; log2(N) when N is a power of two (FFT route), else -1 (direct DFT)
+    int lpf_cache;                // complex values of the per-user cache of transformed paths (0 = none)
     int fov_any, fov_side[2];     // [0] = BS (AoD), [1] = UE (AoA)
     int pat[2];
     int subc_start, subc_step;    // affine selection if subc_step != 0 or K == 1

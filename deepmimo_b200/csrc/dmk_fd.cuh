@@ -99,6 +99,18 @@ __device__ __noinline__ void fd_cta_prologue_outlined(const DevDesc& d, long lon
 __device__ __forceinline__ void lpf_w_tile(const DevDesc& d, const FdShared& sh, int np, int col0, int ncols, float2* sW,
                                            float2* lpf_mem, bool first_tile)
 {
+    // Users whose transformed paths fit (np * K <= d.lpf_cache complex values, no time axis) are transformed once, on the first
+    // tile, into Wc[p][K]; later tiles only copy their 128 columns.  Users with more paths redo the transforms per tile.
+    const bool cached = !d.has_time_axis && (long long)np * d.K <= (long long)d.lpf_cache;
+    float2* Wc = lpf_mem + (size_t)(1 + d.lpf_batch) * d.N;
+    if (cached && !first_tile) {
+        for (int e = threadIdx.x; e < np * kTK; e += kFdThreads) {
+            const int p = e / kTK, cidx = e % kTK;
+            const int col = col0 + cidx;
+            sW[p * kTK + cidx] = col < ncols ? Wc[p * d.K + col] : make_float2(0.f, 0.f);
+        }
+        return;
+    }
     __shared__ float  lpf_a[kMaxPaths];      // (-1)^k sin(pi r) / pi,  tau = k + r
     __shared__ float  lpf_sk[kMaxPaths];     // sinc(r): the sample d == k
     __shared__ int    lpf_k[kMaxPaths];
@@ -157,6 +169,31 @@ __device__ __forceinline__ void lpf_w_tile(const DevDesc& d, const FdShared& sh,
                 __syncthreads();
             }
         }
+        if (cached) {
+            // ---- every selected column of the batch's paths goes to the per-user cache
+            const int K = d.K;
+            for (int e = tid; e < nb * K; e += kFdThreads) {
+                const int b = e / K, ki = e - b * K;
+                int k = subcarrier_at(d, ki) % N;
+                if (k < 0) k += N;
+                float2 w;
+                if (lg >= 0) w = x[b * N + k];
+                else {
+                    const float2* xb = x + b * N;
+                    float wr = 0.f, wi = 0.f;
+                    int idx = 0;
+                    for (int dd = 0; dd < N; ++dd) {
+                        const float sv = xb[dd].x;
+                        const float2 t = tw[idx];
+                        wr = fmaf(sv, t.x, wr); wi = fmaf(sv, t.y, wi);
+                        idx += k; if (idx >= N) idx -= N;
+                    }
+                    w = make_float2(wr, wi);
+                }
+                Wc[(p0 + b) * K + ki] = w;
+            }
+            continue;
+        }
         // ---- the tile's columns
         for (int e = tid; e < nb * kTK; e += kFdThreads) {
             const int b = e / kTK, cidx = e % kTK;
@@ -184,6 +221,14 @@ __device__ __forceinline__ void lpf_w_tile(const DevDesc& d, const FdShared& sh,
                 if (d.has_time_axis) w = cmul(w, phasor_cycles(sh.fd[p] * d.times[it]));
             }
             sW[p * kTK + cidx] = w;
+        }
+    }
+    if (cached) {
+        __syncthreads();
+        for (int e = tid; e < np * kTK; e += kFdThreads) {
+            const int p = e / kTK, cidx = e % kTK;
+            const int col = col0 + cidx;
+            sW[p * kTK + cidx] = col < ncols ? Wc[p * d.K + col] : make_float2(0.f, 0.f);
         }
     }
 }
