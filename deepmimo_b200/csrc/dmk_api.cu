@@ -233,7 +233,8 @@ int dmk_channels_fd(const dmk_desc* desc, const float* power_dbw, const float* p
     const bool use_tc = affine && !d.has_time_axis && div_ok && (d.K % (kTcN / 2) == 0) && d.K <= 4096 && tc_smem <= 112 * 1024 &&
                         !want_tile && !want_ffma && ((d.M >= 64 && !d.fov_any) || want_tc);   // FoV leaves few paths, tiny arrays little output: FP32 kernel wins
     const bool use_fast = !use_tc && affine && !d.has_time_axis && div_ok && fast_smem <= 110 * 1024 && !want_tile;
-    const int tile_w = use_tc ? (kTcN / 2) * tcfg.nsub : (use_fast ? kTKW : kTK);
+    const int tile_w_tc1 = (kTcN / 2) * tcfg.nsub;
+    const int tile_w = use_tc ? tile_w_tc1 : (use_fast ? kTKW : kTK);
     const int n_ct = (ncols + tile_w - 1) / tile_w;
     // Few users: split each user's column tiles over several CTAs so the grid covers >= 4 waves.
     const long long want = 4LL * 2 * device_sm_count();
@@ -293,7 +294,20 @@ int dmk_channels_fd(const dmk_desc* desc, const float* power_dbw, const float* p
     TcCfg pcfg = tcfg;
     size_t ptc_smem = 0;
     int n_helpers = 1;
-    {
+    // Sized up to three times: the preferred tile (two 64-subcarrier sub-tiles for small arrays), then one sub-tile (32 KB less B
+    // operand), then 64-row tiles (16 KB less A operand) for shapes whose tables are large (e.g. a 64-element panel row), before the
+    // shape goes to the one-CTA-per-user kernel.
+    for (int attempt = 0; attempt < 3; ++attempt) {
+        if (attempt == 1) {
+            if (pcfg.nsub == 1) continue;
+            pcfg.nsub = 1;
+        }
+        if (attempt == 2) {                                      // last resort: 64-row tiles (16 KB less A operand)
+            if (pcfg.mtile <= 64) break;
+            pcfg.mtile = 64; pcfg.nsub = 1;
+        }
+        n_helpers = 1;
+
         const int pc = (d.P > 0 ? d.P : 1) + 1;                  // + the zero row the builders read for padding slots
         size_t off = 0;
         auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 15) & ~size_t(15); return (int)o; };
@@ -319,6 +333,7 @@ int dmk_channels_fd(const dmk_desc* desc, const float* power_dbw, const float* p
         const char* hf = getenv("DMK_WS_HELPERS");
         if ((per_user_bytes <= 384 * 1024 || (hf && atoi(hf) == 4)) && smem4 <= 220 * 1024 && !(hf && atoi(hf) == 1)) n_helpers = 4;
         ptc_smem = 1024 + off + 2 * n_helpers * buf_bytes;
+        if (n_helpers == 4 || ptc_smem <= 113200) break;
     }
     const bool use_tcp = use_tc && !want_tc1 && (n_helpers == 4 || ptc_smem <= 113200) && grid < 0xffffff00LL;   // H = 1: + ~2.6 KB static + 1 KB reserve, two CTAs per SM
     if (use_tcp) {
