@@ -111,31 +111,7 @@ bf_kernel(const __grid_constant__ DevDesc d, const __grid_constant__ BfCfg c)
             for (int i = 0; i < 8; ++i)
                 #pragma unroll
                 for (int j = 0; j < 4; ++j) acc[i][j] = make_float2(0.f, 0.f);
-            const float4* wrow = reinterpret_cast<const float4*>(sW) + lane;          // columns 2*lane, 2*lane+1 (and +64)
-            const float4* arow = reinterpret_cast<const float4*>(sA) + warp * 4;      // rows warp*8 .. +7
-            #pragma unroll 1
-            for (int p = 0; p < np; ++p) {
-                const float4 w01 = wrow[p * (kTK / 2)];
-                const float4 w23 = wrow[p * (kTK / 2) + 32];
-                const float2 w[4] = {make_float2(w01.x, w01.y), make_float2(w01.z, w01.w),
-                                     make_float2(w23.x, w23.y), make_float2(w23.z, w23.w)};
-                float2 a[8];
-                #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const float4 t = arow[p * (kTM / 2) + i];
-                    a[2 * i] = make_float2(t.x, t.y);
-                    a[2 * i + 1] = make_float2(t.z, t.w);
-                }
-                #pragma unroll
-                for (int i = 0; i < 8; ++i)
-                    #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        acc[i][j].x = fmaf(a[i].x, w[j].x, acc[i][j].x);
-                        acc[i][j].x = fmaf(-a[i].y, w[j].y, acc[i][j].x);
-                        acc[i][j].y = fmaf(a[i].x, w[j].y, acc[i][j].y);
-                        acc[i][j].y = fmaf(a[i].y, w[j].x, acc[i][j].y);
-                    }
-            }
+            tile_rank_update(sW, sA, np, lane, warp, acc);
             // ---- |Y| summed over this tile's columns; each warp owns its 8 rows, so no atomics
             #pragma unroll
             for (int i = 0; i < 8; ++i) {

@@ -84,6 +84,35 @@ __device__ __noinline__ void fd_cta_prologue_outlined(const DevDesc& d, long lon
     fd_cta_prologue(d, user, sh, sc, write_masks);
 }
 
+// Rank-np update of a thread's 8 x 4 register tile from the W tile [np][kTK] and the A tile [np][kTM] in shared memory (generic
+// tile kernels): four scalar FFMA per complex MAC.  The packed form (two FFMA2 with (re, re) / (-im, im) operands built in registers
+// from this A layout) was measured 20 % slower here (1.71 -> 2.08 ms on cfg2 x 1024 users): the operand shuffles cost more than the
+// FFMAs they save; fd_fast_kernel pays for a pre-duplicated A strip in shared memory instead.
+__device__ __forceinline__ void tile_rank_update(const float2* sW, const float2* sA, int np, int lane, int warp, float2 (&acc)[8][4])
+{
+    const float4* wrow = reinterpret_cast<const float4*>(sW) + lane;          // columns 2*lane, 2*lane+1 (and +64)
+    const float4* arow = reinterpret_cast<const float4*>(sA) + warp * 4;      // rows warp*8 .. +7
+    #pragma unroll 1
+    for (int p = 0; p < np; ++p) {
+        const float4 w01 = wrow[p * (kTK / 2)];
+        const float4 w23 = wrow[p * (kTK / 2) + 32];
+        const float2 w[4] = {make_float2(w01.x, w01.y), make_float2(w01.z, w01.w), make_float2(w23.x, w23.y), make_float2(w23.z, w23.w)};
+        #pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float4 t = arow[p * (kTM / 2) + i];                          // rows 2i, 2i+1: (re, im, re, im)
+            const float2 a[2] = {make_float2(t.x, t.y), make_float2(t.z, t.w)};
+            #pragma unroll
+            for (int h = 0; h < 2; ++h)
+                #pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    float2& c = acc[2 * i + h][j];
+                    c.x = fmaf(a[h].x, w[j].x, c.x); c.x = fmaf(-a[h].y, w[j].y, c.x);
+                    c.y = fmaf(a[h].x, w[j].y, c.y); c.y = fmaf(a[h].y, w[j].x, c.y);
+                }
+        }
+    }
+}
+
 // -------------------------------------------------------------------------------------------------
 // Receive low-pass filter (ofdm.rx_filter = 1; channel.py:166-168, :193-194).  The per-path frequency response is no
 // longer a pure phasor but the N-point DFT of the sampled sinc,
@@ -302,31 +331,7 @@ fd_tile_kernel(const __grid_constant__ DevDesc d, const int ksplit)
                 #pragma unroll
                 for (int j = 0; j < 4; ++j) acc[i][j] = make_float2(0.f, 0.f);
 
-            const float4* wrow = reinterpret_cast<const float4*>(sW) + lane;          // columns 2*lane, 2*lane+1
-            const float4* arow = reinterpret_cast<const float4*>(sA) + warp * 4;      // rows warp*8 .. +7
-            #pragma unroll 1
-            for (int p = 0; p < np; ++p) {
-                const float4 w01 = wrow[p * (kTK / 2)];
-                const float4 w23 = wrow[p * (kTK / 2) + 32];
-                const float2 w[4] = {make_float2(w01.x, w01.y), make_float2(w01.z, w01.w),
-                                     make_float2(w23.x, w23.y), make_float2(w23.z, w23.w)};
-                float2 a[8];
-                #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const float4 t = arow[p * (kTM / 2) + i];
-                    a[2 * i] = make_float2(t.x, t.y);
-                    a[2 * i + 1] = make_float2(t.z, t.w);
-                }
-                #pragma unroll
-                for (int i = 0; i < 8; ++i)
-                    #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        acc[i][j].x = fmaf(a[i].x, w[j].x, acc[i][j].x);
-                        acc[i][j].x = fmaf(-a[i].y, w[j].y, acc[i][j].x);
-                        acc[i][j].y = fmaf(a[i].x, w[j].y, acc[i][j].y);
-                        acc[i][j].y = fmaf(a[i].y, w[j].x, acc[i][j].y);
-                    }
-            }
+            tile_rank_update(sW, sA, np, lane, warp, acc);
 
             // ---- store: each lane owns columns {2l, 2l+1} and {64+2l, 64+2l+1} of the tile
             #pragma unroll
