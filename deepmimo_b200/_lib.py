@@ -39,11 +39,22 @@ class DmkDesc(ctypes.Structure):
         ("n_times", ctypes.c_int32),
         ("times", ctypes.c_void_p),
         ("flags", ctypes.c_int32),
+        ("kernel_hint", ctypes.c_int32),
+        ("ws_helpers", ctypes.c_int32),
     ]
 
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 FLAG_INDEPENDENT_LAUNCH = 1
+KERNEL_HINTS = {"": 0, "auto": 0, "tile": 1, "ffma": 2, "tc": 3, "tc1": 4, "small": 5}      # enum dmk_kernel_hint
+
+
+def kernel_hint_from_env(var: str = "DMK_FD_KERNEL") -> int:
+    """Test / A-B knob: DMK_FD_KERNEL (or DMK_BF_KERNEL) = tile | ffma | tc | tc1 | small -> dmk_desc.kernel_hint."""
+    v = os.environ.get(var, "").strip().lower()
+    if v not in KERNEL_HINTS:
+        raise ValueError(f"{var}={v!r}: expected one of {sorted(k for k in KERNEL_HINTS if k)}")
+    return KERNEL_HINTS[v]
 SYMBOLS = ("dmk_channels_fd", "dmk_channels_td", "dmk_beam_amplitude_fd", "dmk_path_prologue", "dmk_np_sincosf",
            "dmk_last_error", "dmk_abi_version", "dmk_launch_count", "dmk_last_kernel")
 
@@ -90,6 +101,11 @@ def load() -> ctypes.CDLL:
                 if not os.path.exists(path):
                     raise DmkError(f"libdmk.so is missing and could not be built ({e}); "
                                    "deepmimo_b200 has no CPU fallback") from e
+                # an older library exists (e.g. a box without nvcc): say so instead of silently running stale kernels;
+                # an ABI mismatch still raises below
+                import warnings
+                warnings.warn(f"libdmk.so is older than its sources and the rebuild failed ({str(e)[:200]}); "
+                              "using the existing library", RuntimeWarning, stacklevel=2)
         lib = ctypes.CDLL(path)
         for s in SYMBOLS:
             if not hasattr(lib, s):

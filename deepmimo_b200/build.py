@@ -35,27 +35,51 @@ def nvcc_path() -> str:
     raise RuntimeError("nvcc not found: libdmk.so cannot be built (no CPU fallback exists)")
 
 
+STAMP = LIB + ".srchash"      # content hash of the sources the library was built from (mtimes do not survive a snapshot copy)
+
+
+def source_hash() -> str:
+    import hashlib
+    h = hashlib.sha256()
+    for p in [os.path.join(CSRC, s) for s in SOURCES + HEADERS] + [os.path.abspath(__file__)]:
+        with open(p, "rb") as f:
+            h.update(os.path.basename(p).encode() + b"\0" + f.read())
+    h.update(os.environ.get("DMK_NVCC_EXTRA", "").encode())
+    return h.hexdigest()
+
+
 def is_stale() -> bool:
-    if not os.path.exists(LIB):
+    if not os.path.exists(LIB) or not os.path.exists(STAMP):
         return True
-    t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, s) for s in SOURCES + HEADERS] + [os.path.abspath(__file__)]
-    return any(os.path.getmtime(p) > t for p in deps)
+    with open(STAMP) as f:
+        return f.read().strip() != source_hash()
 
 
 def build_lib(force: bool = False, verbose: bool = False) -> str:
     """Compile deepmimo_b200/csrc/*.cu into deepmimo_b200/libdmk.so.  Returns the library path."""
     if not force and not is_stale():
         return LIB
-    extra = os.environ.get("DMK_NVCC_EXTRA", "").split()          # e.g. -DDMK_TC_TRACE for the phase-timing debug build
-    cmd = [nvcc_path(), *NVCC_FLAGS, *extra, "-o", LIB + ".tmp", *[os.path.join(CSRC, s) for s in SOURCES]]
-    proc = subprocess.run(cmd, capture_output=True, text=True)
-    log = proc.stdout + proc.stderr
-    with open(os.path.join(PKG, "build.log"), "w") as f:
-        f.write(" ".join(cmd) + "\n" + log)
-    if proc.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + log)
-    os.replace(LIB + ".tmp", LIB)
+    # One builder at a time (every torchrun rank may find the library stale at once): an exclusive file lock, a per-process
+    # temporary output, and a re-check under the lock so that the ranks that waited reuse the winner's build.
+    import fcntl
+    with open(os.path.join(PKG, ".build.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        if not force and not is_stale():
+            return LIB
+        extra = os.environ.get("DMK_NVCC_EXTRA", "").split()      # e.g. -DDMK_TC_TRACE for the phase-timing debug build
+        tmp = f"{LIB}.{os.getpid()}.tmp"
+        cmd = [nvcc_path(), *NVCC_FLAGS, *extra, "-o", tmp, *[os.path.join(CSRC, s) for s in SOURCES]]
+        proc = subprocess.run(cmd, capture_output=True, text=True)
+        log = proc.stdout + proc.stderr
+        with open(os.path.join(PKG, "build.log"), "w") as f:
+            f.write(" ".join(cmd) + "\n" + log)
+        if proc.returncode != 0:
+            if os.path.exists(tmp):
+                os.remove(tmp)
+            raise RuntimeError("nvcc failed:\n" + log)
+        os.replace(tmp, LIB)
+        with open(STAMP, "w") as f:
+            f.write(source_hash())
     if verbose:
         print(log)
     return LIB

@@ -16,6 +16,7 @@ Layers
 from __future__ import annotations
 
 import ctypes
+import os
 from dataclasses import dataclass, field
 from typing import Any, Iterator, Optional, Tuple
 
@@ -327,6 +328,8 @@ class ChannelPlan:
         m = masks or {}
         mp = lambda k: None if m.get(k) is None else m[k].data_ptr()
         self.desc.flags = _lib.FLAG_INDEPENDENT_LAUNCH if independent else 0
+        self.desc.kernel_hint = _lib.kernel_hint_from_env("DMK_FD_KERNEL")
+        self.desc.ws_helpers = int(os.environ.get("DMK_WS_HELPERS", "0") or 0)
         common = [ctypes.byref(self.desc)] + [ptr(self.t[k]) for k in PATH_KEYS] + \
                  [ptr(self.ue_rot), ptr(self.doppler), n, self.n_cols, out.data_ptr()]
         with torch.cuda.device(self.device):
@@ -350,6 +353,7 @@ class ChannelPlan:
         m = masks or {}
         mp = lambda k: None if m.get(k) is None else m[k].data_ptr()
         self.desc.flags = 0
+        self.desc.kernel_hint = _lib.kernel_hint_from_env("DMK_BF_KERNEL")
         with torch.cuda.device(self.device):
             rc = self.lib.dmk_beam_amplitude_fd(
                 ctypes.byref(self.desc), *[self.t[k].data_ptr() for k in PATH_KEYS],
@@ -388,6 +392,33 @@ def _get(dataset, key, default=None):
             return default
 
 
+C_LIGHT = 299792458          # deepmimo_v3/consts.py:112
+
+
+def constant_doppler_shift(dataset, params, carrier_freq=None):
+    """`enable_doppler = 1` (channel.py:50): the one Doppler definition in the reference tree is v3's
+    (deepmimo_v3/generator/python/construct_deepmimo.py:267-280) -- with per-path radial velocity `doppler_vel` [m/s] and
+    acceleration `doppler_acc` [m/s^2] of a dynamic scenario every frequency-domain path gain is multiplied by the constant phase
+    exp(-j 2 pi f_c (v tau / c + a tau^2 / (2 c))), tau = ToA.  Returned as the per-path Doppler shift f_D [Hz] that produces
+    exactly that phase at the single snapshot time t = 1 s, or None when the flag is off, the branch is time-domain (v3 applies no
+    Doppler there, :90-91) or the dataset carries no velocities (v3: `doppler_available` false -> silently static)."""
+    if not params.get("enable_doppler") or not params.get("freq_domain", 1):
+        return None
+    vel, acc = _get(dataset, "doppler_vel"), _get(dataset, "doppler_acc")
+    if vel is None or acc is None:
+        return None
+    if int(params["ofdm"].get("rx_filter", 0)):
+        raise NotImplementedError("enable_doppler with ofdm.rx_filter = 1 (per-tap Doppler of construct_deepmimo.py:274) is not implemented")
+    if carrier_freq is None:
+        rt = _get(dataset, "rt_params")
+        carrier_freq = None if rt is None else (rt.get("frequency") if hasattr(rt, "get") else getattr(rt, "frequency", None))
+    if carrier_freq is None:
+        raise ValueError("enable_doppler needs the carrier frequency: dataset['rt_params']['frequency'] or carrier_freq=")
+    tau = np.asarray(dataset["delay"], dtype=np.float64)
+    v, a = np.asarray(vel, dtype=np.float64), np.asarray(acc, dtype=np.float64)
+    return (-float(carrier_freq) * (v * tau / C_LIGHT + a * tau ** 2 / (2 * C_LIGHT))).astype(np.float32)
+
+
 def make_plan(dataset, params=None, *, times=None, doppler=None, device=None, seed_numpy_rng=True,
               warn=True) -> Tuple[ChannelPlan, Any]:
     """Validate parameters against the dataset and move its path matrices to the device."""
@@ -418,7 +449,15 @@ def default_chunk_users(plan: ChannelPlan, budget_bytes: int = 1 << 30) -> int:
     return max(1, min(plan.n_users, budget_bytes // max(per_user, 1)))
 
 
-def iter_channels(plan: ChannelPlan, chunk_users: Optional[int] = None, n_buffers: int = 2) -> Iterator[Tuple[int, int, Any]]:
+def chunk_is_independent(i: int, n_buffers: int) -> bool:
+    """Whether chunk `i` of a chain of launches that cycles through `n_buffers` output buffers may carry
+    DMK_FLAG_INDEPENDENT_LAUNCH (include/dmk.h, ordering contract).  A flagged launch only waits for the previous launch to
+    have *begun*, so a run of s flagged launches can overlap with s predecessors; chunk i reuses the buffer of chunk
+    i - n_buffers, hence at most n_buffers - 1 consecutive flagged launches, then one plain stream-ordered launch."""
+    return n_buffers > 1 and (i % n_buffers) != 0
+
+
+def iter_channels(plan: ChannelPlan, chunk_users: Optional[int] = None, n_buffers: int = 3) -> Iterator[Tuple[int, int, Any]]:
     """Stream H in chunks through a ring of `n_buffers` device buffers: yields (start, stop, tensor).
 
     The yielded tensor is valid until `n_buffers - 1` further chunks have been requested; the consumer
@@ -430,14 +469,14 @@ def iter_channels(plan: ChannelPlan, chunk_users: Optional[int] = None, n_buffer
     for start in range(0, plan.n_users, chunk):
         stop = min(start + chunk, plan.n_users)
         buf = ring[i % len(ring)][: stop - start]
-        plan.run(buf, start, stop, independent=(i > 0 and len(ring) > 1))   # chunks of one range, different buffers
+        plan.run(buf, start, stop, independent=chunk_is_independent(i, len(ring)))   # chunks of one range, different buffers
         yield start, stop, buf
         i += 1
 
 
 def compute_channels(dataset, params=None, *, out: str = "numpy", device=None, chunk_users: Optional[int] = None,
                      times=None, doppler=None, return_info: bool = False, cache: bool = True, host_out=None,
-                     seed_numpy_rng: bool = True, warn: bool = True):
+                     seed_numpy_rng: bool = True, warn: bool = True, carrier_freq=None):
     """Compute MIMO channels for every user of `dataset` on the GPU.
 
     Same arguments, layout and caching behaviour as the reference's `Dataset.compute_channels`:
@@ -448,20 +487,30 @@ def compute_channels(dataset, params=None, *, out: str = "numpy", device=None, c
     cached); `times` [T] appends a trailing snapshot axis with per-path Doppler `doppler` [n, P] Hz (or
     `dataset['doppler']`) -- row a11 of SURVEY.md; `return_info=True` also returns the masks
     (`ChannelInfo`); `host_out` is an optional preallocated (ideally pinned) complex64 tensor/array.
+    `params.enable_doppler = 1` applies v3's constant per-path Doppler phase when the dataset carries `doppler_vel` /
+    `doppler_acc` (see `constant_doppler_shift`); the output keeps the reference's 4-D shape.
     """
     torch = _torch()
     if out not in ("numpy", "torch"):
         raise ValueError("out must be 'numpy' or 'torch'")
+    squeeze_time = False
+    if times is None and doppler is None:
+        p_eff = params if params is not None else (_get(dataset, "ch_params") or ChannelGenParameters())
+        doppler = constant_doppler_shift(dataset, p_eff, carrier_freq)
+        if doppler is not None:
+            times, squeeze_time = np.array([1.0]), True
     plan, params = make_plan(dataset, params, times=times, doppler=doppler, device=device,
                              seed_numpy_rng=seed_numpy_rng, warn=warn)
     n = plan.n_users
-    masks = plan.alloc_masks() if (return_info or True) else None
+    masks = plan.alloc_masks() if return_info else None
 
     if out == "torch":
         res = plan.alloc_out()
         if n:
             plan.run(res, 0, n, masks)
         info = plan.info_from_masks(masks) if return_info else None
+        if squeeze_time:
+            res = res[..., 0]
         return (res, info) if return_info else res
 
     # ---- host output: chunked kernels on the compute stream, D2H on a copy stream, two device buffers
@@ -470,6 +519,8 @@ def compute_channels(dataset, params=None, *, out: str = "numpy", device=None, c
         host_t = torch.empty(shape, dtype=torch.complex64, pin_memory=True)
     else:
         host_t = host_out if isinstance(host_out, torch.Tensor) else torch.from_numpy(host_out)
+        if squeeze_time and host_t.dim() == len(shape) - 1:
+            host_t = host_t.unsqueeze(-1)
         if tuple(host_t.shape) != shape or host_t.dtype != torch.complex64:
             raise ValueError(f"host_out must be complex64 of shape {shape}")
     if n and int(np.prod(shape)):
@@ -484,7 +535,7 @@ def compute_channels(dataset, params=None, *, out: str = "numpy", device=None, c
             if done[b] is not None:
                 compute.wait_event(done[b])              # buffer b has been drained by the copy stream
             buf = bufs[b][: stop - start]
-            sub = {k: v[start:stop] for k, v in masks.items()}
+            sub = None if masks is None else {k: v[start:stop] for k, v in masks.items()}
             plan.run(buf, start, stop, sub, stream=compute)
             ev = torch.cuda.Event()
             ev.record(compute)
@@ -495,6 +546,8 @@ def compute_channels(dataset, params=None, *, out: str = "numpy", device=None, c
                 done[b].record(copy)
         copy.synchronize()
     H = host_t.numpy() if host_out is None or isinstance(host_out, torch.Tensor) else host_out
+    if squeeze_time:
+        H = H[..., 0]
     info = plan.info_from_masks(masks) if return_info else None
     if cache:
         try:

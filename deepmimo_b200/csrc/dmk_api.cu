@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <cstring>
 #include <cstdlib>
+#include <mutex>
 
 #include "dmk_fd.cuh"
 #include "dmk_fd_tc.cuh"
@@ -121,16 +122,44 @@ int check_arrays(const float* a, const float* b, const float* c, const float* e,
     return DMK_OK;
 }
 
-int device_sm_count()
+// Per-device state.  cudaFuncSetAttribute and the SM count are properties of a (function, device) pair, so the
+// one-time opt-in to > 48 KB of dynamic shared memory is tracked per device: a process may call the library on
+// cuda:0 and then on cuda:1 (compute_channels(device=...), MacroDataset over several GPUs).
+constexpr int kMaxDevices = 64;
+constexpr int kSmemSmall = 72 * 1024, kSmemWs1 = 114 * 1024, kSmemWs4 = 220 * 1024, kSmemTc = 112 * 1024,
+              kSmemFast = 110 * 1024, kSmemTile = 200 * 1024;
+struct DeviceState { bool ready = false; int sms = 0; };
+DeviceState g_dev[kMaxDevices];
+std::mutex g_dev_mu;
+
+int device_state(const DeviceState*& out)
 {
-    static int sms = 0;
-    if (!sms) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        if (sms <= 0) sms = 148;
+    using namespace dmk;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaGetDevice");
+    if (dev < 0 || dev >= kMaxDevices) return fail(DMK_ERR_UNSUPPORTED, "device ordinal %d outside [0, %d)", dev, kMaxDevices);
+    std::lock_guard<std::mutex> lk(g_dev_mu);
+    DeviceState& s = g_dev[dev];
+    if (!s.ready) {
+        e = cudaDeviceGetAttribute(&s.sms, cudaDevAttrMultiProcessorCount, dev);
+        if (e != cudaSuccess || s.sms <= 0) return cuda_fail(e, "cudaDeviceGetAttribute(multiProcessorCount)");
+        const cudaFuncAttribute a = cudaFuncAttributeMaxDynamicSharedMemorySize;
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(fd_small_kernel<4>, a, kSmemSmall);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(fd_small_kernel<8>, a, kSmemSmall);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(fd_small_kernel<16>, a, kSmemSmall);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(fd_ws_kernel<1>, a, kSmemWs1);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(fd_ws_kernel<4>, a, kSmemWs4);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(fd_tc_kernel, a, kSmemTc);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(fd_fast_kernel, a, kSmemFast);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(bf_fast_kernel, a, kSmemFast);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(fd_tile_kernel, a, kSmemTile);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(bf_kernel, a, kSmemTile);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(MaxDynamicSharedMemorySize)");
+        s.ready = true;
     }
-    return sms;
+    out = &s;
+    return DMK_OK;
 }
 
 }  // namespace
@@ -172,9 +201,16 @@ int dmk_channels_fd(const dmk_desc* desc, const float* power_dbw, const float* p
     d.fov_mask = fov_mask; d.valid_mask = valid_mask; d.clip_mask = clip_mask;
 
     cudaStream_t st = reinterpret_cast<cudaStream_t>(cuda_stream);
+    const DeviceState* dev = nullptr;
+    rc = device_state(dev);
+    if (rc) return rc;
+    d.n_sms = dev->sms;
     const int ncols = d.K * d.T;
-    // Production path: affine subcarrier selection, no time axis, tables fit in shared memory.
-    const bool affine = ((d.subc_step != 0) || (d.K == 1)) && !d.rx_filter;      // the LPF runs in the generic tile kernel
+    // Production path: affine subcarrier selection, no time axis, tables fit in shared memory.  A single selected subcarrier
+    // given only as a device list (subc_step == 0, subcarriers != NULL) is not affine from the host's point of view: it goes to
+    // the generic tile kernel, which reads the list.
+    if (d.K == 1 && d.subc_step == 0 && !d.subc) d.subc_step = 1;
+    const bool affine = (d.subc_step != 0) && !d.rx_filter;      // the LPF runs in the generic tile kernel
     FastCfg cfg;
     size_t fast_smem = 0;
     {
@@ -195,10 +231,10 @@ int dmk_channels_fd(const dmk_desc* desc, const float* power_dbw, const float* p
     }
     const bool div_ok = (unsigned long long)d.M * (unsigned long long)(d.Mt > d.bs0 ? d.Mt : d.bs0) < 0xffffffffULL;
     // Kernel choice: tensor-core (tcgen05, FP16 hi/lo split) > packed-FP32 CUDA-core > generic tile kernel.
-    // DMK_FD_KERNEL=tc|ffma|tile overrides it (parity tests and A/B timing use this).
-    const char* force = getenv("DMK_FD_KERNEL");
-    const bool want_tile = force && !strcmp(force, "tile");
-    const bool want_ffma = force && !strcmp(force, "ffma");
+    // dmk_desc.kernel_hint overrides it (parity tests and A/B timing use this; the Python driver maps DMK_FD_KERNEL to it).
+    const int hint = desc->kernel_hint;
+    const bool want_tile = hint == DMK_KERNEL_TILE;
+    const bool want_ffma = hint == DMK_KERNEL_FFMA;
     TcCfg tcfg;
     size_t tc_smem = 1024;                                   // slack for the 1024-byte alignment of the operand tiles
     {
@@ -208,10 +244,6 @@ int dmk_channels_fd(const dmk_desc* desc, const float* power_dbw, const float* p
         tcfg.pcap = pc;
         tcfg.nA = (d.K + 15) / 16;
         tcfg.mtile = d.M >= 128 ? 128 : (d.M > 32 ? 64 : (d.M > 16 ? 32 : 16));   // antenna rows per tile = tcgen05 N
-        if (const char* mt = getenv("DMK_TC_MTILE")) {      // experiment knob: force the antenna-row tile (16/32/64/128)
-            const int v = atoi(mt);
-            if (v == 16 || v == 32 || v == 64 || v == 128) tcfg.mtile = v;
-        }
         tcfg.nsub = tcfg.mtile <= 64 ? 2 : 1;                // keep a pipeline stage at 64 KB of output for small arrays
         tcfg.off_A  = take((size_t)2 * tcfg.mtile * 128);    // A_hi, A_lo
         tcfg.off_B  = take((size_t)tcfg.nsub * 2 * kTcN * 128);   // B_hi, B_lo per sub-tile
@@ -229,15 +261,15 @@ int dmk_channels_fd(const dmk_desc* desc, const float* power_dbw, const float* p
     }
     // Tiny arrays (M < 64) and FoV-sparse scenarios are per-user-overhead bound: the packed-FP32 kernel is faster there
     // (profiles/README.md); DMK_FD_KERNEL=tc still forces the tensor-core kernel.
-    const bool want_tc = force && (!strcmp(force, "tc") || !strcmp(force, "tc1"));
-    const bool use_tc = affine && !d.has_time_axis && div_ok && (d.K % (kTcN / 2) == 0) && d.K <= 4096 && tc_smem <= 112 * 1024 &&
+    const bool want_tc = hint == DMK_KERNEL_TC || hint == DMK_KERNEL_TC1;
+    const bool use_tc = affine && !d.has_time_axis && div_ok && (d.K % (kTcN / 2) == 0) && d.K <= 4096 && tc_smem <= (size_t)kSmemTc &&
                         !want_tile && !want_ffma && ((d.M >= 64 && !d.fov_any) || want_tc);   // FoV leaves few paths, tiny arrays little output: FP32 kernel wins
-    const bool use_fast = !use_tc && affine && !d.has_time_axis && div_ok && fast_smem <= 110 * 1024 && !want_tile;
+    const bool use_fast = !use_tc && affine && !d.has_time_axis && div_ok && fast_smem <= (size_t)kSmemFast && !want_tile;
     const int tile_w_tc1 = (kTcN / 2) * tcfg.nsub;
     const int tile_w = use_tc ? tile_w_tc1 : (use_fast ? kTKW : kTK);
     const int n_ct = (ncols + tile_w - 1) / tile_w;
     // Few users: split each user's column tiles over several CTAs so the grid covers >= 4 waves.
-    const long long want = 4LL * 2 * device_sm_count();
+    const long long want = 4LL * 2 * dev->sms;
     long long ksplit = (want + n_users - 1) / n_users;
     if (ksplit > n_ct) ksplit = n_ct;
     if (ksplit < 1) ksplit = 1;
@@ -245,7 +277,6 @@ int dmk_channels_fd(const dmk_desc* desc, const float* power_dbw, const float* p
     if (grid > 0x7fffffffLL) return fail(DMK_ERR_INVALID_ARG, "grid too large: split the user range");
     // Small arrays (M <= 16): one warp per user, see dmk_fd_small.cuh.  DMK_FD_KERNEL=small forces it where eligible.
     {
-        const bool want_small = force && !strcmp(force, "small");
         SmallCfg sc;
         const int pc = d.P > 0 ? d.P : 1;
         const int mt = d.M <= 4 ? 4 : (d.M <= 8 ? 8 : 16);
@@ -263,21 +294,12 @@ int dmk_channels_fd(const dmk_desc* desc, const float* power_dbw, const float* p
         sc.warp_bytes = (int)off;
         sc.mul_mt = cfg.mul_mt; sc.mul_bs0 = cfg.mul_bs0;
         const size_t small_smem = off * kSmallWarps;
-        const bool small_ok = affine && !d.has_time_axis && div_ok && d.M <= 16 && d.K <= 4096 && small_smem <= 72 * 1024;
-        const bool use_small = small_ok && !want_tile && !want_ffma && !want_tc && (want_small || true);
+        const bool small_ok = affine && !d.has_time_axis && div_ok && d.M <= 16 && d.K <= 4096 && small_smem <= (size_t)kSmemSmall;
+        const bool use_small = small_ok && !want_tile && !want_ffma && !want_tc;
         if (use_small) {
-            if (d.K == 1 && d.subc_step == 0) d.subc_step = 1;
             const long long sgrid = (n_users + kSmallWarps - 1) / kSmallWarps;
             if (sgrid > 0x7fffffffLL) return fail(DMK_ERR_INVALID_ARG, "grid too large: split the user range");
             cudaError_t e = cudaSuccess;
-            static bool attr_small = false;
-            if (!attr_small) {
-                e = cudaFuncSetAttribute(fd_small_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024);
-                if (e == cudaSuccess) e = cudaFuncSetAttribute(fd_small_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024);
-                if (e == cudaSuccess) e = cudaFuncSetAttribute(fd_small_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024);
-                if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(fd_small_kernel)");
-                attr_small = true;
-            }
             if (mt == 4)      fd_small_kernel<4><<<(unsigned)sgrid, kSmallWarps * 32, small_smem, st>>>(d, sc);
             else if (mt == 8) fd_small_kernel<8><<<(unsigned)sgrid, kSmallWarps * 32, small_smem, st>>>(d, sc);
             else              fd_small_kernel<16><<<(unsigned)sgrid, kSmallWarps * 32, small_smem, st>>>(d, sc);
@@ -290,7 +312,7 @@ int dmk_channels_fd(const dmk_desc* desc, const float* power_dbw, const float* p
     }
     // Warp-specialised persistent tensor-core kernel (default); DMK_FD_KERNEL=tc1 keeps the one-CTA-per-user version, which also
     // takes the shapes whose double-buffered tables do not fit next to the operand tiles.
-    const bool want_tc1 = force && !strcmp(force, "tc1");
+    const bool want_tc1 = hint == DMK_KERNEL_TC1;
     TcCfg pcfg = tcfg;
     size_t ptc_smem = 0;
     int n_helpers = 1;
@@ -330,27 +352,19 @@ int dmk_channels_fd(const dmk_desc* desc, const float* power_dbw, const float* p
         // single CTA per SM (shared memory and registers allow it because only one CTA is resident).
         const size_t per_user_bytes = (size_t)d.M * d.K * sizeof(float2);
         const size_t smem4 = 1024 + off + 8 * buf_bytes;
-        const char* hf = getenv("DMK_WS_HELPERS");
-        if ((per_user_bytes <= 384 * 1024 || (hf && atoi(hf) == 4)) && smem4 <= 220 * 1024 && !(hf && atoi(hf) == 1)) n_helpers = 4;
+        const int hf = desc->ws_helpers;                      // 0 = by shape, 1 or 4 pins the instantiation (tests, A/B timing)
+        if ((per_user_bytes <= 384 * 1024 || hf == 4) && smem4 <= (size_t)kSmemWs4 && hf != 1) n_helpers = 4;
         ptc_smem = 1024 + off + 2 * n_helpers * buf_bytes;
         if (n_helpers == 4 || ptc_smem <= 113200) break;
     }
     const bool use_tcp = use_tc && !want_tc1 && (n_helpers == 4 || ptc_smem <= 113200) && grid < 0xffffff00LL;   // H = 1: + ~2.6 KB static + 1 KB reserve, two CTAs per SM
     if (use_tcp) {
         // warp-specialised persistent kernel (dmk_fd_ws.cuh): the production tensor-core path
-        if (d.K == 1 && d.subc_step == 0) d.subc_step = 1;
-        static bool attr_ws = false;
-        if (!attr_ws) {
-            cudaError_t e = cudaFuncSetAttribute(fd_ws_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(114 * 1024));
-            if (e == cudaSuccess) e = cudaFuncSetAttribute(fd_ws_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024));
-            if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(fd_ws_kernel)");
-            attr_ws = true;
-        }
         static std::atomic<unsigned> ticket_seq{0};
         unsigned int* tickets = nullptr;
         cudaError_t e = cudaGetSymbolAddress(reinterpret_cast<void**>(&tickets), g_tc_ticket);
         if (e != cudaSuccess) return cuda_fail(e, "cudaGetSymbolAddress(g_tc_ticket)");
-        const long long resident = (n_helpers == 1 ? 2LL : 1LL) * device_sm_count();
+        const long long resident = (n_helpers == 1 ? 2LL : 1LL) * dev->sms;
         const long long pgrid = grid < resident ? grid : resident;
         // Programmatic dependent launch: the kernel releases its dependents at once, so the next libdmk launch can fill SMs
         // as this one's persistent CTAs retire.  Unless the caller set DMK_FLAG_INDEPENDENT_LAUNCH the kernel itself
@@ -373,13 +387,6 @@ int dmk_channels_fd(const dmk_desc* desc, const float* power_dbw, const float* p
         return DMK_OK;
     }
     if (use_tc) {
-        if (d.K == 1 && d.subc_step == 0) d.subc_step = 1;
-        static bool attr_tc = false;
-        if (!attr_tc) {
-            cudaError_t e = cudaFuncSetAttribute(fd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(112 * 1024));
-            if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(fd_tc_kernel)");
-            attr_tc = true;
-        }
         fd_tc_kernel<<<(unsigned)grid, kTcThreads, tc_smem, st>>>(d, tcfg, (int)ksplit);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return cuda_fail(e, "fd_tc_kernel launch");
@@ -388,13 +395,6 @@ int dmk_channels_fd(const dmk_desc* desc, const float* power_dbw, const float* p
         return DMK_OK;
     }
     if (use_fast) {
-        if (d.K == 1 && d.subc_step == 0) d.subc_step = 1;
-        static size_t attr_fast = 0;
-        if (fast_smem > attr_fast) {
-            cudaError_t e = cudaFuncSetAttribute(fd_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(110 * 1024));
-            if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(fd_fast_kernel)");
-            attr_fast = 110 * 1024;
-        }
         fd_fast_kernel<<<(unsigned)grid, kFdThreads, fast_smem, st>>>(d, cfg, (int)ksplit);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return cuda_fail(e, "fd_fast_kernel launch");
@@ -405,18 +405,12 @@ int dmk_channels_fd(const dmk_desc* desc, const float* power_dbw, const float* p
     size_t smem = (size_t)kMaxPaths * (kTK + kTM) * sizeof(float2);
     if (d.rx_filter) {
         smem += (size_t)(1 + d.lpf_batch) * d.N * sizeof(float2);      // twiddle table + FFT batch (dmk_fd.cuh: lpf_w_tile)
-        if (smem > 200 * 1024)
+        if (smem > (size_t)kSmemTile)
             return fail(DMK_ERR_UNSUPPORTED, "ofdm.rx_filter=1 supports ofdm.subcarriers <= 9728 (got %d)", d.N);
         // what is left of 200 KB caches the transformed paths of a user (np * K complex values) across its column tiles
-        d.lpf_cache = (int)((200 * 1024 - smem) / sizeof(float2));
+        d.lpf_cache = (int)((kSmemTile - smem) / sizeof(float2));
         if ((long long)d.lpf_cache > (long long)kMaxPaths * d.K) d.lpf_cache = kMaxPaths * d.K;
         smem += (size_t)d.lpf_cache * sizeof(float2);
-    }
-    static size_t attr_set = 0;
-    if (smem > attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(fd_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(fd_tile_kernel)");
-        attr_set = smem;
     }
     fd_tile_kernel<<<(unsigned)grid, kFdThreads, smem, st>>>(d, (int)ksplit);
     cudaError_t e = cudaGetLastError();
@@ -444,6 +438,10 @@ int dmk_channels_td(const dmk_desc* desc, const float* power_dbw, const float* p
     d.out = reinterpret_cast<float2*>(out_c64);
     d.fov_mask = fov_mask; d.valid_mask = valid_mask; d.path_slot = path_slot;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(cuda_stream);
+    const DeviceState* dev = nullptr;
+    rc = device_state(dev);
+    if (rc) return rc;
+    d.n_sms = dev->sms;
     td_kernel<<<(unsigned)n_users, kTdThreads, 0, st>>>(d);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "td_kernel launch");
@@ -474,10 +472,14 @@ int dmk_beam_amplitude_fd(const dmk_desc* desc, const float* power_dbw, const fl
     d.fov_mask = fov_mask; d.valid_mask = valid_mask; d.clip_mask = clip_mask;
     if (d.K == 1 && d.subc_step == 0 && !d.subc) d.subc_step = 1;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(cuda_stream);
+    const DeviceState* dev = nullptr;
+    rc = device_state(dev);
+    if (rc) return rc;
+    d.n_sms = dev->sms;
     // Production route: the packed-FP32 kernel in beam mode (virtual TX panel 1 x n_beams, dmk_fd.cuh: fd_fast_body<true>).
     // Needs an affine subcarrier selection and tables that fit; otherwise the generic tile version below runs.
     {
-        const bool affine = (d.subc_step != 0) || (d.K == 1);
+        const bool affine = d.subc_step != 0;
         DevDesc db = d;
         db.bs0 = 1; db.bs1 = n_beams; db.Mt = n_beams; db.M = d.Mr * n_beams;
         FastCfg cfg;
@@ -500,18 +502,11 @@ int dmk_beam_amplitude_fd(const dmk_desc* desc, const float* power_dbw, const fl
         bc.F = reinterpret_cast<const float2*>(beams_c64);
         bc.out = mean_abs;
         const bool div_ok = (unsigned long long)db.M * (unsigned long long)db.Mt < 0xffffffffULL;
-        const char* force = getenv("DMK_BF_KERNEL");
         // scratch tables [np][bs0|1], [np][bs1|1], [np][Mr] live in the W tile area, one staged codebook row [n_beams][bs0] in the
         // A strip area, and a thread accumulates at most 8 (beam, path) pairs
         const bool scratch_ok = (d.bs0 | 1) + (d.bs1 | 1) + d.Mr <= kTKW && (size_t)n_beams * d.bs0 * sizeof(float2) <= (size_t)8 * pc * 8 * sizeof(float4) &&
                                 (long long)n_beams * pc <= 8LL * kFdThreads;
-        if (affine && div_ok && fast_smem <= 110 * 1024 && scratch_ok && !(force && !strcmp(force, "tile"))) {
-            static size_t attr_bff = 0;
-            if (fast_smem > attr_bff) {
-                cudaError_t e = cudaFuncSetAttribute(bf_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(110 * 1024));
-                if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(bf_fast_kernel)");
-                attr_bff = 110 * 1024;
-            }
+        if (affine && div_ok && fast_smem <= (size_t)kSmemFast && scratch_ok && desc->kernel_hint != DMK_KERNEL_TILE) {
             bf_fast_kernel<<<(unsigned)n_users, kFdThreads, fast_smem, st>>>(db, cfg, bc);
             cudaError_t e = cudaGetLastError();
             if (e != cudaSuccess) return cuda_fail(e, "bf_fast_kernel launch");
@@ -532,13 +527,7 @@ int dmk_beam_amplitude_fd(const dmk_desc* desc, const float* power_dbw, const fl
     c.off_tZ   = take((size_t)kMaxPaths * d.bs1 * sizeof(float2));
     c.off_aR   = take((size_t)kMaxPaths * d.Mr * sizeof(float2));
     const size_t smem = (size_t)kMaxPaths * (kTK + kTM) * sizeof(float2) + off;
-    if (smem > 200 * 1024) return fail(DMK_ERR_UNSUPPORTED, "beam tables need %zu bytes of shared memory (> 200 KB): fewer beams or a smaller panel", smem);
-    static size_t attr_bf = 0;
-    if (smem > attr_bf) {
-        cudaError_t e = cudaFuncSetAttribute(bf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(bf_kernel)");
-        attr_bf = smem;
-    }
+    if (smem > (size_t)kSmemTile) return fail(DMK_ERR_UNSUPPORTED, "beam tables need %zu bytes of shared memory (> 200 KB): fewer beams or a smaller panel", smem);
     bf_kernel<<<(unsigned)n_users, kFdThreads, smem, st>>>(d, c);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "bf_kernel launch");

@@ -36,6 +36,7 @@ struct DevDesc {
     float  n_f32;                 // float32(N)
     double inv_n;                 // 1/N
     int    ld;
+    int    n_sms;                 // SMs of the device the launch runs on (prefetch distance of the one-CTA-per-user kernels)
     long long n_users;
     const float *power, *phase, *delay, *az[2], *el[2], *doppler;   // az/el: [0] = AoD, [1] = AoA
     const double* ue_rot;         // per-user [n,3] degrees or nullptr

@@ -44,20 +44,23 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* b)
 {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(b)) : "memory");
 }
-// Wait for the phase with the given parity to complete.  A lost arrival must fail loudly, never hang the device.
+// Wait for the phase with the given parity to complete.  A lost arrival must fail loudly rather than hang the device, but a
+// legitimately slow neighbour (time-sliced GPU, debugger) must not be killed: the watchdog runs on the global nanosecond
+// timer and only fires after 30 s without progress on this barrier.
 __device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity)
 {
     const uint32_t bar = smem_u32(b);
     uint32_t ok = 0;
-    long long t0 = 0;
+    unsigned long long t0 = 0;
     for (unsigned spins = 0; ; ++spins) {
         asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
                      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
         if (ok) break;
-        if ((spins & 1023u) == 1023u) {
-            const long long now = clock64();
+        if ((spins & 4095u) == 4095u) {
+            unsigned long long now;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
             if (t0 == 0) t0 = now;
-            else if (now - t0 > 4000000000LL) __trap();      // ~2 s
+            else if (now - t0 > 30000000000ULL) __trap();
         }
     }
 }

@@ -189,7 +189,7 @@ __device__ __forceinline__ bool prologue_needs_angles(const DevDesc& d)
 __device__ __forceinline__ void prefetch_user_rows_shifted(const DevDesc& d, long long user)
 {
     const int t = threadIdx.x - 224;
-    const long long ahead = user + 4LL * 2 * 148;
+    const long long ahead = user + 4LL * 2 * (d.n_sms > 0 ? d.n_sms : 148);
     if (t < 0 || t >= 7 || ahead >= d.n_users) return;
     const float* base = (t == 0) ? d.power : (t == 1) ? d.phase : (t == 2) ? d.delay : (t == 3) ? d.az[0] : (t == 4) ? d.el[0]
                       : (t == 5) ? d.az[1] : d.el[1];

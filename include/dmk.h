@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define DMK_ABI_VERSION 2
+#define DMK_ABI_VERSION 3
 #define DMK_MAX_PATHS   32    /* path columns per user handled by one launch (reference: MAX_PATHS = 25, consts.py:180) */
 #define DMK_MAX_TIMES   4096  /* time snapshots per launch */
 
@@ -75,14 +75,32 @@ typedef struct dmk_desc {
     int32_t n_times;            /* 0 = no trailing time axis; T >= 1 appends [.., T] (row a11)      */
     const double *times;        /* DEVICE pointer, [T] snapshot times in seconds                    */
     int32_t flags;              /* DMK_FLAG_* (ABI 2); 0 = plain stream-ordered launch                   */
+    int32_t kernel_hint;        /* dmk_kernel_hint (ABI 3); 0 = the library picks the kernel by shape     */
+    int32_t ws_helpers;         /* 0 = by shape; 1 or 4 pins the helper-warp count of the persistent tensor-core kernel (tests) */
 } dmk_desc;
+
+/* dmk_desc.kernel_hint: force a kernel family where the shape is eligible for it (parity tests run every family on the same
+ * inputs; A/B timing).  A hint the shape is not eligible for falls through to the next family, exactly like the automatic choice. */
+typedef enum dmk_kernel_hint {
+    DMK_KERNEL_AUTO  = 0,
+    DMK_KERNEL_TILE  = 1,   /* generic tile kernel (any subcarrier list, time axis, rx_filter)      */
+    DMK_KERNEL_FFMA  = 2,   /* packed-FP32 CUDA-core kernel                                         */
+    DMK_KERNEL_TC    = 3,   /* persistent warp-specialised tcgen05 kernel                           */
+    DMK_KERNEL_TC1   = 4,   /* one-CTA-per-user tcgen05 kernel                                      */
+    DMK_KERNEL_SMALL = 5    /* small-array kernel (M <= 16)                                         */
+} dmk_kernel_hint;
 
 /* dmk_desc.flags.
  * DMK_FLAG_INDEPENDENT_LAUNCH: the caller asserts that this launch neither reads nor overwrites anything the
  * kernel launched immediately before it on the same stream writes (e.g. consecutive user chunks of one
  * compute_channels call going to different output buffers).  The persistent tensor-core kernel then starts
  * filling SMs while the previous launch drains its tail (programmatic dependent launch without a grid
- * dependency wait).  Without the flag every launch observes full stream order. */
+ * dependency wait).  Without the flag every launch observes full stream order.
+ * Ordering contract: a flagged launch begins only after every CTA of the previous launch has begun, and an
+ * unflagged launch begins only after everything before it has completed.  A flagged launch that follows s - 1
+ * other flagged launches can therefore overlap with its s predecessors but never with anything older than the
+ * last unflagged launch's predecessors: with a ring of R output buffers, at most R - 1 consecutive launches may
+ * carry the flag before one launch goes without it (deepmimo_b200.iter_channels does exactly that). */
 #define DMK_FLAG_INDEPENDENT_LAUNCH 1
 
 /* Frequency-domain channels (freq_domain = 1):

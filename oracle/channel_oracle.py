@@ -11,9 +11,12 @@ container (``tests/golden/make_golden.py`` writes the fixtures under
 ``tests/golden/*.npz``; ``tests/test_oracle_golden.py`` replays them).  The
 reference's own tests store no golden vectors for this path, so
 the reference-generated fixtures are the pin.  Row a11 (Doppler / time
-snapshots) has **no** reference implementation in v4 -- that part of the oracle
-(`doppler_hz`, `times`) is "parity unpinned": it is the definition, cross-checked
-only against the reference at t = 0.
+snapshots) has no implementation in v4; the oracle's `doppler_hz` / `times`
+extension is pinned against the one Doppler definition in the reference tree,
+v3's constant per-path phase (deepmimo_v3/.../construct_deepmimo.py:267-280), by
+tests/golden/doppler_v3.npz (produced by running v3 itself) and against the v4
+reference at t = 0; the multi-snapshot time axis beyond that is this repo's
+definition (exp(+j 2 pi f_D t) per path).
 
 Every function cites the reference file:line it follows (paths relative to
 /root/reference).  dtype flow is deliberately the reference's (float32 inputs,
@@ -268,6 +271,22 @@ def compute_channels(data: dict, *, bs_shape=(8, 1), ue_shape=(1, 1), bs_spacing
             else:
                 H[i, :, :, :n_i, :] = (arp * pg[None, None, :])[..., None] * dphase[None, None, :, :]
     return dict(H=H, fov_mask=fov_mask, valid=valid, clip=clip, path_slot=path_slot)
+
+
+# --------------------------------------------------------------------------
+# row a11: v3's constant per-path Doppler phase (the only Doppler definition in the reference tree)
+# --------------------------------------------------------------------------
+LIGHTSPEED = 299792458   # deepmimo_v3/consts.py:112
+
+
+def v3_doppler_shift(toa, vel, acc, carrier_hz: float) -> np.ndarray:
+    """deepmimo_v3/generator/python/construct_deepmimo.py:267-280 (no-LPF branch): path gains are multiplied by
+    exp(-j 2 pi f_c (v tau / c + a tau^2 / (2 c))), tau = ToA.  Returned as the float32 per-path Doppler shift f_D [Hz] for which
+    `compute_channels(..., doppler_hz=f_D, times=[1.0])` applies exactly that phase (exp(+j 2 pi f_D t) at t = 1 s).
+    Pinned by tests/golden/doppler_v3.npz (generated by running v3 itself)."""
+    tau = np.asarray(toa, dtype=np.float64)
+    v, a = np.asarray(vel, dtype=np.float64), np.asarray(acc, dtype=np.float64)
+    return (-carrier_hz * (v * tau / LIGHTSPEED + a * tau ** 2 / (2 * LIGHTSPEED))).astype(np.float32)
 
 
 # --------------------------------------------------------------------------
