@@ -34,12 +34,17 @@ os.environ.setdefault("TQDM_DISABLE", "1")
 
 METRIC = "H coefficients/s (complex64)"
 UNIT = "coef/s"
-WORKLOADS = {"cfg1": 1, "cfg2": 2, "cfg3": 3, "cfg4": 4, "cfg5": 5}
+# workload name -> (BASELINE.json config number, scenario variant).  cfg1..cfg5 are SURVEY.md 8d's configurations; the others are
+# sensitivity variants: every user with all 25 paths, config 3 without its FoV filter.
+WORKLOADS = {"cfg1": (1, {}), "cfg2": (2, {}), "cfg3": (3, {}), "cfg4": (4, {}), "cfg5": (5, {}),
+             "cfg2_dense": (2, {"dense": True}), "cfg5_dense": (5, {"dense": True}), "cfg3_nofov": (3, {"fov": False})}
 # --impl reference: users per host core in one step (about 3 s of NumPy work per core at the default K + W)
 CPU_SAMPLE_USERS = {1: 12000, 2: 24, 3: 48, 4: 3000, 5: 160}
 # cpu_baseline leg of the b200 arm: one core, about 10-30 s of NumPy work
 CPU_BASELINE_USERS = {1: 80000, 2: 128, 3: 256, 4: 20000, 5: 1024}
+DEFAULT_USERS = {1: 80_000, 2: 4096, 3: 8192, 4: 50_000, 5: 200_000}      # SURVEY.md 8 size table (per GPU)
 FP32_LANES_PER_SM = 128
+PARITY_USERS = 64              # users pulled out of the timed buffers and compared with the oracle (untimed)
 
 
 def _lib_last_kernel():
@@ -65,10 +70,10 @@ def measured_peaks():
 # ------------------------------------------------------------------------------------------------
 def scenario_for(workload: str, rank: int, users):
     from deepmimo_b200.synth import scenario
-    cfg = WORKLOADS[workload]
+    cfg, var = WORKLOADS[workload]
     if cfg == 5:
-        return scenario(5, users, bs_index=rank)            # one BS per GPU
-    return scenario(cfg, users, shard=rank)
+        return scenario(5, users, bs_index=rank, **var)     # one BS per GPU
+    return scenario(cfg, users, shard=rank, **var)
 
 
 def oracle_call(s, lo, hi):
@@ -106,6 +111,56 @@ def algorithmic_counts(s, plan, info):
         t = 1 if plan.spec.times is None else len(plan.spec.times)
         flops = 6 * plan.spec.m_rx * plan.spec.m_tx * t * int(active.sum())
     return n_coef, bytes_alg, flops, float(active.sum()) / max(n, 1)
+
+
+def ring_segments(n_users: int, chunk: int, n_ring: int):
+    """What the ring buffers hold after a pass over [0, n_users) in chunks of `chunk` users through `n_ring` buffers:
+    a list of (first user, buffer index, first row, rows).  A short last chunk leaves the tail of the chunk that used its buffer
+    before it in place -- that data was written inside the timed region too."""
+    n_chunks = (n_users + chunk - 1) // chunk
+    segs = []
+    for b in range(min(n_ring, n_chunks)):
+        i = ((n_chunks - 1 - b) // n_ring) * n_ring + b            # last chunk that went to buffer b
+        rows = min(chunk, n_users - i * chunk)
+        segs.append((i * chunk, b, 0, rows))
+        if rows < chunk and i - n_ring >= 0:
+            segs.append(((i - n_ring) * chunk + rows, b, rows, chunk - rows))
+    return segs
+
+
+def parity_check(s, plan, ring, chunk, info, n_sample=PARITY_USERS, seed=0):
+    """Untimed: pull users out of the buffers the timed loop has just written and compare them with the oracle (the checker) --
+    per-user relative Frobenius error of the coefficients against north_star's 1e-5, masks bit for bit.  The sample always holds
+    the first and the last user of every ring segment, i.e. it spans the chunk boundaries of the ring."""
+    import torch
+    from util import TOL_REL_FRO, oracle_on_users, per_user_rel_fro
+    t0 = time.perf_counter()
+    segs = ring_segments(plan.n_users, chunk, len(ring))
+    rng = np.random.default_rng(seed)
+    where = {}
+    for u0, b, r0, rows in segs:
+        for u in (u0, u0 + rows - 1):
+            where[u] = (b, r0 + (u - u0))
+    total = sum(r for _, _, _, r in segs)
+    while len(where) < min(n_sample, total):
+        u0, b, r0, rows = segs[int(rng.integers(len(segs)))]
+        k = int(rng.integers(rows))
+        where[u0 + k] = (b, r0 + k)
+    users = np.array(sorted(where))
+    got = torch.stack([ring[where[u][0]][where[u][1]] for u in users]).cpu().numpy()
+    o = oracle_on_users(s, users)
+    err = per_user_rel_fro(got, o["H"])
+    p = o["valid"].shape[1]
+    masks_equal = bool(np.array_equal(info.valid[users][:, :p], o["valid"]))
+    if plan.spec.freq_domain:
+        masks_equal &= bool(np.array_equal(info.clip[users][:, :p], o["clip"]))
+    if o["fov_mask"] is not None:
+        masks_equal &= info.fov_mask is not None and bool(np.array_equal(info.fov_mask[users], o["fov_mask"]))
+    nan_free = not bool(np.isnan(got.view(np.float32)).any())
+    return {"max_rel_fro": float(err.max()), "tolerance": TOL_REL_FRO, "masks_equal": masks_equal, "users": int(len(users)),
+            "ring_segments": len(segs), "nan_free": nan_free,
+            "ok": bool(err.max() <= TOL_REL_FRO and masks_equal and nan_free),
+            "checker": "oracle/channel_oracle.py on users pulled from the timed output buffers", "seconds": round(time.perf_counter() - t0, 2)}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -173,6 +228,7 @@ def time_plan(plan, out_ring, chunk, steps, warmup, flush, dist, world):
     """Per-step CUDA-event timing on the launch stream; L2 flushed (untimed) between steps.
     Returns (sum of step times in ms on this rank, list of step ms)."""
     import torch
+    from deepmimo_b200.channels import chunk_is_independent
     stream = torch.cuda.current_stream()
     n = plan.n_users
 
@@ -180,7 +236,8 @@ def time_plan(plan, out_ring, chunk, steps, warmup, flush, dist, world):
         i = 0
         for a in range(0, n, chunk):
             b = min(a + chunk, n)
-            plan.run(out_ring[i % len(out_ring)][: b - a], a, b, independent=(i > 0 and len(out_ring) > 1 and not os.environ.get("DMK_BENCH_NO_PDL")))
+            plan.run(out_ring[i % len(out_ring)][: b - a], a, b,
+                     independent=chunk_is_independent(i, len(out_ring)) and not os.environ.get("DMK_BENCH_NO_PDL"))
             i += 1
 
     for _ in range(warmup):
@@ -203,57 +260,94 @@ def time_plan(plan, out_ring, chunk, steps, warmup, flush, dist, world):
     return float(sum(ms)), ms
 
 
-def run_workload(workload, users, steps, warmup, rank, world, dist, flush, want_clocks=True):
+def run_workload(workload, users, steps, warmup, rank, world, dist, flush, want_clocks=True, parity=True):
+    """One workload on this rank.  The rank's share comes from the product's sharding path
+    (deepmimo_b200.sharding.compute_channels_sharded over one dataset per base station / shard, lazily materialised), with
+    the timed ring loop as the `compute` consumer."""
     import torch
     import deepmimo_b200 as dmb
     from deepmimo_b200 import _lib
     from deepmimo_b200.channels import default_chunk_users
+    from deepmimo_b200.sharding import compute_channels_sharded
 
-    s = scenario_for(workload, rank, users)
-    ds = dmb.Dataset(dict(s.data))
-    if s.bs_fov is not None:
-        ds.apply_fov(bs_fov=s.bs_fov, ue_fov=s.ue_fov)
-    params = dmb.ChannelGenParameters(s.params)
-    plan, _ = dmb.make_plan(ds, params, times=s.times, doppler=s.doppler_hz, warn=False)
-    per_user = plan.spec.coefs_per_user(plan.n_cols) * 8
-    total_bytes = per_user * plan.n_users
-    free_b, _tot = torch.cuda.mem_get_info()
-    if total_bytes <= min(64 << 30, int(free_b * 0.6)) and not os.environ.get("DMK_BENCH_FORCE_RING"):
-        chunk, ring = plan.n_users, [plan.alloc_out()]
-        layout = f"single [{plan.n_users} users] output tensor ({total_bytes / 2**30:.1f} GiB) rewritten every step"
-    else:
-        chunk = default_chunk_users(plan, int(float(os.environ.get("DMK_BENCH_CHUNK_GIB", "4")) * (1 << 30)))   # ring of 4 GiB chunks (SURVEY.md 8d cfg 5)
-        ring = [plan.alloc_out(chunk) for _ in range(3)]
-        layout = f"ring of 3 x {chunk} users ({chunk * per_user / 2**30:.1f} GiB) output chunks in HBM"
-    # masks once (also gives the algorithmic flop count)
-    masks = plan.alloc_masks()
-    i = 0
-    for a in range(0, plan.n_users, chunk):
-        b = min(a + chunk, plan.n_users)
-        plan.run(ring[i % len(ring)][: b - a], a, b, {k: v[a:b] for k, v in masks.items()})
-        i += 1
-    torch.cuda.synchronize()
-    info = plan.info_from_masks(masks)
-    n_coef, bytes_alg, flops, pbar = algorithmic_counts(s, plan, info)
+    made = {}
 
-    sampler = ClockSampler(torch.cuda.current_device()) if (want_clocks and not os.environ.get("DMK_BENCH_NO_CLOCKS")) else None
-    l0 = _lib.launch_count()
-    if sampler:
-        sampler.start()
-    total_ms, ms = time_plan(plan, ring, chunk, steps, warmup, flush, dist, world)
-    if sampler:
-        sampler.stop_flag.set()
-        sampler.join()
-    launches = (_lib.launch_count() - l0) * steps // (steps + warmup)      # launches inside the timed region
-    return dict(scenario=s, plan=plan, ds=ds, params=params, total_ms=total_ms, ms=ms, n_coef=n_coef, bytes_alg=bytes_alg,
-                flops=flops, pbar=pbar, layout=layout, launches=launches, kernel=_lib.last_kernel(),
-                clocks=sampler.result() if sampler else None, launches_per_step=(plan.n_users + chunk - 1) // chunk)
+    def factory(b):
+        def make():
+            s = made[b] = scenario_for(workload, b, users)
+            ds = dmb.Dataset(dict(s.data))
+            if s.bs_fov is not None:
+                ds.apply_fov(bs_fov=s.bs_fov, ue_fov=s.ue_fov)
+            return ds
+        return make
+
+    cfg = WORKLOADS[workload][0]
+    n_per = users if users is not None else DEFAULT_USERS[cfg]
+    my = scenario_for(workload, rank, 1)                       # parameters of this rank's scenario (cheap: one user)
+    out = {}
+
+    def timed(ds, params):
+        s = made[rank]
+        params = dmb.ChannelGenParameters(s.params)             # per-user rotation of this shard
+        plan, _ = dmb.make_plan(ds, params, times=s.times, doppler=s.doppler_hz, warn=False)
+        per_user = plan.spec.coefs_per_user(plan.n_cols) * 8
+        total_bytes = per_user * plan.n_users
+        free_b, _tot = torch.cuda.mem_get_info()
+        if total_bytes <= min(64 << 30, int(free_b * 0.6)) and not os.environ.get("DMK_BENCH_FORCE_RING"):
+            chunk, ring = plan.n_users, [plan.alloc_out()]
+            layout = f"single [{plan.n_users} users] output tensor ({total_bytes / 2**30:.1f} GiB) rewritten every step"
+        else:
+            chunk = default_chunk_users(plan, int(float(os.environ.get("DMK_BENCH_CHUNK_GIB", "4")) * (1 << 30)))   # ring of 4 GiB chunks (SURVEY.md 8d cfg 5)
+            ring = [plan.alloc_out(chunk) for _ in range(3)]
+            layout = f"ring of 3 x {chunk} users ({chunk * per_user / 2**30:.1f} GiB) output chunks in HBM"
+        # masks once (also gives the algorithmic flop count)
+        masks = plan.alloc_masks()
+        i = 0
+        for a in range(0, plan.n_users, chunk):
+            b = min(a + chunk, plan.n_users)
+            plan.run(ring[i % len(ring)][: b - a], a, b, {k: v[a:b] for k, v in masks.items()})
+            i += 1
+        torch.cuda.synchronize()
+        info = plan.info_from_masks(masks)
+        n_coef, bytes_alg, flops, pbar = algorithmic_counts(s, plan, info)
+        for r in ring:
+            r.fill_(float("nan"))                               # whatever parity_check reads below was written by the timed loop
+
+        sampler = ClockSampler(torch.cuda.current_device()) if (want_clocks and not os.environ.get("DMK_BENCH_NO_CLOCKS")) else None
+        l0 = _lib.launch_count()
+        if sampler:
+            sampler.start()
+        total_ms, ms = time_plan(plan, ring, chunk, steps, warmup, flush, dist, world)
+        if sampler:
+            sampler.stop_flag.set()
+            sampler.join()
+        launches = (_lib.launch_count() - l0) * steps // (steps + warmup)      # launches inside the timed region
+        par = None
+        if parity:
+            try:
+                par = parity_check(s, plan, ring, chunk, info, seed=rank)
+            except Exception as e:  # noqa: BLE001
+                par = {"ok": False, "error": str(e)[:300]}
+        out.update(scenario=s, plan=plan, ds=ds, params=params, total_ms=total_ms, ms=ms, n_coef=n_coef, bytes_alg=bytes_alg,
+                   flops=flops, pbar=pbar, layout=layout, launches=launches, kernel=_lib.last_kernel(), parity=par,
+                   clocks=sampler.result() if sampler else None, launches_per_step=(plan.n_users + chunk - 1) // chunk)
+        return None
+
+    items = compute_channels_sharded([factory(b) for b in range(world)], dmb.ChannelGenParameters(my.params), rank=rank,
+                                     world_size=world, compute=timed, sizes=[n_per] * world)
+    assert len(items) == 1 and items[0][0].bs == rank and items[0][0].n == n_per, items
+    out["shard"] = f"bs/shard {items[0][0].bs}, users [{items[0][0].start}, {items[0][0].stop})"
+    return out
 
 
 def run_e2e(res, steps, rank, world, dist, cap_bytes=4 << 30):
-    """Public-API path with host buffers: pinned H2D of the path matrices + kernels + D2H of H, every step."""
+    """Public-API path with host buffers, every step: pinned H2D of the path matrices + kernels + D2H of H.  Three legs on the
+    same users: `pinned` (caller-provided page-locked result buffer), `default` (the call a user makes, no host_out: the result
+    is allocated inside), and `ceiling` (the D2H copies alone into the same pinned buffer in the same chunks, no kernels) --
+    what the host link of this box delivers when every rank copies at once."""
     import torch
     import deepmimo_b200 as dmb
+    from deepmimo_b200.channels import default_chunk_users
     s, plan = res["scenario"], res["plan"]
     per_user = plan.spec.coefs_per_user(plan.n_cols) * 8
     n = int(max(1, min(plan.n_users, cap_bytes // per_user)))
@@ -276,26 +370,50 @@ def run_e2e(res, steps, rank, world, dist, cap_bytes=4 << 30):
     h2d += (int(np.asarray(prm.ue_antenna.rotation).nbytes) if rot.ndim == 2 else 0) + (int(dop.nbytes) if dop is not None else 0)
     d2h = int(np.prod(shape)) * 8
 
-    def call():
+    def call_pinned():
         return dmb.compute_channels(ds, prm, times=s.times, doppler=dop, host_out=host_out, cache=False, warn=False)
 
-    for _ in range(2):
-        call()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        call()                              # returns after the copy stream has drained (host array complete)
-    torch.cuda.synchronize()
-    dt = time.perf_counter() - t0
-    if world > 1:
-        dist.barrier()
-    return dict(seconds=dt, steps=steps, users=n, coefs_per_step=int(np.prod(shape)), h2d=h2d, d2h=d2h)
+    def call_default():
+        return dmb.compute_channels(ds, prm, times=s.times, doppler=dop, warn=False)     # result allocated inside, cached on ds
+
+    sub_plan, _ = dmb.make_plan(ds, prm, times=s.times, doppler=dop, warn=False)
+    chunk = default_chunk_users(sub_plan)
+    dev_bufs = [sub_plan.alloc_out(min(chunk, n)) for _ in range(2 if n > chunk else 1)]
+    for b in dev_bufs:
+        b.zero_()
+    copy = torch.cuda.Stream()
+
+    def call_ceiling():
+        with torch.cuda.stream(copy):
+            for i, a in enumerate(range(0, n, chunk)):
+                z = min(a + chunk, n)
+                host_out[a:z].copy_(dev_bufs[i % len(dev_bufs)][: z - a], non_blocking=True)
+        copy.synchronize()
+
+    def timed(fn, warm):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            fn()                            # returns after the copy stream has drained (host array complete)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            dist.barrier()
+        return dt
+
+    t_pin = timed(call_pinned, 2)
+    t_ceil = timed(call_ceiling, 1)
+    t_def = timed(call_default, 3)          # the first two calls page-lock their result blocks; afterwards they are reused
+    return dict(seconds=t_pin, seconds_default=t_def, seconds_ceiling=t_ceil, steps=steps, users=n,
+                coefs_per_step=int(np.prod(shape)), h2d=h2d, d2h=d2h)
 
 
 def cpu_baseline(s, workload, cores=1):
-    cfg = WORKLOADS[workload]
+    cfg = WORKLOADS[workload][0]
     n = min(s.n_ue, CPU_BASELINE_USERS[cfg])
     t0 = time.perf_counter()
     H = oracle_call(s, 0, n)
@@ -361,27 +479,64 @@ def gpu_main(args):
     value = total_coefs * args.steps / (total_ms / 1e3)
 
     e2e = run_e2e(res, args.e2e_steps, rank, world, dist)
-    e_t = torch.tensor([e2e["seconds"]], dtype=torch.float64, device="cuda")
-    e_c = torch.tensor([float(e2e["coefs_per_step"])], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(e_t, op=dist.ReduceOp.MAX)
-        dist.all_reduce(e_c, op=dist.ReduceOp.SUM)
-    e2e_value = float(e_c.item()) * e2e["steps"] / float(e_t.item())
+
+    def agg_rate(seconds, coefs_per_step, nsteps):
+        e_t = torch.tensor([seconds], dtype=torch.float64, device="cuda")
+        e_c = torch.tensor([float(coefs_per_step)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(e_t, op=dist.ReduceOp.MAX)
+            dist.all_reduce(e_c, op=dist.ReduceOp.SUM)
+        return float(e_c.item()) * nsteps / float(e_t.item())
+
+    e2e_value = agg_rate(e2e["seconds"], e2e["coefs_per_step"], e2e["steps"])
+    e2e_default = agg_rate(e2e["seconds_default"], e2e["coefs_per_step"], e2e["steps"])
+    e2e_ceiling = agg_rate(e2e["seconds_ceiling"], e2e["coefs_per_step"], e2e["steps"])
+
+    def summarise(r, nsteps):
+        """Per-workload record; times are the max over ranks, rates the whole-job aggregate."""
+        t = torch.tensor([r["total_ms"]], dtype=torch.float64, device="cuda")
+        c = torch.tensor([float(r["n_coef"]), float(r["bytes_alg"]), float(r["flops"])], dtype=torch.float64, device="cuda")
+        ok = torch.tensor([1.0 if (r["parity"] or {}).get("ok") else 0.0, (r["parity"] or {}).get("max_rel_fro", float("nan"))],
+                          dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dist.all_reduce(c, op=dist.ReduceOp.SUM)
+            okmin, errmax = ok[:1].clone(), ok[1:].clone()
+            dist.all_reduce(okmin, op=dist.ReduceOp.MIN)
+            dist.all_reduce(errmax, op=dist.ReduceOp.MAX)
+            ok = torch.cat([okmin, errmax])
+        ms = float(t.item()) / nsteps
+        n_coef, bytes_alg, flops = (float(v) for v in c.tolist())
+        gbs_per_gpu = bytes_alg / world / (ms / 1e3) / 1e9
+        fp32_peak = 2 * 148 * FP32_LANES_PER_SM * sm_max_mhz * 1e6 / 1e12
+        t_write, t_fma = bytes_alg / world / (hbm_peak * 1e9), flops / world / (fp32_peak * 1e12)
+        par = dict(r["parity"] or {})
+        if world > 1:
+            par.update(ok=bool(ok[0].item() > 0.5), max_rel_fro=float(ok[1].item()), ranks=world)
+        return {"coef_per_s": n_coef / (ms / 1e3), "ms_per_step": ms, "users_per_gpu": r["plan"].n_users,
+                "gb_per_s_per_gpu": gbs_per_gpu, "hbm_frac": gbs_per_gpu / hbm_peak,
+                "tflops_fp32_per_gpu": flops / world / (ms / 1e3) / 1e12, "t_min_over_t": max(t_write, t_fma) / (ms / 1e3),
+                "t_min_bound": "fp32" if t_fma > t_write else "hbm", "mean_active_paths": r["pbar"], "layout": r["layout"],
+                "kernel": r["kernel"].split(" ")[0], "shard": r["shard"], "parity": par}
 
     extra = {}
-    if rank == 0 and world == 1 and args.others:
-        for w in [w for w in ("cfg1", "cfg3", "cfg4", "cfg5") if w != args.workload]:
+    if args.others:
+        # the city-scale configuration runs at EVERY N (one base station per rank through the sharding path); the remaining
+        # shapes and the sensitivity variants only at N = 1
+        names = ["cfg5"] if world > 1 else ["cfg1", "cfg3", "cfg4", "cfg5", "cfg2_dense", "cfg5_dense", "cfg3_nofov"]
+        for w in [w for w in names if w != args.workload]:
             try:
-                r = run_workload(w, None, 5, 3, 0, 1, dist, flush, want_clocks=False)
-                ms = r["total_ms"] / 5
-                extra[w] = {"coef_per_s": r["n_coef"] / (ms / 1e3), "ms_per_step": ms, "users": r["plan"].n_users,
-                            "gb_per_s": r["bytes_alg"] / (ms / 1e3) / 1e9, "tflops_fp32": r["flops"] / (ms / 1e3) / 1e12,
-                            "mean_active_paths": r["pbar"], "layout": r["layout"], "kernel": r["kernel"].split(" ")[0]}
+                r = run_workload(w, None, 5, 3, rank, world, dist, flush, want_clocks=False)
+                rec = summarise(r, 5)
+                if rank == 0:
+                    extra[w] = rec
                 del r
                 torch.cuda.empty_cache()
             except Exception as e:  # noqa: BLE001
+                if world > 1:
+                    raise
                 extra[w] = {"error": str(e)[:200]}
-
+    if rank == 0 and world == 1 and args.others:
         # row f3: fused beam amplitude map (16-beam steering_vec codebook) on the headline shape -- H is never written
         try:
             import deepmimo_b200 as dmb
@@ -446,9 +601,17 @@ def gpu_main(args):
                          "t_min_bound": "fp32" if t_fma > t_write else "hbm"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"],
                     "users_per_gpu": e2e["users"], "steps": e2e["steps"],
+                    "ceiling": e2e_ceiling, "frac": e2e_value / e2e_ceiling,
+                    "ceiling_what": "the same D2H copies (same pinned buffer, same chunks, all ranks at once) with no kernels: "
+                                    "what this box's host link delivers",
+                    "d2h_gb_per_s": e2e_value * 8 / 1e9, "ceiling_gb_per_s": e2e_ceiling * 8 / 1e9,
                     "cpu_affinity": (f"rank pinned to the {n_local_cpus} CPUs NVML reports local to its GPU" if n_local_cpus else "not set"),
                     "path": "deepmimo_b200.compute_channels(dataset, params, host_out=pinned): pinned H2D + fused kernel "
                             "(1 GiB chunks, 2 device buffers) + D2H overlapped on a copy stream"},
+            "e2e_default": {"value": e2e_default, "unit": UNIT, "frac_of_pinned": e2e_default / e2e_value,
+                            "path": "deepmimo_b200.compute_channels(dataset, params) -- no host_out: the result is allocated inside "
+                                    "(page-locked up to DMK_PINNED_CAP_GIB, blocks of dropped results are reused) and cached on the dataset"},
+            "parity": res["parity"],
             "gpu_launches": res["launches"],
             "clocks": clocks,
         }
@@ -470,7 +633,7 @@ def reference_main(args):
     if rank != 0:
         return
     import multiprocessing as mp
-    cfg = WORKLOADS[args.workload]
+    cfg = WORKLOADS[args.workload][0]
     cores = os.cpu_count() or 1
     # bounded sample: scale the per-step sample so that K + W steps end within a few minutes
     per = max(1, int(CPU_SAMPLE_USERS[cfg] * min(1.0, 15.0 / (args.steps + args.warmup))))

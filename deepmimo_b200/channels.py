@@ -17,6 +17,7 @@ from __future__ import annotations
 
 import ctypes
 import os
+import threading
 from dataclasses import dataclass, field
 from typing import Any, Iterator, Optional, Tuple
 
@@ -25,6 +26,7 @@ import numpy as np
 from . import _lib
 from .params import ChannelGenParameters, RADIATION_PATTERNS
 
+_RNG_LOCK = threading.Lock()
 PATH_KEYS = ("power", "phase", "delay", "aoa_az", "aoa_el", "aod_az", "aod_el")   # deepmimo/consts.py:188-194
 MAX_COLS = 32   # DMK_MAX_PATHS
 
@@ -432,16 +434,22 @@ def make_plan(dataset, params=None, *, times=None, doppler=None, device=None, se
         dataset.set_channel_params(params)             # validate + deep copy + cache invalidation (dataset.py:197-222)
     else:
         params.validate(n_ue)
-    if seed_numpy_rng:
-        np.random.seed(1001)                           # dataset.py:250 (global RNG side effect kept)
-    spec = parse_spec(params, n_ue, bs_fov=_get(dataset, "bs_fov"), ue_fov=_get(dataset, "ue_fov"), times=times,
-                      seed_numpy_rng=False)
+    with _RNG_LOCK:                                    # seed + draw must not interleave between host threads (MacroDataset over devices)
+        if seed_numpy_rng:
+            np.random.seed(1001)                       # dataset.py:250 (global RNG side effect kept)
+        spec = parse_spec(params, n_ue, bs_fov=_get(dataset, "bs_fov"), ue_fov=_get(dataset, "ue_fov"), times=times,
+                          seed_numpy_rng=False)
     if doppler is None and times is not None:
         doppler = _get(dataset, "doppler")
     plan = ChannelPlan(spec, arrays, doppler=doppler if times is not None else None, device=device)
     if warn and spec.freq_domain and isinstance(arrays["delay"], np.ndarray):
         delay_overflow_warning(arrays["delay"], spec, spec.n_paths_eff(plan.n_cols))
     return plan, params
+
+
+def pinned_cap_bytes() -> int:
+    """Largest result `compute_channels(host_memory='auto')` allocates as page-locked memory."""
+    return int(float(os.environ.get("DMK_PINNED_CAP_GIB", "16")) * (1 << 30))
 
 
 def default_chunk_users(plan: ChannelPlan, budget_bytes: int = 1 << 30) -> int:
@@ -476,7 +484,7 @@ def iter_channels(plan: ChannelPlan, chunk_users: Optional[int] = None, n_buffer
 
 def compute_channels(dataset, params=None, *, out: str = "numpy", device=None, chunk_users: Optional[int] = None,
                      times=None, doppler=None, return_info: bool = False, cache: bool = True, host_out=None,
-                     seed_numpy_rng: bool = True, warn: bool = True, carrier_freq=None):
+                     seed_numpy_rng: bool = True, warn: bool = True, carrier_freq=None, host_memory: str = "auto"):
     """Compute MIMO channels for every user of `dataset` on the GPU.
 
     Same arguments, layout and caching behaviour as the reference's `Dataset.compute_channels`:
@@ -487,6 +495,9 @@ def compute_channels(dataset, params=None, *, out: str = "numpy", device=None, c
     cached); `times` [T] appends a trailing snapshot axis with per-path Doppler `doppler` [n, P] Hz (or
     `dataset['doppler']`) -- row a11 of SURVEY.md; `return_info=True` also returns the masks
     (`ChannelInfo`); `host_out` is an optional preallocated (ideally pinned) complex64 tensor/array.
+    `host_memory`: where a result allocated here lives -- 'pinned' (page-locked, D2H at PCIe line rate), 'pageable' (plain NumPy
+    memory like the reference's; D2H staged through two pinned chunk buffers and a host copy thread) or 'auto' (pinned up to
+    `pinned_cap_bytes()`, default 16 GiB or DMK_PINNED_CAP_GIB, and pageable beyond that or when page-locking fails).
     `params.enable_doppler = 1` applies v3's constant per-path Doppler phase when the dataset carries `doppler_vel` /
     `doppler_acc` (see `constant_doppler_shift`); the output keeps the reference's 4-D shape.
     """
@@ -515,36 +526,78 @@ def compute_channels(dataset, params=None, *, out: str = "numpy", device=None, c
 
     # ---- host output: chunked kernels on the compute stream, D2H on a copy stream, two device buffers
     shape = plan.out_shape()
+    nbytes = int(np.prod(shape)) * 8
+    staged = False                       # True: destination is pageable memory, D2H goes through two pinned chunk buffers
     if host_out is None:
-        host_t = torch.empty(shape, dtype=torch.complex64, pin_memory=True)
+        mode = host_memory
+        if mode not in ("auto", "pinned", "pageable"):
+            raise ValueError("host_memory must be 'auto', 'pinned' or 'pageable'")
+        if mode == "auto":
+            mode = "pinned" if nbytes <= pinned_cap_bytes() else "pageable"
+        host_t = None
+        if mode == "pinned":
+            try:
+                # torch's caching host allocator keeps page-locked blocks of dropped results: a loop that rebinds its result
+                # alternates between two blocks and pins nothing after the second call
+                host_t = torch.empty(shape, dtype=torch.complex64, pin_memory=True)
+            except RuntimeError:
+                if host_memory == "pinned":
+                    raise
+        if host_t is None:               # like the reference: plain pageable memory, no page-locked block stays held
+            host_t = torch.from_numpy(np.empty(shape, dtype=np.complex64))
+            staged = True
     else:
         host_t = host_out if isinstance(host_out, torch.Tensor) else torch.from_numpy(host_out)
         if squeeze_time and host_t.dim() == len(shape) - 1:
             host_t = host_t.unsqueeze(-1)
         if tuple(host_t.shape) != shape or host_t.dtype != torch.complex64:
             raise ValueError(f"host_out must be complex64 of shape {shape}")
-    if n and int(np.prod(shape)):
-        chunk = default_chunk_users(plan) if chunk_users is None else max(1, int(chunk_users))
+        staged = not host_t.is_pinned()
+    if n and nbytes:
+        chunk = default_chunk_users(plan, (256 << 20) if staged else (1 << 30)) if chunk_users is None else max(1, int(chunk_users))
         compute = torch.cuda.current_stream(plan.device)
         copy = torch.cuda.Stream(device=plan.device)
         bufs = [plan.alloc_out(min(chunk, n)) for _ in range(2 if n > chunk else 1)]
         done = [None] * len(bufs)
-        for i, start in enumerate(range(0, n, chunk)):
-            stop = min(start + chunk, n)
-            b = i % len(bufs)
-            if done[b] is not None:
-                compute.wait_event(done[b])              # buffer b has been drained by the copy stream
-            buf = bufs[b][: stop - start]
-            sub = None if masks is None else {k: v[start:stop] for k, v in masks.items()}
-            plan.run(buf, start, stop, sub, stream=compute)
-            ev = torch.cuda.Event()
-            ev.record(compute)
-            copy.wait_event(ev)
-            with torch.cuda.stream(copy):
-                host_t[start:stop].copy_(buf, non_blocking=True)
-                done[b] = torch.cuda.Event()
-                done[b].record(copy)
-        copy.synchronize()
+        stage = [torch.empty(bufs[0].shape, dtype=torch.complex64, pin_memory=True) for _ in bufs] if staged else None
+        landed = [None] * len(bufs)      # staged: future of the host thread that empties stage[b]
+        pool = None
+        if staged:
+            from concurrent.futures import ThreadPoolExecutor
+            pool = ThreadPoolExecutor(1)
+            host_np = host_t.numpy()
+
+        def unload(b, start, stop, ev):
+            ev.synchronize()
+            np.copyto(host_np[start:stop], stage[b][: stop - start].numpy())
+
+        try:
+            for i, start in enumerate(range(0, n, chunk)):
+                stop = min(start + chunk, n)
+                b = i % len(bufs)
+                if done[b] is not None:
+                    compute.wait_event(done[b])          # buffer b has been drained by the copy stream
+                buf = bufs[b][: stop - start]
+                sub = None if masks is None else {k: v[start:stop] for k, v in masks.items()}
+                plan.run(buf, start, stop, sub, stream=compute)
+                ev = torch.cuda.Event()
+                ev.record(compute)
+                copy.wait_event(ev)
+                if staged and landed[b] is not None:
+                    landed[b].result()                   # the host thread has emptied stage[b]
+                with torch.cuda.stream(copy):
+                    (stage[b][: stop - start] if staged else host_t[start:stop]).copy_(buf, non_blocking=True)
+                    done[b] = torch.cuda.Event()
+                    done[b].record(copy)
+                if staged:
+                    landed[b] = pool.submit(unload, b, start, stop, done[b])
+            for f in landed:
+                if f is not None:
+                    f.result()
+            copy.synchronize()
+        finally:
+            if pool is not None:
+                pool.shutdown(wait=True)
     H = host_t.numpy() if host_out is None or isinstance(host_out, torch.Tensor) else host_out
     if squeeze_time:
         H = H[..., 0]

@@ -196,6 +196,31 @@ class MacroDataset:
     def append(self, dataset: Dataset) -> None:
         self.datasets.append(dataset)
 
+    def compute_channels(self, params: Optional[ChannelGenParameters] = None, *, devices=None, **kwargs):
+        """Per-child `compute_channels` (dataset.py:939-950: a list of arrays, or the single result).
+
+        `devices` (e.g. ["cuda:0", "cuda:1"]) spreads the children round-robin over several GPUs of this process, one
+        host thread per device: base stations are independent, so there is no exchange between them.  Without
+        it the children run one after the other on the current device, like the reference's loop."""
+        if not devices or len(self.datasets) <= 1:
+            if devices:
+                kwargs.setdefault("device", devices[0])
+            res = [d.compute_channels(params, **kwargs) for d in self.datasets]
+            return res[0] if len(res) == 1 else res
+        from concurrent.futures import ThreadPoolExecutor
+        devices = list(devices)
+
+        def worker(slot):
+            return [(i, self.datasets[i].compute_channels(params, device=devices[slot], **kwargs))
+                    for i in range(slot, len(self.datasets), len(devices))]
+
+        out = [None] * len(self.datasets)
+        with ThreadPoolExecutor(len(devices)) as pool:
+            for part in pool.map(worker, range(len(devices))):
+                for i, h in part:
+                    out[i] = h
+        return out
+
     def __getattr__(self, name):
         if name.startswith("__") or name == "datasets":
             raise AttributeError(name)

@@ -86,12 +86,15 @@ def slice_params(params, n_ue: int, start: int, stop: int):
 
 
 def compute_channels_sharded(datasets, params, *, rank: Optional[int] = None, world_size: Optional[int] = None,
-                             compute: Optional[Callable] = None, **kwargs):
+                             compute: Optional[Callable] = None, sizes: Optional[Sequence[int]] = None, **kwargs):
     """Compute this rank's share of the channels of one or several base-station datasets.
 
-    `datasets`: a Dataset, a MacroDataset or a list of Datasets.  Returns a list of
-    (ShardItem, H) for the calling rank, H as returned by `compute` (default:
-    deepmimo_b200.compute_channels with out='torch', i.e. a CUDA tensor that stays on this GPU).
+    `datasets`: a Dataset, a MacroDataset or a list of Datasets.  A list entry may also be a zero-argument callable that
+    returns the Dataset: with `sizes` (users per base station) given, a rank only materialises the base stations it owns a
+    part of -- at city scale (8 x 200 k users) no rank loads the other ranks' ray data.  Returns a list of
+    (ShardItem, H) for the calling rank, H as returned by `compute(dataset_slice, params_slice, **kwargs)` (default:
+    deepmimo_b200.compute_channels with out='torch', i.e. a CUDA tensor that stays on this GPU; a streaming consumer passes
+    its own function, e.g. one that walks `iter_channels`).
     A (3,2) random UE rotation is drawn for the whole base station first (same values as the
     unsharded call) and then sliced.
     """
@@ -100,8 +103,13 @@ def compute_channels_sharded(datasets, params, *, rank: Optional[int] = None, wo
         datasets = datasets.datasets
     elif not isinstance(datasets, (list, tuple)):
         datasets = [datasets]
+    datasets = list(datasets)
     rank, world_size = rank_world(rank, world_size)
-    sizes = [int(np.asarray(d["power"]).shape[0]) for d in datasets]
+    if sizes is None:
+        datasets = [d() if callable(d) and not hasattr(d, "keys") else d for d in datasets]
+        sizes = [int(np.asarray(d["power"]).shape[0]) for d in datasets]
+    elif len(sizes) != len(datasets):
+        raise ValueError("sizes must have one entry per dataset")
     plan = shard_plan(sizes, world_size)[rank]
     if compute is None:
         kwargs.setdefault("out", "torch")
@@ -110,7 +118,11 @@ def compute_channels_sharded(datasets, params, *, rank: Optional[int] = None, wo
     results = []
     for it in plan:
         ds = datasets[it.bs]
+        if callable(ds) and not hasattr(ds, "keys"):
+            ds = datasets[it.bs] = ds()
         n = sizes[it.bs]
+        if int(np.asarray(ds["power"]).shape[0]) != n:
+            raise ValueError(f"dataset {it.bs} has {int(np.asarray(ds['power']).shape[0])} users, sizes says {n}")
         p = params.deepcopy()
         p.validate(n)
         rot = p["ue_antenna"].get("rotation")
@@ -118,12 +130,14 @@ def compute_channels_sharded(datasets, params, *, rank: Optional[int] = None, wo
             np.random.seed(1001)
             _, per_user = resolve_ue_rotation(rot, n, seed_numpy_rng=False)
             p["ue_antenna"]["rotation"] = per_user
-        sub = slice_dataset(ds, it.start, it.stop)
-        for key in ("bs_fov", "ue_fov"):
-            v = ds.get(key) if hasattr(ds, "get") else None
-            if v is not None:
-                sub[key] = v
-        results.append((it, compute(sub, slice_params(p, n, it.start, it.stop), **kwargs)))
+        whole = it.start == 0 and it.stop == n
+        sub = ds if whole else slice_dataset(ds, it.start, it.stop)
+        if not whole:
+            for key in ("bs_fov", "ue_fov"):
+                v = ds.get(key) if hasattr(ds, "get") else None
+                if v is not None:
+                    sub[key] = v
+        results.append((it, compute(sub, p if whole else slice_params(p, n, it.start, it.stop), **kwargs)))
     return results
 
 

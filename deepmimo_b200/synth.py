@@ -18,16 +18,19 @@ C_LIGHT = 299792458.0
 
 
 def make_paths(n_ue: int, seed: int, *, n_sc: int = 512, bandwidth: float = 10e6, n_cols: int = MAX_PATHS,
-               clip_frac: float = 0.005, zero_frac: float = 0.10) -> dict:
+               clip_frac: float = 0.005, zero_frac: float = 0.10, dense: bool = False) -> dict:
     """Path matrices for `n_ue` users (SURVEY.md 8d "Synthetic inputs").
 
     n_paths: `zero_frac` users with 0 paths, else U{1..n_cols}; power dBW U(-160,-60) sorted
     descending; phase deg U(-180,180); delay s U(3e-8,4e-6) ascending, `clip_frac` of valid
     paths moved to U(1,1.5)*N/B (exercises the delay clip); el deg U(0,180); az deg U(-180,180).
+    `dense`: every user has all `n_cols` paths (the P = 25 case north_star's hypothesis H4 reasons about).
     """
     rng = np.random.default_rng(seed)
     n_paths = rng.integers(1, n_cols + 1, n_ue)
     n_paths[rng.random(n_ue) < zero_frac] = 0
+    if dense:
+        n_paths[:] = n_cols
     pad = np.arange(n_cols)[None, :] >= n_paths[:, None]
 
     def fill(lo, hi):
@@ -97,27 +100,41 @@ def doppler_from_velocity(data: dict, seed: int, carrier_hz: float, vmax: float 
     return fd.astype(np.float32)
 
 
-def scenario(cfg: int, n_ue: Optional[int] = None, *, bs_index: int = 0, shard: int = 0) -> Scenario:
+def scenario(cfg: int, n_ue: Optional[int] = None, *, bs_index: int = 0, shard: int = 0, dense: bool = False,
+             fov: bool = True) -> Scenario:
     """The five BASELINE.json configurations, optionally with fewer users.
 
     `shard` offsets every seed by 100*shard (distinct data per rank in weak-scaling runs); `bs_index`
-    selects the base station of config 5 (seed 1005 + 10*b)."""
+    selects the base station of config 5 (seed 1005 + 10*b).  Sensitivity variants for the benchmark: `dense` gives every user
+    all 25 paths, `fov=False` drops the field-of-view filter of config 3 (its dipole patterns stay)."""
     so = 100 * shard
+    s = _scenario(cfg, n_ue, bs_index, so, dense)
+    if not fov:
+        s.bs_fov = s.ue_fov = None
+        s.name += "_nofov"
+        s.notes += " -- FoV filter off"
+    if dense:
+        s.name += "_dense"
+        s.notes += " -- dense: 25 valid paths for every user"
+    return s
+
+
+def _scenario(cfg: int, n_ue: Optional[int], bs_index: int, so: int, dense: bool) -> Scenario:
     if cfg == 1:
         n = 80_000 if n_ue is None else n_ue
-        d = make_paths(n, 1001 + so, n_sc=64, bandwidth=10e6)
+        d = make_paths(n, 1001 + so, n_sc=64, bandwidth=10e6, dense=dense)
         return Scenario("cfg1_asu_8x1_K64", d, _params([8, 1], [1, 1], 64, 64, 10e6),
                         notes="1 BS, 8x1 ULA, 1 UE antenna, N=K=64, B=10 MHz, FD, isotropic")
     if cfg == 2:
         n = 4096 if n_ue is None else n_ue
-        d = make_paths(n, 1002 + so, n_sc=512, bandwidth=50e6)
+        d = make_paths(n, 1002 + so, n_sc=512, bandwidth=50e6, dense=dense)
         ue_rot = np.random.default_rng(42 + so).uniform(0, 45, (n, 3))
         return Scenario("cfg2_32x8_2x2_K512", d,
                         _params([32, 8], [2, 2], 512, 512, 50e6, bs_rot=[30, 40, 30], ue_rot=ue_rot),
                         notes="32x8 rotated BS UPA + 2x2 UE (per-user rotation), N=K=512, B=50 MHz, 3.5 GHz, isotropic")
     if cfg == 3:
         n = 8192 if n_ue is None else n_ue
-        d = make_paths(n, 1003 + so, n_sc=1024, bandwidth=100e6)
+        d = make_paths(n, 1003 + so, n_sc=1024, bandwidth=100e6, dense=dense)
         return Scenario("cfg3_64x4_dipole_fov_K1024", d,
                         _params([64, 4], [1, 1], 1024, 1024, 100e6, bs_rot=[0, 30, -135],
                                 bs_pat="halfwave-dipole", ue_pat="halfwave-dipole"),
@@ -125,7 +142,7 @@ def scenario(cfg: int, n_ue: Optional[int] = None, *, bs_index: int = 0, shard: 
                         notes="64x4 UPA, half-wave dipole, BS FoV [140,120], UE FoV [90,80], N=K=1024, B=100 MHz")
     if cfg == 4:
         n = 50_000 if n_ue is None else n_ue
-        d = make_paths(n, 1004 + so, n_sc=512, bandwidth=10e6)
+        d = make_paths(n, 1004 + so, n_sc=512, bandwidth=10e6, dense=dense)
         fd = doppler_from_velocity(d, 2004 + so, 3.5e9)
         return Scenario("cfg4_td_doppler_T16", d,
                         _params([8, 4], [2, 1], 512, 1, 10e6, freq_domain=0),
@@ -133,7 +150,7 @@ def scenario(cfg: int, n_ue: Optional[int] = None, *, bs_index: int = 0, shard: 
                         notes="time domain, 8x4 BS, 2x1 UE, 25 path slots, 16 snapshots of 1 ms, Doppler from UE velocity")
     if cfg == 5:
         n = 200_000 if n_ue is None else n_ue
-        d = make_paths(n, 1005 + 10 * bs_index + so, n_sc=1024, bandwidth=100e6)
+        d = make_paths(n, 1005 + 10 * bs_index + so, n_sc=1024, bandwidth=100e6, dense=dense)
         return Scenario(f"cfg5_city_bs{bs_index}_8x8_K1024", d, _params([8, 8], [1, 1], 1024, 1024, 100e6),
                         notes="city-scale shard: one BS x 200k users, 8x8 BS UPA, 1 UE antenna, N=K=1024, B=100 MHz")
     raise ValueError(f"unknown config {cfg}")

@@ -47,3 +47,47 @@ def oracle_kwargs_from_params(p: dict, bs_fov=None, ue_fov=None) -> dict:
                 bs_fov=bs_fov, ue_fov=ue_fov, num_paths=p["num_paths"], freq_domain=bool(p["freq_domain"]),
                 subcarriers=p["ofdm"]["subcarriers"], selected_subcarriers=p["ofdm"]["selected_subcarriers"],
                 bandwidth=p["ofdm"]["bandwidth"], rx_filter=int(p["ofdm"].get("rx_filter", 0)))
+
+
+def scenario_subset(s, idx):
+    """The users `idx` of a synth.Scenario as (data, oracle kwargs, doppler): every per-user array follows the selection."""
+    idx = np.asarray(idx)
+    n = s.n_ue
+    data = {k: (v[idx] if getattr(v, "shape", (0,))[0] == n and k != "tx_pos" else v) for k, v in s.data.items()}
+    kw = oracle_kwargs_from_params(s.params, s.bs_fov, s.ue_fov)
+    rot = np.asarray(kw["ue_rotation"])
+    if rot.ndim == 2 and rot.shape[0] == n:
+        kw["ue_rotation"] = rot[idx]
+    dop = None if s.doppler_hz is None else s.doppler_hz[idx]
+    return data, kw, dop
+
+
+def _oracle_job(args):
+    from oracle import channel_oracle as orc
+    data, kw, dop, times = args
+    o = orc.compute_channels(data, **kw, doppler_hz=dop, times=times)
+    return o["H"], o["valid"], o["clip"], o["fov_mask"]
+
+
+def oracle_on_users(s, idx, procs=None):
+    """Oracle channels + masks of the users `idx` (any order) of scenario `s`, spread over `procs` processes (the NumPy path is
+    single-threaded like the reference's per-user loop; default: all host cores, at most one job per 8 users)."""
+    import multiprocessing as mp
+    import os
+    idx = np.asarray(idx)
+    procs = min(os.cpu_count() or 1, 32, max(1, len(idx) // 8)) if procs is None else procs
+    parts = [p for p in np.array_split(np.arange(len(idx)), procs) if len(p)]
+    jobs = []
+    for p in parts:
+        data, kw, dop = scenario_subset(s, idx[p])
+        jobs.append((data, kw, dop, s.times))
+    if len(jobs) == 1:
+        res = [_oracle_job(jobs[0])]
+    else:
+        with mp.get_context("fork").Pool(len(jobs)) as pool:
+            res = pool.map(_oracle_job, jobs)
+    H = np.concatenate([r[0] for r in res])
+    valid = np.concatenate([r[1] for r in res])
+    clip = np.concatenate([r[2] for r in res])
+    fov = None if res[0][3] is None else np.concatenate([r[3] for r in res])
+    return dict(H=H, valid=valid, clip=clip, fov_mask=fov)
