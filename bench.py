@@ -270,25 +270,23 @@ def run_workload(workload, users, steps, warmup, rank, world, dist, flush, want_
     from deepmimo_b200.channels import default_chunk_users
     from deepmimo_b200.sharding import compute_channels_sharded
 
-    made = {}
+    cfg = WORKLOADS[workload][0]
+    n_per = users if users is not None else DEFAULT_USERS[cfg]
+    made = {rank: scenario_for(workload, rank, users)}          # this rank's base station / shard; the others are never built here
 
     def factory(b):
         def make():
-            s = made[b] = scenario_for(workload, b, users)
+            s = made[b] if b in made else made.setdefault(b, scenario_for(workload, b, users))
             ds = dmb.Dataset(dict(s.data))
             if s.bs_fov is not None:
                 ds.apply_fov(bs_fov=s.bs_fov, ue_fov=s.ue_fov)
             return ds
         return make
 
-    cfg = WORKLOADS[workload][0]
-    n_per = users if users is not None else DEFAULT_USERS[cfg]
-    my = scenario_for(workload, rank, 1)                       # parameters of this rank's scenario (cheap: one user)
     out = {}
 
     def timed(ds, params):
         s = made[rank]
-        params = dmb.ChannelGenParameters(s.params)             # per-user rotation of this shard
         plan, _ = dmb.make_plan(ds, params, times=s.times, doppler=s.doppler_hz, warn=False)
         per_user = plan.spec.coefs_per_user(plan.n_cols) * 8
         total_bytes = per_user * plan.n_users
@@ -333,7 +331,7 @@ def run_workload(workload, users, steps, warmup, rank, world, dist, flush, want_
                    clocks=sampler.result() if sampler else None, launches_per_step=(plan.n_users + chunk - 1) // chunk)
         return None
 
-    items = compute_channels_sharded([factory(b) for b in range(world)], dmb.ChannelGenParameters(my.params), rank=rank,
+    items = compute_channels_sharded([factory(b) for b in range(world)], dmb.ChannelGenParameters(made[rank].params), rank=rank,
                                      world_size=world, compute=timed, sizes=[n_per] * world)
     assert len(items) == 1 and items[0][0].bs == rank and items[0][0].n == n_per, items
     out["shard"] = f"bs/shard {items[0][0].bs}, users [{items[0][0].start}, {items[0][0].stop})"

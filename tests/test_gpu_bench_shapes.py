@@ -31,11 +31,11 @@ def _sample_check(s, H_t, masks, idx, what):
 
 
 def test_cfg2_bench_launch_shape_matches_oracle():
-    """cfg2 at 1 024 users in ONE launch: ksplit = 1 and several users per persistent CTA, like the 4 096-user bench launch."""
+    """cfg2 at 1 280 users in ONE launch: ksplit = 1 and several users per persistent CTA, like the 4 096-user bench launch."""
     import deepmimo_b200 as dmb
     from deepmimo_b200 import _lib
     from deepmimo_b200.synth import scenario
-    n = 1024
+    n = 1280
     s = scenario(2, n)
     plan, _ = dmb.make_plan(make_dataset(dmb, s), dmb.ChannelGenParameters(s.params), warn=False)
     H, masks = plan.alloc_out(), plan.alloc_masks()
@@ -45,7 +45,7 @@ def test_cfg2_bench_launch_shape_matches_oracle():
     f = _kernel_fields(k)
     assert k.startswith("fd_ws_kernel") and f["ksplit"] == 1 and f["items"] == n and f["items"] > 2 * f["grid"], k
     idx = np.sort(np.random.default_rng(7).choice(n, 256, replace=False))
-    err = _sample_check(s, H, masks, idx, "cfg2 x 1024 users")
+    err = _sample_check(s, H, masks, idx, f"cfg2 x {n} users")
     print(f"cfg2 x {n} users [{k}]: 256-user sample, max per-user rel. Frobenius {err:.2e}")
 
 
