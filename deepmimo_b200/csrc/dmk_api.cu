@@ -126,7 +126,7 @@ int check_arrays(const float* a, const float* b, const float* c, const float* e,
 // one-time opt-in to > 48 KB of dynamic shared memory is tracked per device: a process may call the library on
 // cuda:0 and then on cuda:1 (compute_channels(device=...), MacroDataset over several GPUs).
 constexpr int kMaxDevices = 64;
-constexpr int kSmemSmall = 72 * 1024, kSmemWs1 = 114 * 1024, kSmemWs4 = 220 * 1024, kSmemTc = 112 * 1024,
+constexpr int kSmemSmall = 72 * 1024, kSmemSmall2 = 100 * 1024, kSmemWs1 = 114 * 1024, kSmemWs4 = 220 * 1024, kSmemTc = 112 * 1024,
               kSmemFast = 110 * 1024, kSmemTile = 200 * 1024;
 struct DeviceState { bool ready = false; int sms = 0; };
 DeviceState g_dev[kMaxDevices];
@@ -148,6 +148,9 @@ int device_state(const DeviceState*& out)
         if (e == cudaSuccess) e = cudaFuncSetAttribute(fd_small_kernel<4>, a, kSmemSmall);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(fd_small_kernel<8>, a, kSmemSmall);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(fd_small_kernel<16>, a, kSmemSmall);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(fd_small2_kernel<4>, a, kSmemSmall2);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(fd_small2_kernel<8>, a, kSmemSmall2);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(fd_small2_kernel<16>, a, kSmemSmall2);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(fd_ws_kernel<1>, a, kSmemWs1);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(fd_ws_kernel<4>, a, kSmemWs4);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(fd_tc_kernel, a, kSmemTc);
@@ -275,11 +278,54 @@ int dmk_channels_fd(const dmk_desc* desc, const float* power_dbw, const float* p
     if (ksplit < 1) ksplit = 1;
     const long long grid = n_users * ksplit;
     if (grid > 0x7fffffffLL) return fail(DMK_ERR_INVALID_ARG, "grid too large: split the user range");
-    // Small arrays (M <= 16): one warp per user, see dmk_fd_small.cuh.  DMK_FD_KERNEL=small forces it where eligible.
+    // Small arrays (M <= 16): warp-level kernels, see dmk_fd_small.cuh.  Default: the densely packed fd_small2_kernel;
+    // DMK_KERNEL_SMALL1 keeps the round-1 one-warp-per-user kernel for A/B timing.
     {
-        SmallCfg sc;
         const int pc = d.P > 0 ? d.P : 1;
         const int mt = d.M <= 4 ? 4 : (d.M <= 8 ? 8 : 16);
+        const bool small_shape = affine && !d.has_time_axis && div_ok && d.M <= 16 && d.K <= 4096;
+        const bool small_wanted = !want_tile && !want_ffma && !want_tc;
+        if (small_shape && small_wanted && hint != DMK_KERNEL_SMALL1) {
+            Small2Cfg sc;
+            memset(&sc, 0, sizeof(sc));
+            if (d.K <= 64)       { sc.n0 = 8;  sc.log0 = 3; sc.n1 = (d.K + 7) / 8;   sc.n2 = 0; }
+            else if (d.K <= 256) { sc.n0 = 16; sc.log0 = 4; sc.n1 = (d.K + 15) / 16; sc.n2 = 0; }
+            else                 { sc.n0 = 16; sc.log0 = 4; sc.n1 = 16;              sc.n2 = (d.K + 255) / 256; }
+            const int n_seed = sc.n0 + sc.n1 + sc.n2;
+            sc.strideA = mt * 16 + 16;                         // +16 B: the 32 lanes of a chain round store to 32 different pool rows
+            sc.strideW = n_seed | 1;
+            const int per_path = sc.strideA + sc.strideW * 8;
+            const int budget = 18 * 1024;                       // 12 warps per SM
+            int cap = (budget - 256) / per_path;
+            if (cap > 64) cap = 64;
+            if (cap < d.P0) cap = d.P0;                         // one user always fits
+            sc.cap = cap;
+            size_t off = 0;
+            auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 15) & ~size_t(15); return (int)o; };
+            sc.off_A    = take((size_t)cap * sc.strideA);
+            sc.off_W    = take((size_t)cap * sc.strideW * 8);
+            sc.off_list = take((size_t)cap);
+            sc.off_meta = take((size_t)(2 * kS2Window + 1) * sizeof(int));
+            sc.warp_bytes = (int)off;
+            sc.mul_mt = cfg.mul_mt; sc.mul_bs0 = cfg.mul_bs0;
+            // contiguous users per warp: 16 when that still leaves >= 2 waves of CTAs, fewer for short user ranges
+            long long upw = n_users / (2LL * 3 * dev->sms * kS2Warps);
+            upw = upw < 4 ? 4 : (upw > 16 ? 16 : upw);
+            sc.users_per_warp = (int)upw;
+            const size_t small_smem = off * kS2Warps;
+            const long long sgrid = (n_users + upw * kS2Warps - 1) / (upw * kS2Warps);
+            if (small_smem <= (size_t)kSmemSmall2 && sgrid <= 0x7fffffffLL) {
+                if (mt == 4)      fd_small2_kernel<4><<<(unsigned)sgrid, kS2Warps * 32, small_smem, st>>>(d, sc);
+                else if (mt == 8) fd_small2_kernel<8><<<(unsigned)sgrid, kS2Warps * 32, small_smem, st>>>(d, sc);
+                else              fd_small2_kernel<16><<<(unsigned)sgrid, kS2Warps * 32, small_smem, st>>>(d, sc);
+                cudaError_t e = cudaGetLastError();
+                if (e != cudaSuccess) return cuda_fail(e, "fd_small2_kernel launch");
+                g_launches.fetch_add(1);
+                snprintf(g_kernel, sizeof(g_kernel), "fd_small2_kernel<%d rows,dense pairs> grid=%lld users/warp=%lld cap=%d smem=%zu", mt, sgrid, upw, cap, small_smem);
+                return DMK_OK;
+            }
+        }
+        SmallCfg sc;
         size_t off = 0;
         auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 15) & ~size_t(15); return (int)o; };
         sc.pcap = pc;
@@ -294,8 +340,7 @@ int dmk_channels_fd(const dmk_desc* desc, const float* power_dbw, const float* p
         sc.warp_bytes = (int)off;
         sc.mul_mt = cfg.mul_mt; sc.mul_bs0 = cfg.mul_bs0;
         const size_t small_smem = off * kSmallWarps;
-        const bool small_ok = affine && !d.has_time_axis && div_ok && d.M <= 16 && d.K <= 4096 && small_smem <= (size_t)kSmemSmall;
-        const bool use_small = small_ok && !want_tile && !want_ffma && !want_tc;
+        const bool use_small = small_shape && small_wanted && small_smem <= (size_t)kSmemSmall;
         if (use_small) {
             const long long sgrid = (n_users + kSmallWarps - 1) / kSmallWarps;
             if (sgrid > 0x7fffffffLL) return fail(DMK_ERR_INVALID_ARG, "grid too large: split the user range");

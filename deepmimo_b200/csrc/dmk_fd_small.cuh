@@ -157,4 +157,216 @@ fd_small_kernel(const __grid_constant__ DevDesc d, const __grid_constant__ Small
     }
 }
 
+
+// =================================================================================================
+// fd_small2_kernel -- small arrays (M <= 16), densely packed (round 2).
+//
+// ncu on fd_small_kernel (profiles/r01_ncu_fd_small_cfg1.txt) counted ~3 000 warp-instructions per user for 4 KB of output: the
+// float64 chains ran with lanes = path COLUMNS (25 of 32 lanes, of which only the ~12 valid ones do useful work), and the per-user
+// tables were filled by loops whose lanes spent a third of their instructions on index arithmetic.  Here a warp walks a contiguous
+// range of users in passes:
+//   1. window: the power rows of the next 8 users (one coalesced load each) -> per-user bit masks of the columns whose chain must
+//      run (valid power; every column when an FoV mask is built, because the mask is defined for NaN-power columns too);
+//      valid_mask and the default fov/clip entries of the other columns are written here;
+//   2. as many whole users as fit the warp's table pool (`cap` paths) are taken, their (user, column) pairs listed densely;
+//   3. chain rounds, lane = dense pair: the three float64 chains + combine, fov/clip masks, then -- still in that lane -- the path's
+//      steering column A[0..M) (gain folded in, stored (re, re, im, im) for the FFMA2 operand modifiers) and its delay-phasor
+//      seed levels go straight into the pool slot (user's first slot + rank among the user's contributing paths, in column order);
+//   4. per user, lanes = column pairs: W entries from the seed levels (2-3 complex multiplies), 2 FFMA2 per complex MAC, rows in
+//      registers, 512 contiguous bytes per row store.
+// Every phasor that goes into a table has its phase reduced in float64 (phasor_cycles); W is a product of <= 3 of them.
+// Pool rows are padded to an odd multiple of the store width so that the 32 lanes of a round never share a bank.
+// =================================================================================================
+constexpr int kS2Warps  = 4;
+constexpr int kS2Window = 8;          // users examined per pass
+constexpr int kS2MaxSeeds = 48;       // 16 + 16 + 16 (K <= 4096)
+
+struct Small2Cfg {
+    int warp_bytes;                   // bytes of a warp's shared-memory slice
+    int off_A, off_W, off_list, off_meta;
+    int cap;                          // table pool capacity in paths (>= n_cols)
+    int strideA;                      // bytes between pool rows of A: MT * 16 + 16
+    int strideW;                      // float2 between pool rows of the seed levels: n_seed | 1
+    int n0, log0, n1, n2;             // seed levels: column c -> L0[c & (n0-1)], L1[(c >> log0) & 15], L2[c >> 8] (n2 == 0: two levels)
+    int users_per_warp;
+    unsigned mul_mt, mul_bs0;
+};
+
+template <int MT>
+__global__ void __launch_bounds__(kS2Warps * 32, 3)
+fd_small2_kernel(const __grid_constant__ DevDesc d, const __grid_constant__ Small2Cfg cfg)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ float4 s_coef[16];                 // element m -> (y_t, z_t, y_r, z_r) panel coordinates
+    __shared__ double s_kseed[kS2MaxSeeds];       // seed entry e -> subcarrier offset whose delay phasor it holds
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n_seed = cfg.n0 + cfg.n1 + cfg.n2;
+    if (tid < 16) {
+        float4 c = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (tid < d.M) {
+            const int r = tid / d.Mt, t = tid - r * d.Mt;
+            c = make_float4((float)(t % d.bs0), (float)(t / d.bs0), (float)(r % d.ue0), (float)(r / d.ue0));
+        }
+        s_coef[tid] = c;
+    }
+    if (tid >= 32 && tid < 32 + n_seed) {
+        const int e = tid - 32;
+        double k;
+        if (e < cfg.n0)               k = (double)d.subc_step * e;
+        else if (e < cfg.n0 + cfg.n1) k = (double)d.subc_step * cfg.n0 * (e - cfg.n0) + (cfg.n2 == 0 ? (double)d.subc_start : 0.0);
+        else                          k = (double)d.subc_step * 256.0 * (e - cfg.n0 - cfg.n1) + (double)d.subc_start;
+        s_kseed[e] = k;
+    }
+    __syncthreads();                              // the only CTA-wide barrier: warps are independent from here on
+
+    unsigned char* wsm = smem_raw + warp * cfg.warp_bytes;
+    unsigned char* sA   = wsm + cfg.off_A;                                     // [cap][strideA]: MT x (re, re, im, im)
+    float2* sW          = reinterpret_cast<float2*>(wsm + cfg.off_W);          // [cap][strideW]
+    unsigned char* list = wsm + cfg.off_list;                                  // [cap] (user in window << 5) | column
+    int* s_base         = reinterpret_cast<int*>(wsm + cfg.off_meta);          // [kS2Window + 1]
+    int* s_cnt          = s_base + kS2Window + 1;                              // [kS2Window]
+
+    const long long u_begin = ((long long)blockIdx.x * kS2Warps + warp) * cfg.users_per_warp;
+    const long long u_end = min(u_begin + (long long)cfg.users_per_warp, d.n_users);
+    const unsigned ltmask = (1u << lane) - 1u;
+    const int K = d.K, M = d.M, P0 = d.P0;
+    const bool need_angles = prologue_needs_angles(d);
+    const bool vec_ok = ((K & 1) == 0) && ((reinterpret_cast<uintptr_t>(d.out) & 15) == 0);
+
+    for (long long cur = u_begin; cur < u_end; ) {
+        // ---- 1. window: which columns of the next users need their chain
+        unsigned need[kS2Window];
+        #pragma unroll
+        for (int ul = 0; ul < kS2Window; ++ul) {
+            const long long u = cur + ul;
+            const bool in = u < u_end && lane < P0;
+            const float v = in ? d.power[u * (long long)d.ld + lane] : __int_as_float(0x7fc00000);
+            const bool valid = in && lane < d.P && !(v != v);                   // channel.py:260, dataset.py:258-261
+            const bool run = d.fov_any ? in : valid;
+            need[ul] = __ballot_sync(0xffffffffu, run);
+            if (in) {
+                const long long o = u * (long long)P0 + lane;
+                if (d.valid_mask) d.valid_mask[o] = valid ? 1 : 0;
+                if (!run) {                                                     // no FoV mask is built and the column has no power
+                    if (d.fov_mask)  d.fov_mask[o] = 1;
+                    if (d.clip_mask) d.clip_mask[o] = 0;
+                }
+            }
+        }
+        // ---- 2. take whole users while the pool has room; dense list of their (user, column) pairs
+        int cum = 0, n_take = 0;
+        #pragma unroll
+        for (int ul = 0; ul < kS2Window; ++ul) {
+            const int c = __popc(need[ul]);
+            if (ul == n_take && cur + ul < u_end && (ul == 0 || cum + c <= cfg.cap)) {
+                if (lane == 0) { s_base[ul] = cum; s_cnt[ul] = 0; }
+                if ((need[ul] >> lane) & 1u) list[cum + __popc(need[ul] & ltmask)] = (unsigned char)((ul << 5) | lane);
+                cum += c;
+                ++n_take;
+            }
+        }
+        __syncwarp();
+        // ---- 3. chain rounds: lane = dense pair
+        for (int i0 = 0; i0 < cum; i0 += 32) {
+            const int i = i0 + lane;
+            const bool act = i < cum;
+            int ul = kS2Window, col = 0;
+            if (act) { const int e = list[i]; ul = e >> 5; col = e & 31; }
+            const long long user = cur + ul;
+            PathState st;
+            st.contrib = false; st.valid = false; st.fov = true; st.over = false;
+            if (act) {
+                SideOut s0, s1; GainOut g;
+                if (need_angles) { prologue_side<true>(d, user, col, 0, s0, d.Mt > 1);  prologue_side<true>(d, user, col, 1, s1, d.Mr > 1); }
+                else             { prologue_side<false>(d, user, col, 0, s0, d.Mt > 1); prologue_side<false>(d, user, col, 1, s1, d.Mr > 1); }
+                prologue_gain<true>(d, user, col, g);
+                prologue_combine<true>(d, s0, s1, g, st);
+                const long long o = user * (long long)P0 + col;
+                if (d.fov_mask)  d.fov_mask[o]  = st.fov ? 1 : 0;
+                if (d.clip_mask) d.clip_mask[o] = (st.valid && st.over) ? 1 : 0;
+            }
+            const bool contrib = act && st.contrib;
+            const unsigned bc = __ballot_sync(0xffffffffu, contrib);
+            const unsigned same = __match_any_sync(0xffffffffu, ul);             // lanes of the same user (idle lanes: key kS2Window)
+            const int before = act ? s_cnt[ul] : 0;
+            __syncwarp();
+            if (act && lane == __ffs(same) - 1) s_cnt[ul] = before + __popc(bc & same);
+            __syncwarp();
+            if (contrib) {
+                const int q = s_base[ul] + before + __popc(bc & same & ltmask);
+                float4* a = reinterpret_cast<float4*>(sA + (size_t)q * cfg.strideA);
+                #pragma unroll 2
+                for (int m = 0; m < MT; ++m) {
+                    float2 v = make_float2(0.f, 0.f);
+                    if (m < M) {
+                        const float4 cf = s_coef[m];
+                        const double cyc = fma((double)cf.x, st.u[0], fma((double)cf.y, st.v[0], fma((double)cf.z, st.u[1], (double)cf.w * st.v[1])));
+                        v = cmul(st.c, phasor_cycles(cyc));
+                    }
+                    a[m] = make_float4(v.x, v.x, v.y, v.y);
+                }
+                float2* w = sW + (size_t)q * cfg.strideW;
+                #pragma unroll 2
+                for (int e = 0; e < n_seed; ++e) w[e] = phasor_cycles(-(st.wcyc * s_kseed[e]));
+            }
+        }
+        __syncwarp();
+        // ---- 4. accumulate and store, one user at a time: lane owns columns 2l, 2l+1 of a 64-column pass and all rows
+        for (int ul = 0; ul < n_take; ++ul) {
+            const long long user = cur + ul;
+            const int np = s_cnt[ul];
+            const unsigned char* aU = sA + (size_t)s_base[ul] * cfg.strideA;
+            const float2* wU = sW + (size_t)s_base[ul] * cfg.strideW;
+            float2* out_u = d.out + user * (long long)M * K;
+            if (np == 0) {                                                      // zeros (channel.py:257,:269-271)
+                const long long total = (long long)M * K;
+                if (vec_ok) { float4* o = reinterpret_cast<float4*>(out_u); for (long long e = lane; e < total / 2; e += 32) __stcs(o + e, make_float4(0.f, 0.f, 0.f, 0.f)); }
+                else        { for (long long e = lane; e < total; e += 32) __stcs(out_u + e, make_float2(0.f, 0.f)); }
+                continue;
+            }
+            for (int col0 = 0; col0 < K; col0 += 64) {
+                const int c0 = col0 + 2 * lane;
+                const int cc = min(c0, K - 1);                                  // idle lanes read valid table entries
+                const int i0 = cc & (cfg.n0 - 1);
+                const int i1 = cfg.n0 + (cfg.n2 ? ((cc >> 4) & 15) : (cc >> cfg.log0));
+                const int i2 = cfg.n0 + cfg.n1 + (cc >> 8);
+                float2 acc[MT][2];
+                #pragma unroll
+                for (int m = 0; m < MT; ++m) { acc[m][0] = make_float2(0.f, 0.f); acc[m][1] = make_float2(0.f, 0.f); }
+                #pragma unroll 1
+                for (int p = 0; p < np; ++p) {
+                    const float2* wr = wU + (size_t)p * cfg.strideW;
+                    float2 hi = wr[i1];
+                    if (cfg.n2) hi = cmul(hi, wr[i2]);
+                    const float2 w0 = cmul(hi, wr[i0]);
+                    const float2 w1 = cmul(hi, wr[i0 + 1]);
+                    const float2 w0s = make_float2(w0.y, w0.x), w1s = make_float2(w1.y, w1.x);
+                    const float4* ar = reinterpret_cast<const float4*>(aU + (size_t)p * cfg.strideA);
+                    #pragma unroll
+                    for (int m = 0; m < MT; ++m) {
+                        const float4 a = ar[m];
+                        const float2 a1 = make_float2(a.x, a.y), a2 = make_float2(-a.z, a.w);
+                        acc[m][0] = __ffma2_rn(a1, w0, acc[m][0]);
+                        acc[m][0] = __ffma2_rn(a2, w0s, acc[m][0]);
+                        acc[m][1] = __ffma2_rn(a1, w1, acc[m][1]);
+                        acc[m][1] = __ffma2_rn(a2, w1s, acc[m][1]);
+                    }
+                }
+                #pragma unroll
+                for (int m = 0; m < MT; ++m) {
+                    if (m >= M) break;
+                    float2* o = out_u + (long long)m * K + c0;
+                    if (vec_ok && c0 + 1 < K) __stcs(reinterpret_cast<float4*>(o), make_float4(acc[m][0].x, acc[m][0].y, acc[m][1].x, acc[m][1].y));
+                    else {
+                        if (c0 < K)     __stcs(o, acc[m][0]);
+                        if (c0 + 1 < K) __stcs(o + 1, acc[m][1]);
+                    }
+                }
+            }
+        }
+        __syncwarp();                                                           // the pool is rewritten by the next pass
+        cur += n_take;
+    }
+}
+
 }  // namespace dmk

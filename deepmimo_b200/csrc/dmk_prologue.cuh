@@ -31,7 +31,7 @@ struct PathState {
 template <bool kNeedAngles>
 __device__ __forceinline__ void rotate_side(float el_deg, float az_deg,
                                             double sx, double cx, double sy, double cy, double rz,
-                                            double& th, double& ph, double& sin_th_sin_ph, double& cos_th)
+                                            double& th, double& ph, double& sin_th_sin_ph, double& cos_th, bool steer = true)
 {
     const float d2r = 0x1.1df46ap-6f;                       // float32(pi/180): np.deg2rad on float32 (R1)
     float th32 = __fmul_rn(el_deg, d2r);                    // :284
@@ -58,11 +58,13 @@ __device__ __forceinline__ void rotate_side(float el_deg, float az_deg,
         th = (fabs(x) <= 1.0) ? 0.0 : __longlong_as_double(0x7ff8000000000000LL);
         ph = (re == re && im == im) ? 0.0 : __longlong_as_double(0x7ff8000000000000LL);
     }
+    cos_th = x;
+    sin_th_sin_ph = 0.0;
+    if (!steer) return;        // single-element panel (e.g. one UE antenna): only the NaN-ness of the angles is consumed
     const double sin_th = sqrt(__dmul_rn(__dsub_rn(1.0, x), __dadd_rn(1.0, x)));     // sin(arccos(x)); NaN for |x| > 1
     const double h = sqrt(__dadd_rn(__dmul_rn(re, re), __dmul_rn(im, im)));
     const double sin_ph = (h > 0.0) ? __ddiv_rn(im, h) : 0.0;                        // sin(atan2(im, re)); atan2(0, +0) = 0
     sin_th_sin_ph = sin_th * sin_ph;
-    cos_th = x;
 }
 
 // geometry.py:180-193 on one side.  theta in [0, pi] so mod(theta, 2pi) == theta; phi in (-pi, pi].
@@ -92,7 +94,7 @@ struct SideOut { double th, ph, ss, cc, gain; };           // rotated angles, si
 struct GainOut { float p_lin, ec, es; double wcyc, fd; unsigned char valid, over; };
 
 template <bool kNeedAngles>
-__device__ __forceinline__ void prologue_side(const DevDesc& d, long long user, int p, int side, SideOut& o)
+__device__ __forceinline__ void prologue_side(const DevDesc& d, long long user, int p, int side, SideOut& o, bool steer = true)
 {
     const long long off = user * (long long)d.ld + p;
     double sx = d.sx[side], cx = d.cx[side], sy = d.sy[side], cy = d.cy[side], rz = d.rz[side];
@@ -103,7 +105,7 @@ __device__ __forceinline__ void prologue_side(const DevDesc& d, long long user, 
         dsincos_bf(__dmul_rn(r[1], k), sy, cy);
         rz = __dmul_rn(r[2], k);
     }
-    rotate_side<kNeedAngles>(d.el[side][off], d.az[side][off], sx, cx, sy, cy, rz, o.th, o.ph, o.ss, o.cc);
+    rotate_side<kNeedAngles>(d.el[side][off], d.az[side][off], sx, cx, sy, cy, rz, o.th, o.ph, o.ss, o.cc, steer);
     o.gain = 1.0;
 }
 

@@ -87,7 +87,8 @@ typedef enum dmk_kernel_hint {
     DMK_KERNEL_FFMA  = 2,   /* packed-FP32 CUDA-core kernel                                         */
     DMK_KERNEL_TC    = 3,   /* persistent warp-specialised tcgen05 kernel                           */
     DMK_KERNEL_TC1   = 4,   /* one-CTA-per-user tcgen05 kernel                                      */
-    DMK_KERNEL_SMALL = 5    /* small-array kernel (M <= 16)                                         */
+    DMK_KERNEL_SMALL = 5,   /* small-array kernel (M <= 16), densely packed                         */
+    DMK_KERNEL_SMALL1 = 6   /* round-1 small-array kernel (one warp per user), kept for A/B timing  */
 } dmk_kernel_hint;
 
 /* dmk_desc.flags.
