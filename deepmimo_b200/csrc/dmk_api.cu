@@ -295,17 +295,19 @@ int dmk_channels_fd(const dmk_desc* desc, const float* power_dbw, const float* p
             sc.strideA = mt * 16 + 16;                         // +16 B: the 32 lanes of a chain round store to 32 different pool rows
             sc.strideW = n_seed | 1;
             const int per_path = sc.strideA + sc.strideW * 8;
-            const int budget = 18 * 1024;                       // 12 warps per SM
+            // 16 warps per SM (4 CTAs): 13.5 KB per warp.  A pool of ~32-40 paths is one dense chain round per pass.
+            const int budget = 13 * 1024 + 512;
             int cap = (budget - 256) / per_path;
-            if (cap > 64) cap = 64;
+            if (cap > 40) cap = 40;
             if (cap < d.P0) cap = d.P0;                         // one user always fits
+            sc.window = kS2Window;
             sc.cap = cap;
             size_t off = 0;
             auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 15) & ~size_t(15); return (int)o; };
             sc.off_A    = take((size_t)cap * sc.strideA);
             sc.off_W    = take((size_t)cap * sc.strideW * 8);
             sc.off_list = take((size_t)cap);
-            sc.off_meta = take((size_t)(2 * kS2Window + 1) * sizeof(int));
+            sc.off_meta = take((size_t)(4 * kS2Window + 1) * sizeof(int));
             sc.warp_bytes = (int)off;
             sc.mul_mt = cfg.mul_mt; sc.mul_bs0 = cfg.mul_bs0;
             // contiguous users per warp: 16 when that still leaves >= 2 waves of CTAs, fewer for short user ranges

@@ -143,6 +143,18 @@ __device__ __forceinline__ float2 phasor_cycles(double cyc)
     return make_float2(rc, rs);
 }
 
+// exp(j 2 pi cyc) with the SFU: the fraction of a cycle is still taken in float64 (tau * f reaches thousands of cycles), the
+// evaluation is sin.approx / cos.approx of 2 pi fr, |2 pi fr| <= pi.  MUFU.SIN/COS are accurate to 2^-21.4 absolute on [-pi, pi]
+// (CUDA programming guide, intrinsic table), i.e. <= 3.6e-7 on a unit phasor -- three times the polynomial version above, still
+// 28x inside the 1e-5 parity bar -- at 9 instead of ~35 instructions.  Used where a kernel is bound by the number of phasors it
+// has to evaluate per user (small arrays: a few KB of output per user).
+__device__ __forceinline__ float2 phasor_cycles_sfu(double cyc)
+{
+    const double fr = cyc - rint(cyc);            // [-0.5, 0.5]
+    const float x = (float)fr * 6.28318530717958647692f;
+    return make_float2(__cosf(x), __sinf(x));
+}
+
 __device__ __forceinline__ float2 cmul(float2 a, float2 b)
 {
     return make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x));

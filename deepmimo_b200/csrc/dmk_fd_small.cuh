@@ -178,13 +178,14 @@ fd_small_kernel(const __grid_constant__ DevDesc d, const __grid_constant__ Small
 // Pool rows are padded to an odd multiple of the store width so that the 32 lanes of a round never share a bank.
 // =================================================================================================
 constexpr int kS2Warps  = 4;
-constexpr int kS2Window = 8;          // users examined per pass
+constexpr int kS2Window = 4;          // users examined per pass
 constexpr int kS2MaxSeeds = 48;       // 16 + 16 + 16 (K <= 4096)
 
 struct Small2Cfg {
     int warp_bytes;                   // bytes of a warp's shared-memory slice
     int off_A, off_W, off_list, off_meta;
     int cap;                          // table pool capacity in paths (>= n_cols)
+    int window;                       // users examined per pass (<= kS2Window)
     int strideA;                      // bytes between pool rows of A: MT * 16 + 16
     int strideW;                      // float2 between pool rows of the seed levels: n_seed | 1
     int n0, log0, n1, n2;             // seed levels: column c -> L0[c & (n0-1)], L1[(c >> log0) & 15], L2[c >> 8] (n2 == 0: two levels)
@@ -193,9 +194,9 @@ struct Small2Cfg {
 };
 
 template <int MT>
-__global__ void __launch_bounds__(kS2Warps * 32, 3)
+__global__ void __launch_bounds__(kS2Warps * 32, 4)
 fd_small2_kernel(const __grid_constant__ DevDesc d, const __grid_constant__ Small2Cfg cfg)
-{
+{   // (occupancy is set by the host through the shared-memory slice per warp; the bound only caps registers at 128)
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ float4 s_coef[16];                 // element m -> (y_t, z_t, y_r, z_r) panel coordinates
     __shared__ double s_kseed[kS2MaxSeeds];       // seed entry e -> subcarrier offset whose delay phasor it holds
@@ -225,6 +226,8 @@ fd_small2_kernel(const __grid_constant__ DevDesc d, const __grid_constant__ Smal
     unsigned char* list = wsm + cfg.off_list;                                  // [cap] (user in window << 5) | column
     int* s_base         = reinterpret_cast<int*>(wsm + cfg.off_meta);          // [kS2Window + 1]
     int* s_cnt          = s_base + kS2Window + 1;                              // [kS2Window]
+    unsigned* s_need    = reinterpret_cast<unsigned*>(s_cnt + kS2Window);      // [kS2Window] columns whose chain runs
+    unsigned* s_valid   = s_need + kS2Window;                                  // [kS2Window] columns with a path (valid_mask)
 
     const long long u_begin = ((long long)blockIdx.x * kS2Warps + warp) * cfg.users_per_warp;
     const long long u_end = min(u_begin + (long long)cfg.users_per_warp, d.n_users);
@@ -234,39 +237,58 @@ fd_small2_kernel(const __grid_constant__ DevDesc d, const __grid_constant__ Smal
     const bool vec_ok = ((K & 1) == 0) && ((reinterpret_cast<uintptr_t>(d.out) & 15) == 0);
 
     for (long long cur = u_begin; cur < u_end; ) {
-        // ---- 1. window: which columns of the next users need their chain
-        unsigned need[kS2Window];
+        // ---- 1. window: which columns of the next users need their chain.  All loads first (independent, one latency), then the
+        //         ballots; the per-user bit masks go to shared memory so that everything after this is a short rolled loop.
+        const int n_in = (int)min((long long)cfg.window, u_end - cur);
+        const float* prow = d.power + cur * (long long)d.ld + lane;
+        float pw[kS2Window];
+        #pragma unroll
+        for (int ul = 0; ul < kS2Window; ++ul)
+            pw[ul] = (ul < n_in && lane < P0) ? __ldg(prow + ul * d.ld) : __int_as_float(0x7fc00000);
         #pragma unroll
         for (int ul = 0; ul < kS2Window; ++ul) {
-            const long long u = cur + ul;
-            const bool in = u < u_end && lane < P0;
-            const float v = in ? d.power[u * (long long)d.ld + lane] : __int_as_float(0x7fc00000);
-            const bool valid = in && lane < d.P && !(v != v);                   // channel.py:260, dataset.py:258-261
-            const bool run = d.fov_any ? in : valid;
-            need[ul] = __ballot_sync(0xffffffffu, run);
-            if (in) {
-                const long long o = u * (long long)P0 + lane;
-                if (d.valid_mask) d.valid_mask[o] = valid ? 1 : 0;
+            const bool in = ul < n_in && lane < P0;
+            const bool valid = in && lane < d.P && !(pw[ul] != pw[ul]);           // channel.py:260, dataset.py:258-261
+            const unsigned vb = __ballot_sync(0xffffffffu, valid);
+            const unsigned nb = d.fov_any ? __ballot_sync(0xffffffffu, in) : vb;
+            if (lane == ul) { s_valid[ul] = vb; s_need[ul] = nb; }
+        }
+        __syncwarp();
+        // ---- 2. take whole users while the pool has room; dense list of their (user, column) pairs; masks of the columns that
+        //         run no chain (valid_mask of every column)
+        int cum = 0, n_take = 0;
+        long long o = cur * (long long)P0 + lane;
+        #pragma unroll 1
+        for (int ul = 0; ul < n_in; ++ul, o += P0) {
+            const unsigned nb = s_need[ul], vb = s_valid[ul];
+            const int c = __popc(nb);
+            if (ul > 0 && cum + c > cfg.cap) break;
+            if (lane == 0) { s_base[ul] = cum; s_cnt[ul] = 0; }
+            const bool run = (nb >> lane) & 1u;
+            if (run) list[cum + __popc(nb & ltmask)] = (unsigned char)((ul << 5) | lane);
+            if (lane < P0) {
+                if (d.valid_mask) d.valid_mask[o] = (vb >> lane) & 1u;
                 if (!run) {                                                     // no FoV mask is built and the column has no power
                     if (d.fov_mask)  d.fov_mask[o] = 1;
                     if (d.clip_mask) d.clip_mask[o] = 0;
                 }
             }
-        }
-        // ---- 2. take whole users while the pool has room; dense list of their (user, column) pairs
-        int cum = 0, n_take = 0;
-        #pragma unroll
-        for (int ul = 0; ul < kS2Window; ++ul) {
-            const int c = __popc(need[ul]);
-            if (ul == n_take && cur + ul < u_end && (ul == 0 || cum + c <= cfg.cap)) {
-                if (lane == 0) { s_base[ul] = cum; s_cnt[ul] = 0; }
-                if ((need[ul] >> lane) & 1u) list[cum + __popc(need[ul] & ltmask)] = (unsigned char)((ul << 5) | lane);
-                cum += c;
-                ++n_take;
-            }
+            cum += c;
+            ++n_take;
         }
         __syncwarp();
+        // rows of the users after this pass: pull them towards L2/L1 while the chains of this pass run (lane = (array, user))
+        if (lane < 7 * 4) {
+            const int arr = lane >> 2;
+            const long long u = cur + n_take + (lane & 3);
+            if (u < u_end) {
+                const float* base = (arr == 0) ? d.power : (arr == 1) ? d.phase : (arr == 2) ? d.delay : (arr == 3) ? d.az[0] : (arr == 4) ? d.el[0]
+                                  : (arr == 5) ? d.az[1] : d.el[1];
+                asm volatile("prefetch.global.L2 [%0];" :: "l"(base + u * (long long)d.ld));
+            }
+        }
         // ---- 3. chain rounds: lane = dense pair
+        #pragma unroll 1
         for (int i0 = 0; i0 < cum; i0 += 32) {
             const int i = i0 + lane;
             const bool act = i < cum;
@@ -295,23 +317,24 @@ fd_small2_kernel(const __grid_constant__ DevDesc d, const __grid_constant__ Smal
             if (contrib) {
                 const int q = s_base[ul] + before + __popc(bc & same & ltmask);
                 float4* a = reinterpret_cast<float4*>(sA + (size_t)q * cfg.strideA);
-                #pragma unroll 2
+                #pragma unroll 4
                 for (int m = 0; m < MT; ++m) {
                     float2 v = make_float2(0.f, 0.f);
                     if (m < M) {
                         const float4 cf = s_coef[m];
                         const double cyc = fma((double)cf.x, st.u[0], fma((double)cf.y, st.v[0], fma((double)cf.z, st.u[1], (double)cf.w * st.v[1])));
-                        v = cmul(st.c, phasor_cycles(cyc));
+                        v = cmul(st.c, phasor_cycles_sfu(cyc));
                     }
                     a[m] = make_float4(v.x, v.x, v.y, v.y);
                 }
                 float2* w = sW + (size_t)q * cfg.strideW;
-                #pragma unroll 2
-                for (int e = 0; e < n_seed; ++e) w[e] = phasor_cycles(-(st.wcyc * s_kseed[e]));
+                #pragma unroll 4
+                for (int e = 0; e < n_seed; ++e) w[e] = phasor_cycles_sfu(-(st.wcyc * s_kseed[e]));
             }
         }
         __syncwarp();
         // ---- 4. accumulate and store, one user at a time: lane owns columns 2l, 2l+1 of a 64-column pass and all rows
+        #pragma unroll 1
         for (int ul = 0; ul < n_take; ++ul) {
             const long long user = cur + ul;
             const int np = s_cnt[ul];
@@ -327,21 +350,21 @@ fd_small2_kernel(const __grid_constant__ DevDesc d, const __grid_constant__ Smal
             for (int col0 = 0; col0 < K; col0 += 64) {
                 const int c0 = col0 + 2 * lane;
                 const int cc = min(c0, K - 1);                                  // idle lanes read valid table entries
-                const int i0 = cc & (cfg.n0 - 1);
-                const int i1 = cfg.n0 + (cfg.n2 ? ((cc >> 4) & 15) : (cc >> cfg.log0));
-                const int i2 = cfg.n0 + cfg.n1 + (cc >> 8);
+                const float2* w_lo = wU + (cc & (cfg.n0 - 1));
+                const float2* w_m1 = wU + cfg.n0 + (cfg.n2 ? ((cc >> 4) & 15) : (cc >> cfg.log0));
+                const float2* w_m2 = wU + cfg.n0 + cfg.n1 + (cc >> 8);
+                const unsigned char* ar_b = aU;
                 float2 acc[MT][2];
                 #pragma unroll
                 for (int m = 0; m < MT; ++m) { acc[m][0] = make_float2(0.f, 0.f); acc[m][1] = make_float2(0.f, 0.f); }
                 #pragma unroll 1
                 for (int p = 0; p < np; ++p) {
-                    const float2* wr = wU + (size_t)p * cfg.strideW;
-                    float2 hi = wr[i1];
-                    if (cfg.n2) hi = cmul(hi, wr[i2]);
-                    const float2 w0 = cmul(hi, wr[i0]);
-                    const float2 w1 = cmul(hi, wr[i0 + 1]);
+                    float2 hi = *w_m1;
+                    if (cfg.n2) hi = cmul(hi, *w_m2);
+                    const float2 w0 = cmul(hi, w_lo[0]);
+                    const float2 w1 = cmul(hi, w_lo[1]);
                     const float2 w0s = make_float2(w0.y, w0.x), w1s = make_float2(w1.y, w1.x);
-                    const float4* ar = reinterpret_cast<const float4*>(aU + (size_t)p * cfg.strideA);
+                    const float4* ar = reinterpret_cast<const float4*>(ar_b);
                     #pragma unroll
                     for (int m = 0; m < MT; ++m) {
                         const float4 a = ar[m];
@@ -351,15 +374,23 @@ fd_small2_kernel(const __grid_constant__ DevDesc d, const __grid_constant__ Smal
                         acc[m][1] = __ffma2_rn(a1, w1, acc[m][1]);
                         acc[m][1] = __ffma2_rn(a2, w1s, acc[m][1]);
                     }
+                    w_lo += cfg.strideW; w_m1 += cfg.strideW; w_m2 += cfg.strideW; ar_b += cfg.strideA;
                 }
-                #pragma unroll
-                for (int m = 0; m < MT; ++m) {
-                    if (m >= M) break;
-                    float2* o = out_u + (long long)m * K + c0;
-                    if (vec_ok && c0 + 1 < K) __stcs(reinterpret_cast<float4*>(o), make_float4(acc[m][0].x, acc[m][0].y, acc[m][1].x, acc[m][1].y));
-                    else {
-                        if (c0 < K)     __stcs(o, acc[m][0]);
-                        if (c0 + 1 < K) __stcs(o + 1, acc[m][1]);
+                float2* o = out_u + c0;
+                if (vec_ok && col0 + 64 <= K && M == MT) {                      // whole pass inside the row, every register row is real
+                    #pragma unroll
+                    for (int m = 0; m < MT; ++m)
+                        __stcs(reinterpret_cast<float4*>(o + (long long)m * K), make_float4(acc[m][0].x, acc[m][0].y, acc[m][1].x, acc[m][1].y));
+                } else {
+                    #pragma unroll
+                    for (int m = 0; m < MT; ++m) {
+                        if (m >= M) break;
+                        float2* om = o + (long long)m * K;
+                        if (vec_ok && c0 + 1 < K) __stcs(reinterpret_cast<float4*>(om), make_float4(acc[m][0].x, acc[m][0].y, acc[m][1].x, acc[m][1].y));
+                        else {
+                            if (c0 < K)     __stcs(om, acc[m][0]);
+                            if (c0 + 1 < K) __stcs(om + 1, acc[m][1]);
+                        }
                     }
                 }
             }
