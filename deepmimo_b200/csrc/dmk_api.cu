@@ -17,7 +17,7 @@
 namespace {
 
 thread_local char g_err[512] = "";
-thread_local char g_kernel[128] = "";
+thread_local char g_kernel[192] = "";
 std::atomic<long long> g_launches{0};
 
 int fail(int code, const char* fmt, ...)
@@ -357,81 +357,78 @@ int dmk_channels_fd(const dmk_desc* desc, const float* power_dbw, const float* p
             return DMK_OK;
         }
     }
-    // Warp-specialised persistent tensor-core kernel (default); DMK_FD_KERNEL=tc1 keeps the one-CTA-per-user version, which also
-    // takes the shapes whose double-buffered tables do not fit next to the operand tiles.
+    // Warp-specialised persistent tensor-core kernel in the flat-chunk formulation (dmk_fd_ws.cuh): the production path.
+    // DMK_KERNEL_TC1 keeps the one-CTA-per-user kernel, which also takes the shapes whose tables do not fit next to the
+    // 64 KB of operand tiles.
     const bool want_tc1 = hint == DMK_KERNEL_TC1;
-    TcCfg pcfg = tcfg;
-    size_t ptc_smem = 0;
-    int n_helpers = 1;
-    // Sized up to three times: the preferred tile (two 64-subcarrier sub-tiles for small arrays), then one sub-tile (32 KB less B
-    // operand), then 64-row tiles (16 KB less A operand) for shapes whose tables are large (e.g. a 64-element panel row), before the
-    // shape goes to the one-CTA-per-user kernel.
-    for (int attempt = 0; attempt < 3; ++attempt) {
-        if (attempt == 1) {
-            if (pcfg.nsub == 1) continue;
-            pcfg.nsub = 1;
-        }
-        if (attempt == 2) {                                      // last resort: 64-row tiles (16 KB less A operand)
-            if (pcfg.mtile <= 64) break;
-            pcfg.mtile = 64; pcfg.nsub = 1;
-        }
-        n_helpers = 1;
-
+    if (use_tc && !want_tc1) {
+        WsCfg w;
+        memset(&w, 0, sizeof(w));
         const int pc = (d.P > 0 ? d.P : 1) + 1;                  // + the zero row the builders read for padding slots
+        w.S = d.K / (kTcN / 2);
+        const long long n_chunks = (long long)d.M * w.S;
+        w.n_chunks = (int)n_chunks;
+        w.n_stages = (int)((n_chunks + kTcN - 1) / kTcN);
         size_t off = 0;
         auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 15) & ~size_t(15); return (int)o; };
-        pcfg.off_A = take((size_t)2 * pcfg.mtile * 128);
-        pcfg.off_B = take((size_t)pcfg.nsub * 2 * kTcN * 128);
-        pcfg.off_tab = (int)off;
+        w.off_N = take((size_t)2 * kTcN * 128);
+        w.off_M = take((size_t)2 * kTcN * 128);
+        w.off_tab = (int)off;
         size_t toff = 0;
         auto ttake = [&](size_t bytes) { size_t o = toff; toff += (bytes + 15) & ~size_t(15); return (int)o; };
-        pcfg.wa_table = 0;
-        pcfg.sS = (8 + (pcfg.nA + 7) / 8) | 1;
-        pcfg.off_tY = ttake((size_t)pc * pcfg.sY * sizeof(float2));
-        pcfg.off_tQ = ttake((size_t)pc * pcfg.sQ * sizeof(float2));
-        pcfg.off_wB = ttake((size_t)pc * pcfg.sB * sizeof(float2));
-        pcfg.off_seed = ttake((size_t)pc * pcfg.sS * sizeof(float2));
-        pcfg.off_wA = 0;
+        w.sY = d.bs0 | 1; w.sQ = (d.Mr * d.bs1) | 1; w.sB = 17; w.sL = 5; w.sS = w.S | 1;
+        w.off_tY = ttake((size_t)pc * w.sY * sizeof(float2));
+        w.off_tQ = ttake((size_t)pc * w.sQ * sizeof(float2));
+        w.off_wB = ttake((size_t)pc * w.sB * sizeof(float2));
+        w.off_wL = ttake((size_t)pc * w.sL * sizeof(float2));
+        w.off_wS = ttake((size_t)pc * w.sS * sizeof(float2));
         const size_t buf_bytes = ((sizeof(TcUserBuf) + 15) & ~size_t(15)) + toff;      // [user record][tables]
-        pcfg.tab_bytes = (int)buf_bytes;
+        w.tab_bytes = (int)buf_bytes;
+        w.mul_mt = cfg.mul_mt; w.mul_bs0 = cfg.mul_bs0;
+        w.mul_s = w.S > 1 ? (unsigned)((0x100000000ULL + w.S - 1) / w.S) : 0u;
+        const bool chunk_div_ok = n_chunks * (long long)w.S < 0xffffffffLL && n_chunks < 0x7fffffffLL / kTcN;
         // One helper warp prepares a user in ~30-45 k cycles (float64 prologue + tables, latency-bound).  Users whose output is
         // written faster than that (< ~400 KB) make the kernel helper-bound: they get four helper warps and eight buffers in a
         // single CTA per SM (shared memory and registers allow it because only one CTA is resident).
         const size_t per_user_bytes = (size_t)d.M * d.K * sizeof(float2);
-        const size_t smem4 = 1024 + off + 8 * buf_bytes;
+        const size_t smem1 = 1024 + off + 2 * buf_bytes, smem4 = 1024 + off + 8 * buf_bytes;
         const int hf = desc->ws_helpers;                      // 0 = by shape, 1 or 4 pins the instantiation (tests, A/B timing)
-        if ((per_user_bytes <= 384 * 1024 || hf == 4) && smem4 <= (size_t)kSmemWs4 && hf != 1) n_helpers = 4;
-        ptc_smem = 1024 + off + 2 * n_helpers * buf_bytes;
-        if (n_helpers == 4 || ptc_smem <= 113200) break;
-    }
-    const bool use_tcp = use_tc && !want_tc1 && (n_helpers == 4 || ptc_smem <= 113200) && grid < 0xffffff00LL;   // H = 1: + ~2.6 KB static + 1 KB reserve, two CTAs per SM
-    if (use_tcp) {
-        // warp-specialised persistent kernel (dmk_fd_ws.cuh): the production tensor-core path
-        static std::atomic<unsigned> ticket_seq{0};
-        unsigned int* tickets = nullptr;
-        cudaError_t e = cudaGetSymbolAddress(reinterpret_cast<void**>(&tickets), g_tc_ticket);
-        if (e != cudaSuccess) return cuda_fail(e, "cudaGetSymbolAddress(g_tc_ticket)");
-        const long long resident = (n_helpers == 1 ? 2LL : 1LL) * dev->sms;
-        const long long pgrid = grid < resident ? grid : resident;
-        // Programmatic dependent launch: the kernel releases its dependents at once, so the next libdmk launch can fill SMs
-        // as this one's persistent CTAs retire.  Unless the caller set DMK_FLAG_INDEPENDENT_LAUNCH the kernel itself
-        // waits for the previous grid (griddepcontrol.wait) before touching memory: plain stream order.
-        const int pdl_wait = (desc->flags & DMK_FLAG_INDEPENDENT_LAUNCH) ? 0 : 1;
-        cudaLaunchConfig_t lc;
-        memset(&lc, 0, sizeof(lc));
-        lc.gridDim = dim3((unsigned)pgrid); lc.blockDim = dim3((9 + n_helpers) * 32); lc.dynamicSmemBytes = ptc_smem; lc.stream = st;
-        cudaLaunchAttribute at[1];
-        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-        at[0].val.programmaticStreamSerializationAllowed = 1;
-        lc.attrs = at; lc.numAttrs = 1;
-        unsigned int* tk = tickets + (ticket_seq.fetch_add(1) % kTcTickets);
-        if (n_helpers == 1) e = cudaLaunchKernelEx(&lc, fd_ws_kernel<1>, d, pcfg, (int)ksplit, (unsigned)grid, tk, pdl_wait);
-        else                e = cudaLaunchKernelEx(&lc, fd_ws_kernel<4>, d, pcfg, (int)ksplit, (unsigned)grid, tk, pdl_wait);
-        if (e != cudaSuccess) return cuda_fail(e, "fd_ws_kernel launch");
-        g_launches.fetch_add(1);
-        snprintf(g_kernel, sizeof(g_kernel), "fd_ws_kernel<%dx128,3xf16,%d helper%s> grid=%lld items=%lld ksplit=%lld smem=%zu", pcfg.mtile, n_helpers,
-                 n_helpers > 1 ? "s" : "", pgrid, grid, ksplit, ptc_smem);
-        return DMK_OK;
+        int n_helpers = 0;
+        if ((per_user_bytes <= 384 * 1024 || hf == 4 || smem1 > 113200) && smem4 <= (size_t)kSmemWs4 && hf != 1) n_helpers = 4;
+        else if (smem1 <= 113200) n_helpers = 1;              // + ~2.6 KB static + 1 KB reserve: two CTAs per SM
+        // Few users: split each user's stages over several CTAs so the grid covers >= 4 waves.
+        long long wsplit = (want + n_users - 1) / n_users;
+        if (wsplit > w.n_stages) wsplit = w.n_stages;
+        if (wsplit < 1) wsplit = 1;
+        const long long items = n_users * wsplit;
+        if (n_helpers && chunk_div_ok && items < 0xffffff00LL) {
+            const size_t ws_smem = n_helpers == 1 ? smem1 : smem4;
+            static std::atomic<unsigned> ticket_seq{0};
+            unsigned int* tickets = nullptr;
+            cudaError_t e = cudaGetSymbolAddress(reinterpret_cast<void**>(&tickets), g_tc_ticket);
+            if (e != cudaSuccess) return cuda_fail(e, "cudaGetSymbolAddress(g_tc_ticket)");
+            const long long resident = (n_helpers == 1 ? 2LL : 1LL) * dev->sms;
+            const long long pgrid = items < resident ? items : resident;
+            // Programmatic dependent launch: the kernel releases its dependents at once, so the next libdmk launch can fill SMs
+            // as this one's persistent CTAs retire.  Unless the caller set DMK_FLAG_INDEPENDENT_LAUNCH the kernel itself
+            // waits for the previous grid (griddepcontrol.wait) before touching memory: plain stream order.
+            const int pdl_wait = (desc->flags & DMK_FLAG_INDEPENDENT_LAUNCH) ? 0 : 1;
+            cudaLaunchConfig_t lc;
+            memset(&lc, 0, sizeof(lc));
+            lc.gridDim = dim3((unsigned)pgrid); lc.blockDim = dim3((9 + n_helpers) * 32); lc.dynamicSmemBytes = ws_smem; lc.stream = st;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            at[0].val.programmaticStreamSerializationAllowed = 1;
+            lc.attrs = at; lc.numAttrs = 1;
+            unsigned int* tk = tickets + (ticket_seq.fetch_add(1) % kTcTickets);
+            if (n_helpers == 1) e = cudaLaunchKernelEx(&lc, fd_ws_kernel<1>, d, w, (int)wsplit, (unsigned)items, tk, pdl_wait);
+            else                e = cudaLaunchKernelEx(&lc, fd_ws_kernel<4>, d, w, (int)wsplit, (unsigned)items, tk, pdl_wait);
+            if (e != cudaSuccess) return cuda_fail(e, "fd_ws_kernel launch");
+            g_launches.fetch_add(1);
+            snprintf(g_kernel, sizeof(g_kernel), "fd_ws_kernel<128 chunks x 64 sc,3xf16,%d helper%s> grid=%lld items=%lld ksplit=%lld stages=%d smem=%zu",
+                     n_helpers, n_helpers > 1 ? "s" : "", pgrid, items, wsplit, w.n_stages, ws_smem);
+            return DMK_OK;
+        }
     }
     if (use_tc) {
         fd_tc_kernel<<<(unsigned)grid, kTcThreads, tc_smem, st>>>(d, tcfg, (int)ksplit);

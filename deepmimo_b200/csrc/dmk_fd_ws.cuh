@@ -91,9 +91,27 @@ __device__ __forceinline__ void st_split8_f16_rowpair(unsigned char* hi, unsigne
     *reinterpret_cast<uint4*>(lo + off_im) = make_uint4(li[0], li[1], li[2], li[3]);
 }
 
+// Flat-chunk formulation (round 2).  A user's output [M rows][K columns] complex64 is a flat array of 512-byte CHUNKS: chunk
+// c = m * S + seg holds the 64 subcarriers (128 floats) of segment seg of antenna row m, S = K / 64.  With the delay phasor split as
+//     W[p, 64 seg + j] = wS[p, seg] * wF[p, j],        wS = exp(-j 2 pi wcyc (start + 64 step seg)),  wF = exp(-j 2 pi wcyc step j)
+// the coarse factor moves to the antenna side:  H[c, j] = sum_p (A[m, p] wS[p, seg]) wF[p, j].  One tcgen05 stage then computes
+//     D[2j + s, n] = sum_{p, e} Mside[2j + s, 2p + e] * Nside[n, 2p + e]          n = chunk c0 + n, up to 128 chunks per stage
+// where Mside (the 2x2 real form of wF, 128 rows) is built ONCE PER USER and Nside per stage.  TMEM column n of the accumulator is
+// chunk c0 + n and lane 2j + s its float: the accumulator read out column by column IS a contiguous 64 KB piece of the output, so
+// every CTA writes one linear stream (7.4 TB/s in the pure-store micro-benchmark, tools/micro/store_rate3.cu, against 6.5-6.9 for
+// the row-strided tile of round 1), and the per-column-stage B tile of round 1 is gone.
+struct WsCfg {
+    int off_N, off_M;                                   // operand tiles: byte offsets from the 1024-aligned base, hi then lo
+    int off_tab, tab_bytes;                             // user buffers [TcUserBuf][tables]
+    int off_tY, off_tQ, off_wB, off_wL, off_wS;         // byte offsets inside a table buffer
+    int sY, sQ, sB, sL, sS;                             // per-path table strides (float2 units), odd
+    int S, n_chunks, n_stages;                          // segments per row, chunks per user, ceil(n_chunks / 128)
+    unsigned mul_mt, mul_bs0, mul_s;                    // ceil(2^32 / d) reciprocals (0: d == 1)
+};
+
 // Helper warp: ticket -> prologue -> per-user tables of one buffer.  lanes = path columns, then lanes = table entries.
 // Row np of every table is zero-filled: the operand builders read it (index min(p, np)) for the padding slots.
-__device__ __noinline__ void ws_helper_prepare(const DevDesc& d, const TcCfg& cfg, int ksplit, unsigned int n_items, unsigned int n_draw_last,
+__device__ __noinline__ void ws_helper_prepare(const DevDesc& d, const WsCfg& cfg, int ksplit, unsigned int n_items, unsigned int n_draw_last,
                                                unsigned int* ticket, TcUserBuf& ub, unsigned char* tab, int lane)
 {
     unsigned int t = 0;
@@ -115,8 +133,8 @@ __device__ __noinline__ void ws_helper_prepare(const DevDesc& d, const TcCfg& cf
     if (active) {
         SideOut s0, s1;
         GainOut g;
-        if (prologue_needs_angles(d)) { prologue_side<true>(d, user, lane, 0, s0);  prologue_side<true>(d, user, lane, 1, s1); }
-        else                          { prologue_side<false>(d, user, lane, 0, s0); prologue_side<false>(d, user, lane, 1, s1); }
+        if (prologue_needs_angles(d)) { prologue_side<true>(d, user, lane, 0, s0, d.Mt > 1);  prologue_side<true>(d, user, lane, 1, s1, d.Mr > 1); }
+        else                          { prologue_side<false>(d, user, lane, 0, s0, d.Mt > 1); prologue_side<false>(d, user, lane, 1, s1, d.Mr > 1); }
         prologue_gain<true>(d, user, lane, g);
         prologue_combine<true>(d, s0, s1, g, st);
     }
@@ -145,11 +163,12 @@ __device__ __noinline__ void ws_helper_prepare(const DevDesc& d, const TcCfg& cf
     const float inv_scale = 1.0f / mx;
     __syncwarp();
 
-    float2* tY   = reinterpret_cast<float2*>(tab + cfg.off_tY);
-    float2* tQ   = reinterpret_cast<float2*>(tab + cfg.off_tQ);
-    float2* wB   = reinterpret_cast<float2*>(tab + cfg.off_wB);
-    float2* seed = reinterpret_cast<float2*>(tab + cfg.off_seed);
-    const int bs0 = d.bs0, bs1 = d.bs1, nq = d.Mr * d.bs1;
+    float2* tY = reinterpret_cast<float2*>(tab + cfg.off_tY);
+    float2* tQ = reinterpret_cast<float2*>(tab + cfg.off_tQ);
+    float2* wB = reinterpret_cast<float2*>(tab + cfg.off_wB);
+    float2* wL = reinterpret_cast<float2*>(tab + cfg.off_wL);
+    float2* wS = reinterpret_cast<float2*>(tab + cfg.off_wS);
+    const int bs0 = d.bs0, bs1 = d.bs1, nq = d.Mr * d.bs1, S = cfg.S;
     for (int e = lane; e < np * bs0; e += 32) {
         const int p = e / bs0, y = e - p * bs0;
         tY[p * cfg.sY + y] = phasor_cycles((double)y * sh.u[0][p]);
@@ -161,36 +180,22 @@ __device__ __noinline__ void ws_helper_prepare(const DevDesc& d, const TcCfg& cf
         const float2 cs = make_float2(sh.c[p].x * inv_scale, sh.c[p].y * inv_scale);
         tQ[p * cfg.sQ + q] = cmul(cs, phasor_cycles((double)z * sh.v[0][p] + (double)yr * sh.u[1][p] + (double)zr * sh.v[1][p]));
     }
-    for (int e = lane; e < np * 16; e += 32) {
-        const int p = e >> 4, b = e & 15;
-        wB[p * cfg.sB + b] = phasor_cycles(-(sh.wcyc[p] * (double)(d.subc_step * b)));
+    for (int e = lane; e < np * 20; e += 32) {                          // fine delay phasors: wB[b], b < 16, and wL[a], a < 4 (j = 16 a + b)
+        const int p = e / 20, b = e - p * 20;
+        if (b < 16) wB[p * cfg.sB + b] = phasor_cycles(-(sh.wcyc[p] * (double)(d.subc_step * b)));
+        else        wL[p * cfg.sL + (b - 16)] = phasor_cycles(-(sh.wcyc[p] * (double)(d.subc_step * 16 * (b - 16))));
     }
-    const int n_hi = (cfg.nA + 7) >> 3, n_sd = 8 + n_hi;
-    for (int e = lane; e < np * n_sd; e += 32) {
-        const int p = e / n_sd, b = e - p * n_sd;
-        seed[p * cfg.sS + b] = (b < 8) ? phasor_cycles(-(sh.wcyc[p] * (double)(d.subc_step * 16 * b)))                             // seed_lo[b]
-                                       : phasor_cycles(-(sh.wcyc[p] * (double)(d.subc_start + d.subc_step * 128 * (b - 8))));     // seed_hi[b - 8]
+    for (int e = lane; e < np * S; e += 32) {                           // coarse delay phasors, one per 64-subcarrier segment
+        const int p = e / S, sg = e - p * S;
+        wS[p * cfg.sS + sg] = phasor_cycles(-(sh.wcyc[p] * ((double)d.subc_start + (double)d.subc_step * 64.0 * (double)sg)));
     }
     // row np of every table is the zero row: the operand builders read it for the padding slots np .. nslot-1
     const float2 zero = make_float2(0.f, 0.f);
-    for (int e = lane; e < bs0; e += 32)  tY[np * cfg.sY + e] = zero;
-    for (int e = lane; e < nq; e += 32)   tQ[np * cfg.sQ + e] = zero;
-    for (int e = lane; e < 16; e += 32)   wB[np * cfg.sB + e] = zero;
-    for (int e = lane; e < n_sd; e += 32) seed[np * cfg.sS + e] = zero;
-}
-
-// Drain one accumulator (mtile antenna rows x 128 floats of segment `seg`): the warp owns TMEM lane quarter q.
-__device__ __forceinline__ void ws_drain(uint32_t tmem_base, int acc_col, float* out_u, long long pitch, int M, int mtile,
-                                         int row0, int seg, int q, int lane, float scale)
-{
-    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc_col;
-    float* o = out_u + (long long)row0 * pitch + seg * kTcN + q * 32 + lane;
-    if (mtile >= 32) {
-        for (int r = 0; r < mtile; r += 32)
-            tc_store_rows<32>(taddr + r, o + (long long)r * pitch, pitch, row0 + r, M, scale);
-    } else {
-        tc_store_rows<16>(taddr, o, pitch, row0, M, scale);
-    }
+    for (int e = lane; e < bs0; e += 32) tY[np * cfg.sY + e] = zero;
+    for (int e = lane; e < nq; e += 32)  tQ[np * cfg.sQ + e] = zero;
+    for (int e = lane; e < 16; e += 32)  wB[np * cfg.sB + e] = zero;
+    for (int e = lane; e < 4; e += 32)   wL[np * cfg.sL + e] = zero;
+    for (int e = lane; e < S; e += 32)   wS[np * cfg.sS + e] = zero;
 }
 
 // Consumers (drain, builders, issuer) walk the users in the order it = 0, 1, 2, ...: user `it` is prepared by helper it % H into
@@ -216,7 +221,7 @@ __device__ __forceinline__ bool ws_next_user(WsBars& bars, const unsigned char* 
 
 template <int H>        // helper warps per CTA: 1 (two CTAs per SM, large per-user outputs) or 4 (one CTA per SM, helper-bound shapes)
 __global__ void __launch_bounds__((9 + H) * 32, H == 1 ? 2 : 1)
-fd_ws_kernel(const __grid_constant__ DevDesc d, const __grid_constant__ TcCfg cfg, const int ksplit,
+fd_ws_kernel(const __grid_constant__ DevDesc d, const __grid_constant__ WsCfg cfg, const int ksplit,
              const unsigned int n_items, unsigned int* ticket, const int pdl_wait)
 {
     extern __shared__ unsigned char smem_raw[];
@@ -224,16 +229,14 @@ fd_ws_kernel(const __grid_constant__ DevDesc d, const __grid_constant__ TcCfg cf
     if (pdl_wait) asm volatile("griddepcontrol.wait;" ::: "memory");     // plain stream order unless the caller declared independence
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");      // the next launch may take SMs as our CTAs retire
     __shared__ uint32_t tmem_base_s;
-    __shared__ float2 sWa[kTcSlots * 9];              // stage-local coarse delay phasors [slot][8 groups of 16 subcarriers], stride 9
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int mtile = cfg.mtile, nsub = cfg.nsub;
 
     unsigned char* sm = smem_raw + (((smem_u32(smem_raw) + 1023u) & ~1023u) - smem_u32(smem_raw));
-    unsigned char* sAhi = sm + cfg.off_A;                    // [mtile rows][128 B]: 32 path slots x (re, im) fp16
-    unsigned char* sAlo = sAhi + mtile * 128;
-    unsigned char* sBhi = sm + cfg.off_B;                    // per sub-tile: [128 rows][128 B] hi, then lo
-    unsigned char* sBlo = sBhi + kTcN * 128;
+    unsigned char* sNhi = sm + cfg.off_N;                    // [128 chunk rows][128 B]: 32 path slots x (re, im) fp16, K-major SWIZZLE_128B
+    unsigned char* sNlo = sNhi + kTcN * 128;
+    unsigned char* sMhi = sm + cfg.off_M;                    // [128 rows 2j + s][128 B]: fine delay phasors of the user, 2x2 real form
+    unsigned char* sMlo = sMhi + kTcN * 128;
     unsigned char* bufs = sm + cfg.off_tab;                  // 2H buffers of cfg.tab_bytes: [TcUserBuf][tables]
     constexpr int kUb = (int)((sizeof(TcUserBuf) + 15) & ~size_t(15));
     auto user_buf = [&](int b) -> TcUserBuf& { return *reinterpret_cast<TcUserBuf*>(bufs + (size_t)b * cfg.tab_bytes); };
@@ -254,12 +257,7 @@ fd_ws_kernel(const __grid_constant__ DevDesc d, const __grid_constant__ TcCfg cf
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = tmem_base_s;
-    const int K = d.K, M = d.M;
-    const int n_seg = K / (kTcN / 2);                         // 64-subcarrier segments per row
-    const int n_ct = (n_seg + nsub - 1) / nsub;               // pipeline stages (column super-tiles) per row tile
-    const int n_rt = (M + mtile - 1) / mtile;
-    const long long pitch = 2LL * K;                          // floats per output row
-    const int acc_stride = 128 / nsub;                        // TMEM columns per accumulator; 2 * nsub accumulators in 256 columns
+    const int n_chunks = cfg.n_chunks, n_stages = cfg.n_stages;
 
     if (warp >= kWsHelper0) {
         // ------------------------------------------------------------------------------------------ helpers
@@ -276,14 +274,12 @@ fd_ws_kernel(const __grid_constant__ DevDesc d, const __grid_constant__ TcCfg cf
         }
     } else if (warp >= kWsBuild0 && warp < kWsIssuer) {
         // ------------------------------------------------------------------------------------------ operand builders
-        const int bt = tid - kWsBuild0 * 32;                  // 0..127
-        const int a_row  = bt & (mtile - 1);
-        const int a_ngrp = kWsBuilders / mtile > 0 ? kWsBuilders / mtile : 1;      // thread groups per antenna row: 1, 2, 4 or 8
-        const int a_grp  = bt / mtile;
-        const int a_off0 = (a_row >> 3) * 1024 + (a_row & 7) * 128;
+        const int bt = tid - kWsBuild0 * 32;                  // 0..127: N-side row (chunk of the stage) / M-side subcarrier + group
+        const int n_off0 = (bt >> 3) * 1024 + (bt & 7) * 128;
+        const int n_sw = bt & 7;
         const int b_col  = bt & 63;
         const int b_grp  = bt >> 6;                           // 0..1
-        const int b_row0 = 2 * b_col;                         // rows 2c (Re H) and 2c + 1 (Im H)
+        const int b_row0 = 2 * b_col;                         // rows 2j (Re H) and 2j + 1 (Im H)
         const int b_off0 = (b_row0 >> 3) * 1024 + (b_row0 & 7) * 128;
         const int b_sw0 = b_row0 & 7, b_sw1 = (b_row0 + 1) & 7;
         unsigned g = 0;                                       // global stage counter (identical in every role)
@@ -296,93 +292,70 @@ fd_ws_kernel(const __grid_constant__ DevDesc d, const __grid_constant__ TcCfg cf
             const int np = ub.sh.np;
             if (np > 0) {
                 const unsigned char* tab = user_tab(cur);
-                const float2* tY   = reinterpret_cast<const float2*>(tab + cfg.off_tY);
-                const float2* tQ   = reinterpret_cast<const float2*>(tab + cfg.off_tQ);
-                const float2* wB   = reinterpret_cast<const float2*>(tab + cfg.off_wB);
-                const float2* seed = reinterpret_cast<const float2*>(tab + cfg.off_seed);
+                const float2* tY = reinterpret_cast<const float2*>(tab + cfg.off_tY);
+                const float2* tQ = reinterpret_cast<const float2*>(tab + cfg.off_tQ);
+                const float2* wB = reinterpret_cast<const float2*>(tab + cfg.off_wB);
+                const float2* wL = reinterpret_cast<const float2*>(tab + cfg.off_wL);
+                const float2* wS = reinterpret_cast<const float2*>(tab + cfg.off_wS);
                 const int nslot = ((np + 7) >> 3) << 3;       // slots the tensor core reads (table row np is the zero row)
                 const int nq4 = nslot >> 2;
-                bool a_valid = false;
-                for (int ct = ks; ct < n_ct; ct += ksplit) {
-                    const int seg0 = ct * nsub;
-                    const int nsub_here = min(nsub, n_seg - seg0);
-                    bool b_valid = false;
-                    for (int rt = 0; rt < n_rt; ++rt, ++g) {
-                        const int row0 = rt * mtile;
-                        if (g > 0) mbar_wait(&bars.mma_done[(g - 1) & 1], ((g - 1) >> 1) & 1u);     // MMA(g-1) has read the operand tiles
-                        if (!b_valid) {
-                            // stage-local coarse phasors wA[p][grp] = seed_hi * seed_lo for the <= 8 groups of 16 subcarriers
-                            for (int e = bt; e < nslot * 8; e += kWsBuilders) {
-                                const int p = e >> 3, grp = e & 7;
-                                if (grp < 4 * nsub_here) {
-                                    const int a = seg0 * 4 + grp;
-                                    const float2* sd = seed + min(p, np) * cfg.sS;
-                                    sWa[p * 9 + grp] = cmul(sd[8 + (a >> 3)], sd[a & 7]);
-                                }
+                bool m_valid = false;
+                for (int stg = ks; stg < n_stages; stg += ksplit, ++g) {
+                    if (g > 0) mbar_wait(&bars.mma_done[(g - 1) & 1], ((g - 1) >> 1) & 1u);     // MMA(g-1) has read the operand tiles
+                    if (!m_valid) {
+                        // ---- M side, once per user: rows 2j -> (Re wF, -Im wF), 2j + 1 -> (Im wF, Re wF), wF[p, j] = wL[p, j >> 4] wB[p, j & 15]
+                        const float2* wl0 = wL + (b_col >> 4);
+                        const float2* wb0 = wB + (b_col & 15);
+                        #pragma unroll 1
+                        for (int qd = b_grp; qd < nq4; qd += 2) {
+                            float2 w[4];
+                            #pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                const int p = min(qd * 4 + i, np);
+                                w[i] = cmul(wl0[p * cfg.sL], wb0[p * cfg.sB]);
                             }
+                            st_split8_f16_rowpair(sMhi, sMlo, b_off0 + (((qd ^ b_sw0) & 7) << 4), b_off0 + 128 + (((qd ^ b_sw1) & 7) << 4), w);
                         }
-                        // ---- A_hi / A_lo: antenna rows x path slots
-                        if (!(a_valid && n_rt == 1) && bt < a_ngrp * mtile) {
-                            const int am = row0 + a_row;
-                            const bool a_ok = am < M;
-                            int a_q = 0, a_y = 0;
-                            if (a_ok) {
-                                const unsigned mm = (unsigned)am;
-                                const unsigned rr = cfg.mul_mt ? __umulhi(mm, cfg.mul_mt) : mm;
-                                const unsigned t = mm - rr * (unsigned)d.Mt;
-                                const unsigned zt = cfg.mul_bs0 ? __umulhi(t, cfg.mul_bs0) : t;
-                                a_y = (int)(t - zt * (unsigned)d.bs0);
-                                a_q = (int)(rr * (unsigned)d.bs1 + zt);
-                            }
-                            const float2* q0 = tQ + a_q;
-                            const float2* y0 = tY + a_y;
-                            #pragma unroll 1
-                            for (int qd = a_grp; qd < nq4; qd += a_ngrp) {
-                                float2 a[4];
-                                #pragma unroll
-                                for (int i = 0; i < 4; ++i) {
-                                    const int p = min(qd * 4 + i, np);
-                                    a[i] = a_ok ? cmul(q0[p * cfg.sQ], y0[p * cfg.sY]) : make_float2(0.f, 0.f);
-                                }
-                                st_split8_f16(sAhi, sAlo, a_off0 + (((qd ^ (a_row & 7)) & 7) << 4), a);
-                            }
-                        }
-                        // ---- B_hi / B_lo per sub-tile (rows 2c -> Re H, 2c+1 -> Im H)
-                        if (!b_valid) {
-                            asm volatile("bar.sync 3, %0;" :: "n"(kWsBuilders) : "memory");        // sWa complete
-                            const float2* wb0 = wB + (b_col & 15);
-                            #pragma unroll 1
-                            for (int sub = 0; sub < nsub_here; ++sub) {
-                                unsigned char* sBh = sBhi + sub * (2 * kTcN * 128);
-                                unsigned char* sBl = sBh + kTcN * 128;
-                                const float2* wa0 = sWa + sub * 4 + (b_col >> 4);
-                                #pragma unroll 1
-                                for (int qd = b_grp; qd < nq4; qd += 2) {
-                                    float2 w[4];
-                                    #pragma unroll
-                                    for (int i = 0; i < 4; ++i) {
-                                        const int p = qd * 4 + i;
-                                        w[i] = cmul(wa0[p * 9], wb0[min(p, np) * cfg.sB]);
-                                    }
-                                    st_split8_f16_rowpair(sBh, sBl, b_off0 + (((qd ^ b_sw0) & 7) << 4), b_off0 + 128 + (((qd ^ b_sw1) & 7) << 4), w);
-                                }
-                            }
-                        }
-                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                        mbar_arrive(&bars.op_full);
-                        b_valid = true;
-                        a_valid = true;
+                        m_valid = true;
                     }
+                    // ---- N side: row n = chunk c0 + n = (antenna row m, segment seg): A[m, p] * wS[p, seg]
+                    {
+                        const unsigned c = (unsigned)(stg * kTcN + bt);
+                        const bool ok = c < (unsigned)n_chunks;
+                        int a_q = 0, a_y = 0, sg = 0;
+                        if (ok) {
+                            const unsigned mm = cfg.mul_s ? __umulhi(c, cfg.mul_s) : c;              // antenna row
+                            sg = (int)(c - mm * (unsigned)cfg.S);
+                            const unsigned rr = cfg.mul_mt ? __umulhi(mm, cfg.mul_mt) : mm;
+                            const unsigned t = mm - rr * (unsigned)d.Mt;
+                            const unsigned zt = cfg.mul_bs0 ? __umulhi(t, cfg.mul_bs0) : t;
+                            a_y = (int)(t - zt * (unsigned)d.bs0);
+                            a_q = (int)(rr * (unsigned)d.bs1 + zt);
+                        }
+                        const float2* q0 = tQ + a_q;
+                        const float2* y0 = tY + a_y;
+                        const float2* s0 = wS + sg;
+                        #pragma unroll 1
+                        for (int qd = 0; qd < nq4; ++qd) {
+                            float2 a[4];
+                            #pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                const int p = min(qd * 4 + i, np);
+                                a[i] = ok ? cmul(cmul(q0[p * cfg.sQ], y0[p * cfg.sY]), s0[p * cfg.sS]) : make_float2(0.f, 0.f);
+                            }
+                            st_split8_f16(sNhi, sNlo, n_off0 + (((qd ^ n_sw) & 7) << 4), a);
+                        }
+                    }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    mbar_arrive(&bars.op_full);
                 }
             }
             mbar_arrive(&bars.ub_empty[cur]);
         }
     } else if (warp == kWsIssuer) {
         // ------------------------------------------------------------------------------------------ MMA issuer
-        // instruction descriptor: D = F32, A = B = F16 (format 0), both K-major, N = antenna rows of the tile, M = 128 floats
-        const uint32_t idesc = (1u << 4) | ((uint32_t)(mtile >> 3) << 17) | ((uint32_t)(kTcN >> 4) << 24);
-        const uint64_t dAhi = umma_desc_kmajor_sw128(smem_u32(sAhi)), dAlo = umma_desc_kmajor_sw128(smem_u32(sAlo));
-        const uint64_t dBhi = umma_desc_kmajor_sw128(smem_u32(sBhi)), dBlo = umma_desc_kmajor_sw128(smem_u32(sBlo));
+        const uint64_t dNhi = umma_desc_kmajor_sw128(smem_u32(sNhi)), dNlo = umma_desc_kmajor_sw128(smem_u32(sNlo));
+        const uint64_t dMhi = umma_desc_kmajor_sw128(smem_u32(sMhi)), dMlo = umma_desc_kmajor_sw128(smem_u32(sMlo));
         unsigned g = 0;
         unsigned it = 0, done = 0;
         int cur = 0;
@@ -393,45 +366,42 @@ fd_ws_kernel(const __grid_constant__ DevDesc d, const __grid_constant__ TcCfg cf
             const int np = ub.sh.np;
             if (np > 0) {
                 const int ksteps = (np + 7) >> 3;                     // 16 fp16 (8 path slots) per MMA
-                for (int ct = ks; ct < n_ct; ct += ksplit) {
-                    const int nsub_here = min(nsub, n_seg - ct * nsub);
-                    for (int rt = 0; rt < n_rt; ++rt, ++g) {
-                        const unsigned ab = g & 1;
-                        mbar_wait(&bars.op_full, g & 1u);                                 // operand tiles of stage g are in smem
-                        mbar_wait(&bars.acc_empty[ab], ((g >> 1) & 1u) ^ 1u);              // accumulator ab drained (stage g-2)
-                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                        if (elect_one()) {
-                            #pragma unroll 1
-                            for (int sub = 0; sub < nsub_here; ++sub) {
-                                const uint32_t acc = tmem_base + (uint32_t)(((ab * nsub) + sub) * acc_stride);
-                                const uint64_t sub_off = (uint64_t)(sub * (2 * kTcN * 128) >> 4);       // descriptor address field: 16-byte units
-                                #pragma unroll
-                                for (int s = 0; s < 3; ++s) {                                           // hi*hi, lo*hi, hi*lo
-                                    const uint64_t da = (s == 2) ? dAlo : dAhi;
-                                    const uint64_t db = ((s == 1) ? dBlo : dBhi) + sub_off;
-                                    #pragma unroll
-                                    for (int kk = 0; kk < 4; ++kk) {
-                                        if (kk < ksteps) {
-                                            const uint32_t accum = (s | kk) != 0;
-                                            asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
-                                                         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}"
-                                                         :: "r"(acc), "l"(db + 2 * kk), "l"(da + 2 * kk), "r"(idesc), "r"(accum) : "memory");
-                                        }
-                                    }
+                for (int stg = ks; stg < n_stages; stg += ksplit, ++g) {
+                    const unsigned ab = g & 1;
+                    // tcgen05 N = chunks of this stage, rounded up to the instruction granularity (16 for M = 128)
+                    const int n_here = min(kTcN, (n_chunks - stg * kTcN + 15) & ~15);
+                    // instruction descriptor: D = F32, A = B = F16 (format 0), both K-major, N = chunks, M = 128 floats of a chunk
+                    const uint32_t idesc = (1u << 4) | ((uint32_t)(n_here >> 3) << 17) | ((uint32_t)(kTcN >> 4) << 24);
+                    mbar_wait(&bars.op_full, g & 1u);                                 // operand tiles of stage g are in smem
+                    mbar_wait(&bars.acc_empty[ab], ((g >> 1) & 1u) ^ 1u);              // accumulator ab drained (stage g-2)
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    if (elect_one()) {
+                        const uint32_t acc = tmem_base + ab * (uint32_t)kTcN;
+                        #pragma unroll
+                        for (int s = 0; s < 3; ++s) {                                           // hi*hi, lo*hi, hi*lo
+                            const uint64_t dn = (s == 2) ? dNlo : dNhi;
+                            const uint64_t dm = (s == 1) ? dMlo : dMhi;
+                            #pragma unroll
+                            for (int kk = 0; kk < 4; ++kk) {
+                                if (kk < ksteps) {
+                                    const uint32_t accum = (s | kk) != 0;
+                                    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+                                                 "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}"
+                                                 :: "r"(acc), "l"(dm + 2 * kk), "l"(dn + 2 * kk), "r"(idesc), "r"(accum) : "memory");
                                 }
                             }
-                            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
-                                         :: "r"(smem_u32(&bars.mma_done[ab])) : "memory");
                         }
-                        __syncwarp();
+                        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
+                                     :: "r"(smem_u32(&bars.mma_done[ab])) : "memory");
                     }
+                    __syncwarp();
                 }
             }
             mbar_arrive(&bars.ub_empty[cur]);
         }
     } else {
         // ------------------------------------------------------------------------------------------ drain warps 0-3
-        const int q = warp;                                   // TMEM lane quarter = 32 floats (128 bytes) of every row segment
+        const int q = warp;                                   // TMEM lane quarter = 32 floats (128 bytes) of every chunk
         unsigned g = 0;
         unsigned it = 0, done = 0;
         int cur = 0;
@@ -442,29 +412,27 @@ fd_ws_kernel(const __grid_constant__ DevDesc d, const __grid_constant__ TcCfg cf
             const int ks = (int)(item % (unsigned)ksplit);
             const int np = ub.sh.np;
             const float scale = ub.scale;
-            float* out_u = reinterpret_cast<float*>(d.out + user * (long long)M * K);
+            float* out_u = reinterpret_cast<float*>(d.out) + user * (long long)n_chunks * kTcN;
             if (np == 0) {
-                // users without contributing paths: zeros (channel.py:257,:269-271), one 512-byte row segment per warp store
-                float4* o = reinterpret_cast<float4*>(out_u);
+                // users without contributing paths: zeros (channel.py:257,:269-271); a stage is 64 KB of contiguous output
                 const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-                for (int ct = ks; ct < n_ct; ct += ksplit)
-                    for (int sub = 0; sub < nsub && ct * nsub + sub < n_seg; ++sub) {
-                        float4* ot = o + (ct * nsub + sub) * (kTcN / 4) + lane;
-                        for (int m = warp; m < M; m += 4) __stcs(ot + (long long)m * (pitch / 4), z);
-                    }
+                for (int stg = ks; stg < n_stages; stg += ksplit) {
+                    const int n4 = min(kTcN, n_chunks - stg * kTcN) * (kTcN / 4);             // float4 of this stage
+                    float4* o = reinterpret_cast<float4*>(out_u + (long long)stg * kTcN * kTcN);
+                    for (int e = warp * 32 + lane; e < n4; e += 128) __stcs(o + e, z);
+                }
             } else {
-                for (int ct = ks; ct < n_ct; ct += ksplit) {
-                    const int seg0 = ct * nsub;
-                    const int nsub_here = min(nsub, n_seg - seg0);
-                    for (int rt = 0; rt < n_rt; ++rt, ++g) {
-                        const unsigned ab = g & 1;
-                        mbar_wait(&bars.mma_done[ab], (g >> 1) & 1u);
-                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                        for (int sub = 0; sub < nsub_here; ++sub)
-                            ws_drain(tmem_base, (int)((ab * nsub + sub) * acc_stride), out_u, pitch, M, mtile, rt * mtile, seg0 + sub, q, lane, scale);
-                        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                        mbar_arrive(&bars.acc_empty[ab]);
-                    }
+                for (int stg = ks; stg < n_stages; stg += ksplit, ++g) {
+                    const unsigned ab = g & 1;
+                    const int rows = min(kTcN, n_chunks - stg * kTcN);                        // chunks of this stage
+                    mbar_wait(&bars.mma_done[ab], (g >> 1) & 1u);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + ab * (uint32_t)kTcN;
+                    float* o = out_u + (long long)stg * kTcN * kTcN + q * 32 + lane;        // chunk r of the stage: + r * 128 floats
+                    for (int r = 0; r < rows; r += 32)
+                        tc_store_rows<32>(taddr + r, o + r * kTcN, kTcN, r, rows, scale);
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    mbar_arrive(&bars.acc_empty[ab]);
                 }
             }
             mbar_arrive(&bars.ub_empty[cur]);
