@@ -308,12 +308,14 @@ fd_ws_kernel(const __grid_constant__ DevDesc d, const __grid_constant__ WsCfg cf
                         const float2* wb0 = wB + (b_col & 15);
                         #pragma unroll 1
                         for (int qd = b_grp; qd < nq4; qd += 2) {
-                            float2 w[4];
+                            float2 l4[4], b4[4], w[4];
                             #pragma unroll
                             for (int i = 0; i < 4; ++i) {
                                 const int p = min(qd * 4 + i, np);
-                                w[i] = cmul(wl0[p * cfg.sL], wb0[p * cfg.sB]);
+                                l4[i] = wl0[p * cfg.sL]; b4[i] = wb0[p * cfg.sB];
                             }
+                            #pragma unroll
+                            for (int i = 0; i < 4; ++i) w[i] = cmul(l4[i], b4[i]);
                             st_split8_f16_rowpair(sMhi, sMlo, b_off0 + (((qd ^ b_sw0) & 7) << 4), b_off0 + 128 + (((qd ^ b_sw1) & 7) << 4), w);
                         }
                         m_valid = true;
@@ -335,14 +337,20 @@ fd_ws_kernel(const __grid_constant__ DevDesc d, const __grid_constant__ WsCfg cf
                         const float2* q0 = tQ + a_q;
                         const float2* y0 = tY + a_y;
                         const float2* s0 = wS + sg;
-                        #pragma unroll 1
+                        // rows past the user's last chunk read the zero row (index np) of every table: no branch in the loop, the
+                        // twelve table loads of a slot quad are independent and issue back to back
+                        const int p_cap = ok ? np : 0, p_add = ok ? 0 : np;
+                        #pragma unroll 2
                         for (int qd = 0; qd < nq4; ++qd) {
-                            float2 a[4];
+                            float2 tq[4], ty[4], ts[4];
                             #pragma unroll
                             for (int i = 0; i < 4; ++i) {
-                                const int p = min(qd * 4 + i, np);
-                                a[i] = ok ? cmul(cmul(q0[p * cfg.sQ], y0[p * cfg.sY]), s0[p * cfg.sS]) : make_float2(0.f, 0.f);
+                                const int p = min(qd * 4 + i, p_cap) + p_add;
+                                tq[i] = q0[p * cfg.sQ]; ty[i] = y0[p * cfg.sY]; ts[i] = s0[p * cfg.sS];
                             }
+                            float2 a[4];
+                            #pragma unroll
+                            for (int i = 0; i < 4; ++i) a[i] = cmul(cmul(tq[i], ty[i]), ts[i]);
                             st_split8_f16(sNhi, sNlo, n_off0 + (((qd ^ n_sw) & 7) << 4), a);
                         }
                     }
