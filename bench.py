@@ -296,8 +296,9 @@ def run_workload(workload, users, steps, warmup, rank, world, dist, flush, want_
             layout = f"single [{plan.n_users} users] output tensor ({total_bytes / 2**30:.1f} GiB) rewritten every step"
         else:
             chunk = default_chunk_users(plan, int(float(os.environ.get("DMK_BENCH_CHUNK_GIB", "4")) * (1 << 30)))   # ring of 4 GiB chunks (SURVEY.md 8d cfg 5)
-            ring = [plan.alloc_out(chunk) for _ in range(3)]
-            layout = f"ring of 3 x {chunk} users ({chunk * per_user / 2**30:.1f} GiB) output chunks in HBM"
+            n_ring = int(os.environ.get("DMK_BENCH_RING", "3"))
+            ring = [plan.alloc_out(chunk) for _ in range(n_ring)]
+            layout = f"ring of {n_ring} x {chunk} users ({chunk * per_user / 2**30:.1f} GiB) output chunks in HBM"
         # masks once (also gives the algorithmic flop count)
         masks = plan.alloc_masks()
         i = 0

@@ -126,7 +126,7 @@ int check_arrays(const float* a, const float* b, const float* c, const float* e,
 // one-time opt-in to > 48 KB of dynamic shared memory is tracked per device: a process may call the library on
 // cuda:0 and then on cuda:1 (compute_channels(device=...), MacroDataset over several GPUs).
 constexpr int kMaxDevices = 64;
-constexpr int kSmemSmall = 72 * 1024, kSmemSmall2 = 100 * 1024, kSmemWs1 = 114 * 1024, kSmemWs4 = 220 * 1024, kSmemTc = 112 * 1024,
+constexpr int kSmemSmall = 72 * 1024, kSmemSmall2 = 100 * 1024, kSmemWs1 = 220 * 1024, kSmemWs4 = 220 * 1024, kSmemTc = 112 * 1024,
               kSmemFast = 110 * 1024, kSmemTile = 200 * 1024;
 struct DeviceState { bool ready = false; int sms = 0; };
 DeviceState g_dev[kMaxDevices];
@@ -265,11 +265,16 @@ int dmk_channels_fd(const dmk_desc* desc, const float* power_dbw, const float* p
     // Tiny arrays (M < 64) and FoV-sparse scenarios are per-user-overhead bound: the packed-FP32 kernel is faster there
     // (profiles/README.md); DMK_FD_KERNEL=tc still forces the tensor-core kernel.
     const bool want_tc = hint == DMK_KERNEL_TC || hint == DMK_KERNEL_TC1;
-    const bool use_tc = affine && !d.has_time_axis && div_ok && (d.K % (kTcN / 2) == 0) && d.K <= 4096 && tc_smem <= (size_t)kSmemTc &&
-                        !want_tile && !want_ffma && ((d.M >= 64 && !d.fov_any) || want_tc);   // FoV leaves few paths, tiny arrays little output: FP32 kernel wins
-    const bool use_fast = !use_tc && affine && !d.has_time_axis && div_ok && fast_smem <= (size_t)kSmemFast && !want_tile;
+    // Where the tensor-core kernels pay: at least one full stage of 128 chunks (512 B each) per user, or a panel of >= 64 elements.
+    // FoV-sparse scenarios leave few paths per user (per-user overhead dominates): packed-FP32 kernel.  Measured: profiles/README.md.
+    const long long n_chunks_u = (long long)d.M * (d.K / (kTcN / 2));
+    const bool tc_shape = (d.M >= 64 || n_chunks_u >= 128) && !d.fov_any;
+    const bool use_tc = affine && !d.has_time_axis && div_ok && (d.K % (kTcN / 2) == 0) && d.K <= 4096 &&
+                        !want_tile && !want_ffma && hint != DMK_KERNEL_SMALL && hint != DMK_KERNEL_SMALL1 && (tc_shape || want_tc);
+    const bool use_tc1 = use_tc && tc_smem <= (size_t)kSmemTc;            // one-CTA-per-user tensor-core kernel: fallback of the persistent one
+    const bool use_fast = !use_tc1 && affine && !d.has_time_axis && div_ok && fast_smem <= (size_t)kSmemFast && !want_tile;
     const int tile_w_tc1 = (kTcN / 2) * tcfg.nsub;
-    const int tile_w = use_tc ? tile_w_tc1 : (use_fast ? kTKW : kTK);
+    const int tile_w = use_tc1 ? tile_w_tc1 : (use_fast ? kTKW : kTK);
     const int n_ct = (ncols + tile_w - 1) / tile_w;
     // Few users: split each user's column tiles over several CTAs so the grid covers >= 4 waves.
     const long long want = 4LL * 2 * dev->sms;
@@ -278,13 +283,88 @@ int dmk_channels_fd(const dmk_desc* desc, const float* power_dbw, const float* p
     if (ksplit < 1) ksplit = 1;
     const long long grid = n_users * ksplit;
     if (grid > 0x7fffffffLL) return fail(DMK_ERR_INVALID_ARG, "grid too large: split the user range");
+    // Warp-specialised persistent tensor-core kernel in the flat-chunk formulation (dmk_fd_ws.cuh): the production path.
+    // DMK_KERNEL_TC1 keeps the one-CTA-per-user kernel, which also takes the shapes whose tables do not fit next to the
+    // 64 KB of operand tiles.
+    const bool want_tc1 = hint == DMK_KERNEL_TC1;
+    if (use_tc && !want_tc1) {
+        WsCfg w;
+        memset(&w, 0, sizeof(w));
+        const int pc = (d.P > 0 ? d.P : 1) + 1;                  // + the zero row the builders read for padding slots
+        w.S = d.K / (kTcN / 2);
+        const long long n_chunks = (long long)d.M * w.S;
+        w.n_chunks = (int)n_chunks;
+        w.n_stages = (int)((n_chunks + kTcN - 1) / kTcN);
+        size_t off = 0;
+        auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 15) & ~size_t(15); return (int)o; };
+        w.off_N = take((size_t)2 * kTcN * 128);
+        w.off_M = take((size_t)2 * kTcN * 128);
+        w.off_tab = (int)off;
+        size_t toff = 0;
+        auto ttake = [&](size_t bytes) { size_t o = toff; toff += (bytes + 15) & ~size_t(15); return (int)o; };
+        w.sY = d.bs0 | 1; w.sQ = (d.Mr * d.bs1) | 1; w.sB = 17; w.sL = 5; w.sS = w.S | 1;
+        w.off_tY = ttake((size_t)pc * w.sY * sizeof(float2));
+        w.off_tQ = ttake((size_t)pc * w.sQ * sizeof(float2));
+        w.off_wB = ttake((size_t)pc * w.sB * sizeof(float2));
+        w.off_wL = ttake((size_t)pc * w.sL * sizeof(float2));
+        w.off_wS = ttake((size_t)pc * w.sS * sizeof(float2));
+        const size_t buf_bytes = ((sizeof(TcUserBuf) + 15) & ~size_t(15)) + toff;      // [user record][tables]
+        w.tab_bytes = (int)buf_bytes;
+        w.mul_mt = cfg.mul_mt; w.mul_bs0 = cfg.mul_bs0;
+        w.mul_s = w.S > 1 ? (unsigned)((0x100000000ULL + w.S - 1) / w.S) : 0u;
+        const bool chunk_div_ok = n_chunks * (long long)w.S < 0xffffffffLL && n_chunks < 0x7fffffffLL / kTcN;
+        // One helper warp prepares a user in ~30-45 k cycles (float64 prologue + tables, latency-bound).  Users whose output is
+        // written faster than that (< ~400 KB) make the kernel helper-bound: they get four helper warps and eight buffers in a
+        // single CTA per SM (shared memory and registers allow it because only one CTA is resident).
+        const size_t per_user_bytes = (size_t)d.M * d.K * sizeof(float2);
+        const size_t smem1 = 1024 + off + 2 * buf_bytes, smem4 = 1024 + off + 8 * buf_bytes;
+        const int hf = desc->ws_helpers;                      // 0 = by shape, 1 or 4 pins the instantiation (tests, A/B timing)
+        int n_helpers = 0;
+        bool one_cta = false;                                 // one helper, but the tables leave room for a single CTA per SM only
+        if ((per_user_bytes <= 384 * 1024 || hf == 4 || smem1 > 113200) && smem4 <= (size_t)kSmemWs4 && hf != 1) n_helpers = 4;
+        else if (smem1 <= 113200) n_helpers = 1;              // + static + 1 KB reserve: two CTAs per SM
+        else if (smem1 <= (size_t)kSmemWs4) { n_helpers = 1; one_cta = true; }    // wide panels (e.g. 64 x 4): still persistent
+        // Few users: split each user's stages over several CTAs so the grid covers >= 4 waves.
+        long long wsplit = (want + n_users - 1) / n_users;
+        if (wsplit > w.n_stages) wsplit = w.n_stages;
+        if (wsplit < 1) wsplit = 1;
+        const long long items = n_users * wsplit;
+        if (n_helpers && chunk_div_ok && items < 0xffffff00LL) {
+            const size_t ws_smem = n_helpers == 1 ? smem1 : smem4;
+            static std::atomic<unsigned> ticket_seq{0};
+            unsigned int* tickets = nullptr;
+            cudaError_t e = cudaGetSymbolAddress(reinterpret_cast<void**>(&tickets), g_tc_ticket);
+            if (e != cudaSuccess) return cuda_fail(e, "cudaGetSymbolAddress(g_tc_ticket)");
+            const long long resident = ((n_helpers == 1 && !one_cta) ? 2LL : 1LL) * dev->sms;
+            const long long pgrid = items < resident ? items : resident;
+            // Programmatic dependent launch: the kernel releases its dependents at once, so the next libdmk launch can fill SMs
+            // as this one's persistent CTAs retire.  Unless the caller set DMK_FLAG_INDEPENDENT_LAUNCH the kernel itself
+            // waits for the previous grid (griddepcontrol.wait) before touching memory: plain stream order.
+            const int pdl_wait = (desc->flags & DMK_FLAG_INDEPENDENT_LAUNCH) ? 0 : 1;
+            cudaLaunchConfig_t lc;
+            memset(&lc, 0, sizeof(lc));
+            lc.gridDim = dim3((unsigned)pgrid); lc.blockDim = dim3((9 + n_helpers) * 32); lc.dynamicSmemBytes = ws_smem; lc.stream = st;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            at[0].val.programmaticStreamSerializationAllowed = 1;
+            lc.attrs = at; lc.numAttrs = 1;
+            unsigned int* tk = tickets + (ticket_seq.fetch_add(1) % kTcTickets);
+            if (n_helpers == 1) e = cudaLaunchKernelEx(&lc, fd_ws_kernel<1>, d, w, (int)wsplit, (unsigned)items, tk, pdl_wait);
+            else                e = cudaLaunchKernelEx(&lc, fd_ws_kernel<4>, d, w, (int)wsplit, (unsigned)items, tk, pdl_wait);
+            if (e != cudaSuccess) return cuda_fail(e, "fd_ws_kernel launch");
+            g_launches.fetch_add(1);
+            snprintf(g_kernel, sizeof(g_kernel), "fd_ws_kernel<128 chunks x 64 sc,3xf16,%d helper%s> grid=%lld items=%lld ksplit=%lld stages=%d smem=%zu",
+                     n_helpers, n_helpers > 1 ? "s" : "", pgrid, items, wsplit, w.n_stages, ws_smem);
+            return DMK_OK;
+        }
+    }
     // Small arrays (M <= 16): warp-level kernels, see dmk_fd_small.cuh.  Default: the densely packed fd_small2_kernel;
     // DMK_KERNEL_SMALL1 keeps the round-1 one-warp-per-user kernel for A/B timing.
     {
         const int pc = d.P > 0 ? d.P : 1;
         const int mt = d.M <= 4 ? 4 : (d.M <= 8 ? 8 : 16);
         const bool small_shape = affine && !d.has_time_axis && div_ok && d.M <= 16 && d.K <= 4096;
-        const bool small_wanted = !want_tile && !want_ffma && !want_tc;
+        const bool small_wanted = !want_tile && !want_ffma && !want_tc;      // (shapes the persistent tensor-core kernel took never get here)
         if (small_shape && small_wanted && hint != DMK_KERNEL_SMALL1) {
             Small2Cfg sc;
             memset(&sc, 0, sizeof(sc));
@@ -357,80 +437,7 @@ int dmk_channels_fd(const dmk_desc* desc, const float* power_dbw, const float* p
             return DMK_OK;
         }
     }
-    // Warp-specialised persistent tensor-core kernel in the flat-chunk formulation (dmk_fd_ws.cuh): the production path.
-    // DMK_KERNEL_TC1 keeps the one-CTA-per-user kernel, which also takes the shapes whose tables do not fit next to the
-    // 64 KB of operand tiles.
-    const bool want_tc1 = hint == DMK_KERNEL_TC1;
-    if (use_tc && !want_tc1) {
-        WsCfg w;
-        memset(&w, 0, sizeof(w));
-        const int pc = (d.P > 0 ? d.P : 1) + 1;                  // + the zero row the builders read for padding slots
-        w.S = d.K / (kTcN / 2);
-        const long long n_chunks = (long long)d.M * w.S;
-        w.n_chunks = (int)n_chunks;
-        w.n_stages = (int)((n_chunks + kTcN - 1) / kTcN);
-        size_t off = 0;
-        auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 15) & ~size_t(15); return (int)o; };
-        w.off_N = take((size_t)2 * kTcN * 128);
-        w.off_M = take((size_t)2 * kTcN * 128);
-        w.off_tab = (int)off;
-        size_t toff = 0;
-        auto ttake = [&](size_t bytes) { size_t o = toff; toff += (bytes + 15) & ~size_t(15); return (int)o; };
-        w.sY = d.bs0 | 1; w.sQ = (d.Mr * d.bs1) | 1; w.sB = 17; w.sL = 5; w.sS = w.S | 1;
-        w.off_tY = ttake((size_t)pc * w.sY * sizeof(float2));
-        w.off_tQ = ttake((size_t)pc * w.sQ * sizeof(float2));
-        w.off_wB = ttake((size_t)pc * w.sB * sizeof(float2));
-        w.off_wL = ttake((size_t)pc * w.sL * sizeof(float2));
-        w.off_wS = ttake((size_t)pc * w.sS * sizeof(float2));
-        const size_t buf_bytes = ((sizeof(TcUserBuf) + 15) & ~size_t(15)) + toff;      // [user record][tables]
-        w.tab_bytes = (int)buf_bytes;
-        w.mul_mt = cfg.mul_mt; w.mul_bs0 = cfg.mul_bs0;
-        w.mul_s = w.S > 1 ? (unsigned)((0x100000000ULL + w.S - 1) / w.S) : 0u;
-        const bool chunk_div_ok = n_chunks * (long long)w.S < 0xffffffffLL && n_chunks < 0x7fffffffLL / kTcN;
-        // One helper warp prepares a user in ~30-45 k cycles (float64 prologue + tables, latency-bound).  Users whose output is
-        // written faster than that (< ~400 KB) make the kernel helper-bound: they get four helper warps and eight buffers in a
-        // single CTA per SM (shared memory and registers allow it because only one CTA is resident).
-        const size_t per_user_bytes = (size_t)d.M * d.K * sizeof(float2);
-        const size_t smem1 = 1024 + off + 2 * buf_bytes, smem4 = 1024 + off + 8 * buf_bytes;
-        const int hf = desc->ws_helpers;                      // 0 = by shape, 1 or 4 pins the instantiation (tests, A/B timing)
-        int n_helpers = 0;
-        if ((per_user_bytes <= 384 * 1024 || hf == 4 || smem1 > 113200) && smem4 <= (size_t)kSmemWs4 && hf != 1) n_helpers = 4;
-        else if (smem1 <= 113200) n_helpers = 1;              // + ~2.6 KB static + 1 KB reserve: two CTAs per SM
-        // Few users: split each user's stages over several CTAs so the grid covers >= 4 waves.
-        long long wsplit = (want + n_users - 1) / n_users;
-        if (wsplit > w.n_stages) wsplit = w.n_stages;
-        if (wsplit < 1) wsplit = 1;
-        const long long items = n_users * wsplit;
-        if (n_helpers && chunk_div_ok && items < 0xffffff00LL) {
-            const size_t ws_smem = n_helpers == 1 ? smem1 : smem4;
-            static std::atomic<unsigned> ticket_seq{0};
-            unsigned int* tickets = nullptr;
-            cudaError_t e = cudaGetSymbolAddress(reinterpret_cast<void**>(&tickets), g_tc_ticket);
-            if (e != cudaSuccess) return cuda_fail(e, "cudaGetSymbolAddress(g_tc_ticket)");
-            const long long resident = (n_helpers == 1 ? 2LL : 1LL) * dev->sms;
-            const long long pgrid = items < resident ? items : resident;
-            // Programmatic dependent launch: the kernel releases its dependents at once, so the next libdmk launch can fill SMs
-            // as this one's persistent CTAs retire.  Unless the caller set DMK_FLAG_INDEPENDENT_LAUNCH the kernel itself
-            // waits for the previous grid (griddepcontrol.wait) before touching memory: plain stream order.
-            const int pdl_wait = (desc->flags & DMK_FLAG_INDEPENDENT_LAUNCH) ? 0 : 1;
-            cudaLaunchConfig_t lc;
-            memset(&lc, 0, sizeof(lc));
-            lc.gridDim = dim3((unsigned)pgrid); lc.blockDim = dim3((9 + n_helpers) * 32); lc.dynamicSmemBytes = ws_smem; lc.stream = st;
-            cudaLaunchAttribute at[1];
-            at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-            at[0].val.programmaticStreamSerializationAllowed = 1;
-            lc.attrs = at; lc.numAttrs = 1;
-            unsigned int* tk = tickets + (ticket_seq.fetch_add(1) % kTcTickets);
-            if (n_helpers == 1) e = cudaLaunchKernelEx(&lc, fd_ws_kernel<1>, d, w, (int)wsplit, (unsigned)items, tk, pdl_wait);
-            else                e = cudaLaunchKernelEx(&lc, fd_ws_kernel<4>, d, w, (int)wsplit, (unsigned)items, tk, pdl_wait);
-            if (e != cudaSuccess) return cuda_fail(e, "fd_ws_kernel launch");
-            g_launches.fetch_add(1);
-            snprintf(g_kernel, sizeof(g_kernel), "fd_ws_kernel<128 chunks x 64 sc,3xf16,%d helper%s> grid=%lld items=%lld ksplit=%lld stages=%d smem=%zu",
-                     n_helpers, n_helpers > 1 ? "s" : "", pgrid, items, wsplit, w.n_stages, ws_smem);
-            return DMK_OK;
-        }
-    }
-    if (use_tc) {
+    if (use_tc1) {
         fd_tc_kernel<<<(unsigned)grid, kTcThreads, tc_smem, st>>>(d, tcfg, (int)ksplit);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return cuda_fail(e, "fd_tc_kernel launch");

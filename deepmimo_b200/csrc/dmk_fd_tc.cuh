@@ -463,13 +463,14 @@ fd_tc_kernel(const __grid_constant__ DevDesc d, const __grid_constant__ TcCfg cf
 
 
 // Shared with the warp-specialised persistent kernel (dmk_fd_ws.cuh): device-side ticket counters and the per-user record.
-constexpr int kTcTickets = 64;
+constexpr int kTcTickets = 512;      // > resident CTA slots (2 x 148) and > the 128 concurrent grids of a device: launches in flight never share a slot
 __device__ unsigned int g_tc_ticket[kTcTickets];   // zero between launches: the CTA that draws the last ticket resets it
 
 struct TcUserBuf {
     FdShared sh;
     float scale;
     unsigned int item;
+    unsigned char m_fov[kMaxPaths], m_valid[kMaxPaths], m_clip[kMaxPaths];   // mask bytes of the user: written to global memory by the drain warps
 };
 
 }  // namespace dmk

@@ -123,7 +123,6 @@ __device__ __noinline__ void ws_helper_prepare(const DevDesc& d, const WsCfg& cf
     t = __shfl_sync(0xffffffffu, t, 0);
     if (t >= n_items) return;
     const long long user = t / (unsigned)ksplit;
-    const bool write_masks = (t % (unsigned)ksplit) == 0;
     FdShared& sh = ub.sh;
 
     PathState st;
@@ -148,12 +147,11 @@ __device__ __noinline__ void ws_helper_prepare(const DevDesc& d, const WsCfg& cf
         sh.u[1][j] = st.u[1]; sh.v[1][j] = st.v[1];
     }
     if (lane == 0) sh.np = np;
-    if (write_masks && active) {
-        const long long o = user * (long long)d.P0 + lane;
-        if (d.fov_mask)   d.fov_mask[o]   = st.fov ? 1 : 0;
-        if (d.valid_mask) d.valid_mask[o] = st.valid ? 1 : 0;
-        if (d.clip_mask)  d.clip_mask[o]  = (st.valid && st.over) ? 1 : 0;
-    }
+    // The masks are outputs: they leave the SM with the drain warps, the only role that orders itself after the previous launch
+    // (griddepcontrol.wait); everything the helper, the builders and the issuer do touches shared / tensor memory and inputs only.
+    ub.m_fov[lane]   = st.fov ? 1 : 0;
+    ub.m_valid[lane] = st.valid ? 1 : 0;
+    ub.m_clip[lane]  = (st.valid && st.over) ? 1 : 0;
     if (np == 0) return;
     // per-user operand scale: largest |c_p| component (FP16 operands live in [-1, 1])
     float mx = contrib ? fmaxf(fabsf(st.c.x), fabsf(st.c.y)) : 0.f;
@@ -226,8 +224,10 @@ fd_ws_kernel(const __grid_constant__ DevDesc d, const __grid_constant__ WsCfg cf
 {
     extern __shared__ unsigned char smem_raw[];
     __shared__ WsBars bars;
-    if (pdl_wait) asm volatile("griddepcontrol.wait;" ::: "memory");     // plain stream order unless the caller declared independence
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");      // the next launch may take SMs as our CTAs retire
+    // Programmatic dependent launch.  The next launch may take SMs as our CTAs retire; unless the caller declared this launch
+    // independent, the drain warps -- the only role that writes global memory -- order themselves after the previous grid before
+    // their first store, while prologue, tables, operand tiles and the first MMAs of this launch already run under its tail.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     __shared__ uint32_t tmem_base_s;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -410,6 +410,7 @@ fd_ws_kernel(const __grid_constant__ DevDesc d, const __grid_constant__ WsCfg cf
     } else {
         // ------------------------------------------------------------------------------------------ drain warps 0-3
         const int q = warp;                                   // TMEM lane quarter = 32 floats (128 bytes) of every chunk
+        if (pdl_wait) asm volatile("griddepcontrol.wait;" ::: "memory");     // everything before this launch has completed and is visible
         unsigned g = 0;
         unsigned it = 0, done = 0;
         int cur = 0;
@@ -421,6 +422,12 @@ fd_ws_kernel(const __grid_constant__ DevDesc d, const __grid_constant__ WsCfg cf
             const int np = ub.sh.np;
             const float scale = ub.scale;
             float* out_u = reinterpret_cast<float*>(d.out) + user * (long long)n_chunks * kTcN;
+            if (q == 0 && ks == 0 && lane < d.P0) {
+                const long long o = user * (long long)d.P0 + lane;
+                if (d.fov_mask)   d.fov_mask[o]   = ub.m_fov[lane];
+                if (d.valid_mask) d.valid_mask[o] = ub.m_valid[lane];
+                if (d.clip_mask)  d.clip_mask[o]  = ub.m_clip[lane];
+            }
             if (np == 0) {
                 // users without contributing paths: zeros (channel.py:257,:269-271); a stage is 64 KB of contiguous output
                 const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
