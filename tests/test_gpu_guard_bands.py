@@ -59,16 +59,15 @@ def test_fd_odd_column_counts_stay_in_bounds(sel):
     _run_guarded(_plan((7, 3), (1, 2), 1024, sel, 29))
 
 
-@pytest.mark.parametrize("variant", ["auto", "small1"])
+@pytest.mark.parametrize("variant", ["small", "small1"])
 @pytest.mark.parametrize("bs,ue,sel", [((8, 1), (1, 1), np.arange(64)), ((3, 1), (1, 1), np.arange(7)), ((4, 2), (2, 1), np.arange(130)),
                                         ((1, 1), (1, 1), np.arange(1)), ((5, 1), (1, 3), 2 + 5 * np.arange(33)),
                                         ((4, 4), (1, 1), np.arange(300)), ((2, 1), (2, 1), 7 + 3 * np.arange(1000))])
 def test_small_array_kernel_stays_in_bounds(bs, ue, sel, variant, monkeypatch):
     from deepmimo_b200 import _lib
-    if variant != "auto":
-        monkeypatch.setenv("DMK_FD_KERNEL", variant)
+    monkeypatch.setenv("DMK_FD_KERNEL", variant)
     _run_guarded(_plan(bs, ue, 4096, sel, 53))
-    assert _lib.last_kernel().startswith("fd_small2_kernel" if variant == "auto" else "fd_small_kernel<"), _lib.last_kernel()
+    assert _lib.last_kernel().startswith("fd_small2_kernel" if variant == "small" else "fd_small_kernel<"), _lib.last_kernel()
 
 
 @pytest.mark.parametrize("times", [None, np.arange(16) * 1e-3, np.arange(5) * 1e-3, np.arange(70) * 1e-4])

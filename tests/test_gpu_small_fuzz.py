@@ -24,7 +24,7 @@ CASES = [
 ]
 
 
-@pytest.mark.parametrize("variant", ["auto", "small1"])
+@pytest.mark.parametrize("variant", ["small", "small1"])
 @pytest.mark.parametrize("case", range(len(CASES)))
 def test_small_kernels_match_oracle(case, variant, monkeypatch):
     import deepmimo_b200 as dmb
@@ -32,8 +32,7 @@ def test_small_kernels_match_oracle(case, variant, monkeypatch):
     from deepmimo_b200.synth import make_paths
     from oracle import channel_oracle as orc
     bs, ue, n_sc, sel, n, fov, pats, num_paths, holes, per_user = CASES[case]
-    if variant != "auto":
-        monkeypatch.setenv("DMK_FD_KERNEL", variant)
+    monkeypatch.setenv("DMK_FD_KERNEL", variant)      # "small": the dense kernel even where the tensor-core kernel would take the shape
     d = make_paths(n, 900 + case, n_sc=n_sc, bandwidth=50e6, zero_frac=0.15, clip_frac=0.02)
     if holes:
         hole = np.random.default_rng(case).random(d["power"].shape) < 0.2
@@ -48,7 +47,7 @@ def test_small_kernels_match_oracle(case, variant, monkeypatch):
     bs_fov, ue_fov = (None, None) if fov is None else (np.array(fov[0]), np.array(fov[1]))
     H, info = make_dataset(dmb, d, bs_fov, ue_fov).compute_channels(dmb.ChannelGenParameters(p), return_info=True, warn=False)
     o = orc.compute_channels(d, **oracle_kwargs_from_params(p, bs_fov, ue_fov))
-    assert info.kernel.startswith("fd_small2_kernel" if variant == "auto" else "fd_small_kernel<"), info.kernel
+    assert info.kernel.startswith("fd_small2_kernel" if variant == "small" else "fd_small_kernel<"), info.kernel
     err = assert_channels_close(H, o["H"], what=f"small case {case} {variant}")
     assert np.array_equal(info.valid, o["valid"]) and np.array_equal(info.clip, o["clip"])
     if o["fov_mask"] is None:
