@@ -55,7 +55,7 @@ def kernel_hint_from_env(var: str = "DMK_FD_KERNEL") -> int:
     if v not in KERNEL_HINTS:
         raise ValueError(f"{var}={v!r}: expected one of {sorted(k for k in KERNEL_HINTS if k)}")
     return KERNEL_HINTS[v]
-SYMBOLS = ("dmk_channels_fd", "dmk_channels_td", "dmk_beam_amplitude_fd", "dmk_path_prologue", "dmk_np_sincosf",
+SYMBOLS = ("dmk_channels_fd", "dmk_channels_td", "dmk_channels_td_tau", "dmk_beam_amplitude_fd", "dmk_path_prologue", "dmk_user_byproducts", "dmk_np_sincosf",
            "dmk_last_error", "dmk_abi_version", "dmk_launch_count", "dmk_last_kernel")
 
 
@@ -71,10 +71,14 @@ def _declare(lib: ctypes.CDLL) -> None:
     lib.dmk_channels_fd.restype = ctypes.c_int
     lib.dmk_channels_td.argtypes = common + [vp, vp, vp, vp]
     lib.dmk_channels_td.restype = ctypes.c_int
+    lib.dmk_channels_td_tau.argtypes = common + [vp, vp, vp, vp, vp]
+    lib.dmk_channels_td_tau.restype = ctypes.c_int
     lib.dmk_beam_amplitude_fd.argtypes = [desc_p] + [vp] * 7 + [vp, i64, i32, vp, i32, vp, vp, vp, vp, vp]
     lib.dmk_beam_amplitude_fd.restype = ctypes.c_int
     lib.dmk_path_prologue.argtypes = [desc_p] + [vp] * 5 + [vp, i64, i32, vp, vp, vp, vp]
     lib.dmk_path_prologue.restype = ctypes.c_int
+    lib.dmk_user_byproducts.argtypes = [desc_p] + [vp] * 6 + [vp, vp, i64, i32, vp, vp, vp, vp, vp]
+    lib.dmk_user_byproducts.restype = ctypes.c_int
     lib.dmk_np_sincosf.argtypes = [vp, vp, vp, i64, vp]
     lib.dmk_np_sincosf.restype = ctypes.c_int
     lib.dmk_last_error.restype = ctypes.c_char_p

@@ -337,6 +337,8 @@ class ChannelPlan:
         with torch.cuda.device(self.device):
             if self.spec.freq_domain:
                 rc = self.lib.dmk_channels_fd(*common, mp("fov"), mp("valid"), mp("clip"), st.cuda_stream)
+            elif m.get("tau") is not None:
+                rc = self.lib.dmk_channels_td_tau(*common, mp("fov"), mp("valid"), mp("slot"), mp("tau"), st.cuda_stream)
             else:
                 rc = self.lib.dmk_channels_td(*common, mp("fov"), mp("valid"), mp("slot"), st.cuda_stream)
         _lib.check(rc)

@@ -476,6 +476,15 @@ int dmk_channels_td(const dmk_desc* desc, const float* power_dbw, const float* p
                     const double* ue_rot_deg, const float* doppler_hz, int64_t n_users, int32_t ld, void* out_c64,
                     uint8_t* fov_mask, uint8_t* valid_mask, int32_t* path_slot, void* cuda_stream)
 {
+    return dmk_channels_td_tau(desc, power_dbw, phase_deg, delay_s, aoa_az_deg, aoa_el_deg, aod_az_deg, aod_el_deg, ue_rot_deg,
+                               doppler_hz, n_users, ld, out_c64, fov_mask, valid_mask, path_slot, nullptr, cuda_stream);
+}
+
+int dmk_channels_td_tau(const dmk_desc* desc, const float* power_dbw, const float* phase_deg, const float* delay_s,
+                        const float* aoa_az_deg, const float* aoa_el_deg, const float* aod_az_deg, const float* aod_el_deg,
+                        const double* ue_rot_deg, const float* doppler_hz, int64_t n_users, int32_t ld, void* out_c64,
+                        uint8_t* fov_mask, uint8_t* valid_mask, int32_t* path_slot, float* tau, void* cuda_stream)
+{
     using namespace dmk;
     DevDesc d;
     int rc = build_desc(desc, false, d);
@@ -487,7 +496,7 @@ int dmk_channels_td(const dmk_desc* desc, const float* power_dbw, const float* p
     if (n_users > 0x7fffffffLL) return fail(DMK_ERR_INVALID_ARG, "grid too large: split the user range");
     bind_arrays(d, power_dbw, phase_deg, delay_s, aoa_az_deg, aoa_el_deg, aod_az_deg, aod_el_deg, ue_rot_deg, doppler_hz, n_users, ld);
     d.out = reinterpret_cast<float2*>(out_c64);
-    d.fov_mask = fov_mask; d.valid_mask = valid_mask; d.path_slot = path_slot;
+    d.fov_mask = fov_mask; d.valid_mask = valid_mask; d.path_slot = path_slot; d.tau_out = tau;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(cuda_stream);
     const DeviceState* dev = nullptr;
     rc = device_state(dev);
@@ -608,6 +617,31 @@ int dmk_path_prologue(const dmk_desc* desc, const float* power_dbw, const float*
     prologue_kernel<<<(unsigned)grid, 256, 0, st>>>(d, angles_rot, power_gain);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "prologue_kernel launch");
+    g_launches.fetch_add(1);
+    return DMK_OK;
+}
+
+int dmk_user_byproducts(const dmk_desc* desc, const float* power_dbw, const float* phase_deg,
+                        const float* aoa_az_deg, const float* aoa_el_deg, const float* aod_az_deg, const float* aod_el_deg,
+                        const float* inter, const double* ue_rot_deg, int64_t n_users, int32_t ld,
+                        int32_t* num_paths, int32_t* los, float* pathloss_coherent, float* pathloss_noncoherent, void* cuda_stream)
+{
+    using namespace dmk;
+    DevDesc d;
+    int rc = build_desc(desc, false, d);
+    if (rc) return rc;
+    rc = check_arrays(power_dbw, phase_deg, power_dbw, aoa_az_deg, aoa_el_deg, aod_az_deg, aod_el_deg, n_users, ld, d.P0);
+    if (rc) return rc;
+    if (n_users == 0) return DMK_OK;
+    if (los && !inter) return fail(DMK_ERR_INVALID_ARG, "los needs the interaction codes");
+    // delay is not needed for the by-products: alias it to power (never dereferenced by the time-domain gain chain)
+    bind_arrays(d, power_dbw, phase_deg, power_dbw, aoa_az_deg, aoa_el_deg, aod_az_deg, aod_el_deg, ue_rot_deg, nullptr, n_users, ld);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(cuda_stream);
+    const long long grid = (n_users * 32 + 255) / 256;
+    if (grid > 0x7fffffffLL) return fail(DMK_ERR_INVALID_ARG, "grid too large: split the user range");
+    user_byproducts_kernel<<<(unsigned)grid, 256, 0, st>>>(d, inter, num_paths, los, pathloss_coherent, pathloss_noncoherent);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "user_byproducts_kernel launch");
     g_launches.fetch_add(1);
     return DMK_OK;
 }

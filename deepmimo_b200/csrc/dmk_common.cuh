@@ -42,6 +42,7 @@ struct DevDesc {
     const double* ue_rot;         // per-user [n,3] degrees or nullptr
     uint8_t *fov_mask, *valid_mask, *clip_mask;
     int32_t* path_slot;
+    float*   tau_out;             // time domain only: [n, P] delay of the path in each output slot, 0 in empty slots (Sionna layout), or nullptr
     float2*  out;
 };
 

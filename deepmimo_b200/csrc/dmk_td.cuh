@@ -47,6 +47,13 @@ __device__ __forceinline__ void td_cta_prologue(const DevDesc& d, long long user
             if (d.valid_mask) d.valid_mask[o] = st.valid ? 1 : 0;
             if (d.path_slot)  d.path_slot[o]  = st.valid ? j : -1;
         }
+        if (d.tau_out) {
+            // slot j <- ToA of the j-th valid column (sionna_adapter.py:196-198: tau[..., :num_paths] = ToA), zeros behind
+            float* tau_u = d.tau_out + user * (long long)d.P;
+            if (active && st.valid) tau_u[j] = d.delay[user * (long long)d.ld + lane];
+            const int nv = __popc(ballot);
+            if (lane >= nv && lane < d.P) tau_u[lane] = 0.f;
+        }
     }
     __syncthreads();
 }
@@ -153,6 +160,61 @@ prologue_kernel(const __grid_constant__ DevDesc d, double* __restrict__ angles_r
     }
     if (power_gain) power_gain[idx] = st.pw;
     if (d.fov_mask) d.fov_mask[idx] = st.fov ? 1 : 0;
+}
+
+// Per-user by-products, one warp per user, lanes = path columns:
+//   num_paths  = count of non-NaN FoV-filtered AoA azimuths over ALL columns            (dataset.py:613-619)
+//   los        = 1 / 0 / -1 from the interaction code of the first in-FoV path           (dataset.py:569-611)
+//   pathloss   = -10 log10 |sum_p sqrt(p_lin) e^{j phase}|^2 (coherent) / (sum_p sqrt(p_lin))^2 (non-coherent), NaN where 0
+//                over the raw power / phase matrices, no FoV, no element pattern         (dataset.py:541-566)
+__global__ void __launch_bounds__(256)
+user_byproducts_kernel(const __grid_constant__ DevDesc d, const float* __restrict__ inter, int* __restrict__ num_paths,
+                       int* __restrict__ los, float* __restrict__ pl_coh, float* __restrict__ pl_noncoh)
+{
+    const long long user = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (user >= d.n_users) return;
+    const bool active = lane < d.P0;
+    PathState st;
+    st.fov = false; st.ph[1] = __longlong_as_double(0x7ff8000000000000LL);
+    if (active) path_prologue_angles(d, user, lane, st);
+    const bool counted = active && !(st.ph[1] != st.ph[1]) && (!d.fov_any || st.fov);     // where(mask, aoa_az_rot, NaN) is not NaN
+    const int np = __popc(__ballot_sync(0xffffffffu, counted));
+    const unsigned fovb = __ballot_sync(0xffffffffu, active && st.fov);
+    const long long row = user * (long long)d.ld;
+    if (lane == 0) {
+        if (num_paths) num_paths[user] = np;
+        if (los) {
+            const bool has = d.fov_any ? (fovb != 0u) : (np > 0);
+            const int first = d.fov_any ? (fovb ? __ffs(fovb) - 1 : 0) : 0;
+            const float code = inter ? inter[row + first] : __int_as_float(0x7fc00000);
+            los[user] = has ? ((d.fov_any && !fovb) ? 0 : (code == 0.0f ? 1 : 0)) : -1;
+        }
+    }
+    if (pl_coh || pl_noncoh) {
+        double re = 0.0, im = 0.0, amp_sum = 0.0;
+        if (active) {
+            const float pw_db = d.power[row + lane];
+            const float amp = __fsqrt_rn(exp10f(__fdiv_rn(pw_db, 10.0f)));                 // generator_utils.py:35, sqrt in float32
+            float sn, cs;
+            sincosf(__fmul_rn(d.phase[row + lane], 0x1.1df46ap-6f), &sn, &cs);             // np.deg2rad on float32, exp(1j x)
+            const float gr = __fmul_rn(amp, cs), gi = __fmul_rn(amp, sn);
+            if (!(amp != amp)) amp_sum = (double)amp;                                       // nansum drops NaN entries
+            if (!(gr != gr) && !(gi != gi)) { re = (double)gr; im = (double)gi; }
+        }
+        #pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            re += __shfl_xor_sync(0xffffffffu, re, o);
+            im += __shfl_xor_sync(0xffffffffu, im, o);
+            amp_sum += __shfl_xor_sync(0xffffffffu, amp_sum, o);
+        }
+        if (lane == 0) {
+            const float nanf_ = __int_as_float(0x7fc00000);
+            const double tc = re * re + im * im, tn = amp_sum * amp_sum;
+            if (pl_coh)    pl_coh[user]    = tc > 0.0 ? (float)(-10.0 * log10(tc)) : nanf_;
+            if (pl_noncoh) pl_noncoh[user] = tn > 0.0 ? (float)(-10.0 * log10(tn)) : nanf_;
+        }
+    }
 }
 
 __global__ void np_sincosf_kernel(const float* __restrict__ x, float* __restrict__ s, float* __restrict__ c, long long n)

@@ -135,37 +135,23 @@ class Dataset(DotDict):
         return 10 ** (self["power"] / 10)
 
     def compute_pathloss(self, coherent: bool = True) -> np.ndarray:
-        """Path loss in dB per user (dataset.py:541-566): -10 log10 |sum_p sqrt(p_lin) e^{j phase}|^2, NaN where no power."""
-        p_lin = 10 ** (self["power"] / 10)
-        gains = np.sqrt(p_lin).astype(np.complex64)
-        if coherent:
-            gains *= np.exp(1j * np.deg2rad(self["phase"]))
-        total = np.abs(np.nansum(gains, axis=1)) ** 2
-        pl = np.full_like(total, np.nan)
-        ok = total > 0
-        pl[ok] = -10 * np.log10(total[ok])
+        """Path loss in dB per user (dataset.py:541-566): -10 log10 |sum_p sqrt(p_lin) e^{j phase}|^2, NaN where no power.
+        Computed by the per-user by-product kernel (one warp per user)."""
+        from .byproducts import user_byproducts
+        r = user_byproducts(self, self._data.get("ch_params"), want=("pathloss",))
+        pl = r["pathloss"] if coherent else r["pathloss_noncoherent"]
         self._data["pathloss"] = pl
         return pl
 
     def _compute_num_paths(self) -> np.ndarray:
-        """Valid paths per user after FoV filtering (dataset.py:613-619)."""
-        return (~np.isnan(self["_aoa_az_rot_fov"])).sum(axis=1)
+        """Valid paths per user after FoV filtering (dataset.py:613-619), device reduction over the prologue's FoV mask."""
+        from .byproducts import user_byproducts
+        return user_byproducts(self, self._data.get("ch_params"), want=("num_paths",))["num_paths"]
 
     def _compute_los(self) -> np.ndarray:
-        """1 LoS / 0 NLoS / -1 no path: interaction code of the first in-FoV path (dataset.py:569-611)."""
-        inter = self["inter"]
-        los = np.full(inter.shape[0], -1)
-        fov = self["_fov_mask"]
-        if fov is not None:
-            has = np.any(fov, axis=1)
-            first_col = np.argmax(fov, axis=1)
-            first = np.where(has, inter[np.arange(inter.shape[0]), first_col], -1)
-        else:
-            has = self["num_paths"] > 0
-            first = inter[:, 0]
-        los[has] = 0
-        los[(first == 0) & has] = 1
-        return los
+        """1 LoS / 0 NLoS / -1 no path: interaction code of the first in-FoV path (dataset.py:569-611), on the device."""
+        from .byproducts import user_byproducts
+        return user_byproducts(self, self._data.get("ch_params"), want=("los",))["los"]
 
     def _compute_path_byproducts(self) -> None:
         """Rotated angles, FoV mask/angles and power with antenna gain (dataset.py:310-356, :461-512,

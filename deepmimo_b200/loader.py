@@ -40,10 +40,50 @@ def _pinned(a: np.ndarray) -> np.ndarray:
     return torch.from_numpy(a).pin_memory().numpy()
 
 
+class _DeviceFeed:
+    """Host -> device pipeline of the loader: the H2D copy of matrix k (from one of two pinned staging buffers, on a copy stream)
+    runs while scipy parses matrix k + 1.  `finish()` makes the caller's stream wait for the copies."""
+
+    def __init__(self, device):
+        import torch
+        if not torch.cuda.is_available():
+            raise RuntimeError("load_scenario(device=...) needs a CUDA device")
+        self.torch = torch
+        self.device = torch.device(device)
+        self.stream = torch.cuda.Stream(device=self.device)
+        self.stage = [None, None]
+        self.busy = [None, None]
+        self.k = 0
+        self.bytes = 0
+
+    def put(self, a: np.ndarray):
+        torch = self.torch
+        b = self.k & 1
+        self.k += 1
+        if self.busy[b] is not None:
+            self.busy[b].synchronize()                       # the copy that last read this staging buffer has finished
+        if self.stage[b] is None or self.stage[b].numel() < a.nbytes:
+            self.stage[b] = torch.empty(max(a.nbytes, 1 << 20), dtype=torch.uint8, pin_memory=True)
+        st = self.stage[b][: a.nbytes].view(torch.float32).view(a.shape)
+        st.copy_(torch.from_numpy(a))                        # host memcpy into page-locked memory
+        out = torch.empty(a.shape, dtype=torch.float32, device=self.device)
+        with torch.cuda.stream(self.stream):
+            out.copy_(st, non_blocking=True)
+            self.busy[b] = torch.cuda.Event()
+            self.busy[b].record(self.stream)
+        self.bytes += a.nbytes
+        return out
+
+    def finish(self):
+        self.torch.cuda.current_stream(self.device).wait_stream(self.stream)
+
+
 def load_tx_rx_raydata(folder: str, tx_set_id: int, rx_set_id: int, tx_idx: int, rx_idxs=None, max_paths: int = MAX_PATHS,
-                       matrices: Union[str, Iterable[str]] = "all", pin: bool = False) -> Dict[str, np.ndarray]:
-    """Matrices of one TX-RX pair (core.py:186-258)."""
+                       matrices: Union[str, Iterable[str]] = "all", pin: bool = False, device=None, _feed=None) -> Dict[str, np.ndarray]:
+    """Matrices of one TX-RX pair (core.py:186-258).  `device='cuda'` returns the seven path matrices as float32 CUDA tensors fed
+    through the parse / H2D pipeline (`compute_channels` takes them as they are; positions and interaction data stay on the host)."""
     import scipy.io
+    feed = _feed if _feed is not None else (_DeviceFeed(device) if device is not None else None)
     if matrices == "all":
         wanted = MATRIX_KEYS
     else:
@@ -68,7 +108,12 @@ def load_tx_rx_raydata(folder: str, tx_set_id: int, rx_set_id: int, tx_idx: int,
             a = np.ascontiguousarray(a, dtype=np.float32)
         else:
             a = np.ascontiguousarray(a)
-        out[key] = _pinned(a) if (pin and key in PATH_MATRICES) else a
+        if feed is not None and key in PATH_MATRICES and key != "inter":
+            out[key] = feed.put(a)
+        else:
+            out[key] = _pinned(a) if (pin and key in PATH_MATRICES) else a
+    if feed is not None and _feed is None:
+        feed.finish()
     return out
 
 
@@ -105,8 +150,9 @@ def _resolve_sets(sets, txrx: dict, role: str) -> Dict[int, np.ndarray]:
     raise ValueError("tx_sets / rx_sets must be 'all', a list of set ids or a dict {set id: indices}")
 
 
-def load_scenario(folder: str, max_paths: int = MAX_PATHS, tx_sets="all", rx_sets="all", matrices="all", pin: bool = False):
-    """Load a scenario folder into a Dataset (one TX-RX pair) or a MacroDataset (several), core.py:63-183."""
+def load_scenario(folder: str, max_paths: int = MAX_PATHS, tx_sets="all", rx_sets="all", matrices="all", pin: bool = False, device=None):
+    """Load a scenario folder into a Dataset (one TX-RX pair) or a MacroDataset (several), core.py:63-183.
+    `device='cuda'` (or 'cuda:1', ...) streams the path matrices to that GPU while the following files are parsed."""
     params_path = os.path.join(folder, "params.json")
     if not os.path.exists(params_path):
         raise ValueError(f"Parameters file not found in {folder}")
@@ -118,13 +164,16 @@ def load_scenario(folder: str, max_paths: int = MAX_PATHS, tx_sets="all", rx_set
     tx = _resolve_sets(tx_sets, txrx, "tx")
     rx = _resolve_sets(rx_sets, txrx, "rx")
     datasets: List[Dataset] = []
+    feed = _DeviceFeed(device) if device is not None else None
     for tx_set_id, tx_idxs in tx.items():
         for rx_set_id, rx_idxs in rx.items():
             for tx_idx in tx_idxs:
-                d = load_tx_rx_raydata(folder, tx_set_id, rx_set_id, int(tx_idx), rx_idxs, max_paths, matrices, pin)
+                d = load_tx_rx_raydata(folder, tx_set_id, rx_set_id, int(tx_idx), rx_idxs, max_paths, matrices, pin, _feed=feed)
                 d["txrx"] = {"tx_set_id": tx_set_id, "rx_set_id": rx_set_id, "tx_idx": int(tx_idx)}
                 d["name"] = os.path.basename(os.path.normpath(folder))
                 datasets.append(Dataset(d))
+    if feed is not None:
+        feed.finish()
     if not datasets:
         raise ValueError("no TX-RX pair selected")
     return datasets[0] if len(datasets) == 1 else MacroDataset(datasets)

@@ -140,6 +140,21 @@ int dmk_channels_td(const dmk_desc *desc,
                     uint8_t *fov_mask, uint8_t *valid_mask, int32_t *path_slot,
                     void *cuda_stream);
 
+/* Time-domain channels plus the per-slot delays: the (a, tau) pair of the reference's Sionna adapter
+ * (deepmimo/integrations/sionna_adapter.py:174-200).  `out_c64` [n, M_r, M_t, P] is, per user, exactly the block the adapter
+ * copies into a[i_rx, :, i_tx, :, :, 0];
+ *   tau : NULL or DEVICE float32 [n, P]: tau[u, j] = delay of the j-th valid path of user u, 0 in the empty slots
+ *         (== tau[i_rx, i_tx, :num_paths] = ToA, :196-198).  Everything else as dmk_channels_td. */
+int dmk_channels_td_tau(const dmk_desc *desc,
+                        const float *power_dbw, const float *phase_deg, const float *delay_s,
+                        const float *aoa_az_deg, const float *aoa_el_deg,
+                        const float *aod_az_deg, const float *aod_el_deg,
+                        const double *ue_rot_deg, const float *doppler_hz,
+                        int64_t n_users, int32_t ld,
+                        void *out_c64,
+                        uint8_t *fov_mask, uint8_t *valid_mask, int32_t *path_slot, float *tau,
+                        void *cuda_stream);
+
 /* Beam amplitude map, fused (docs/manual.ipynb cell 105 of the reference):
  *   mean_abs[u, b] = mean over RX elements r and selected subcarriers k of | sum_t beams[b, t] H[u, r, t, k] |
  * == np.abs(F1 @ dataset.channel).mean(axis=1).mean(axis=-1) with F1 = beams (rows e.g. from steering_vec,
@@ -172,6 +187,23 @@ int dmk_path_prologue(const dmk_desc *desc,
                       int64_t n_users, int32_t ld,
                       double *angles_rot, double *power_gain, uint8_t *fov_mask,
                       void *cuda_stream);
+
+/* Per-user by-products of the same prologue (the lazy Dataset keys of the reference):
+ *   num_paths            : NULL or DEVICE int32 [n]: paths left after FoV filtering, counted over all columns (dataset.py:613-619)
+ *   los                  : NULL or DEVICE int32 [n]: 1 LoS / 0 NLoS / -1 no path, from `inter` of the first in-FoV path (dataset.py:569-611)
+ *   pathloss_coherent    : NULL or DEVICE float32 [n]: -10 log10 |sum_p sqrt(p_lin) e^{j phase}|^2, NaN where the sum is 0 (dataset.py:541-566)
+ *   pathloss_noncoherent : NULL or DEVICE float32 [n]: the same with the phases dropped (coherent=False)
+ *   inter                : DEVICE float32 [n, n_cols] (ld) interaction codes (0 = line of sight); required when `los` is requested
+ */
+int dmk_user_byproducts(const dmk_desc *desc,
+                        const float *power_dbw, const float *phase_deg,
+                        const float *aoa_az_deg, const float *aoa_el_deg,
+                        const float *aod_az_deg, const float *aod_el_deg,
+                        const float *inter, const double *ue_rot_deg,
+                        int64_t n_users, int32_t ld,
+                        int32_t *num_paths, int32_t *los,
+                        float *pathloss_coherent, float *pathloss_noncoherent,
+                        void *cuda_stream);
 
 /* Test hook for rounding point R2: the device restatement of NumPy's
  * float32 sin/cos used at geometry.py:301-302.  x, s, c are DEVICE float32 [n]. */

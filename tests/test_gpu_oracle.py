@@ -255,8 +255,12 @@ def test_per_user_byproducts_match_reference_definitions():
     assert np.array_equal(ds.power_linear, p_lin, equal_nan=True)
     tot = np.abs(np.nansum(np.sqrt(p_lin).astype(np.complex64) * np.exp(1j * np.deg2rad(s.data["phase"])), axis=1)) ** 2
     pl = ds.pl
+    assert pl.dtype == np.float32 and ds.num_paths.dtype == np.int64 and ds.los.dtype == np.int64      # the reference's dtypes
     assert np.array_equal(np.isnan(pl), ~(tot > 0))
-    np.testing.assert_allclose(pl[tot > 0], -10 * np.log10(tot[tot > 0]), rtol=1e-6)
+    np.testing.assert_allclose(pl[tot > 0], -10 * np.log10(tot[tot > 0]), rtol=2e-6, atol=2e-5)
+    tot_nc = np.abs(np.nansum(np.sqrt(p_lin).astype(np.complex64), axis=1)) ** 2                       # compute_pathloss(coherent=False)
+    pl_nc = ds.compute_pathloss(coherent=False)
+    np.testing.assert_allclose(pl_nc[tot_nc > 0], -10 * np.log10(tot_nc[tot_nc > 0]), rtol=2e-6, atol=2e-5)
     # no FoV: num_paths counts the valid paths, los looks at the first column
     ds2 = make_dataset(dmb, data)
     ds2.set_channel_params(dmb.ChannelGenParameters(s.params))

@@ -60,3 +60,29 @@ def test_matches_reference_loader(tmp_path):
             continue
         assert np.array_equal(got[k], v, equal_nan=True), k
         assert got[k].shape == v.shape
+
+
+@pytest.mark.gpu
+def test_gpu_scenario_folder_to_channels(tmp_path):
+    """Row f1 as a device feed: scenario folder -> parse / H2D pipeline -> CUDA path matrices -> compute_channels, against the oracle."""
+    import torch
+    from oracle import channel_oracle as orc
+    from util import assert_channels_close, oracle_kwargs_from_params
+    from deepmimo_b200.synth import scenario
+    s = scenario(5, 700)
+    pairs = {(0, 0, 1): dict(s.data), (0, 1, 1): dict(scenario(5, 700, bs_index=1).data)}
+    folder = dmb.save_scenario(str(tmp_path / "city"), pairs)
+    macro = dmb.load_scenario(folder, device="cuda")
+    assert len(macro) == 2
+    p = dmb.ChannelGenParameters(s.params)
+    for ti in range(2):
+        ds = macro[ti]
+        for k in ("power", "phase", "delay", "aoa_az", "aoa_el", "aod_az", "aod_el"):
+            assert isinstance(ds[k], torch.Tensor) and ds[k].is_cuda and ds[k].dtype == torch.float32
+            assert np.array_equal(ds[k].cpu().numpy(), pairs[(0, ti, 1)][k], equal_nan=True)
+        assert isinstance(ds["rx_pos"], np.ndarray) and ds.n_ue == 700
+        H = ds.compute_channels(p, warn=False)
+        o = orc.compute_channels(pairs[(0, ti, 1)], **oracle_kwargs_from_params(s.params))
+        assert_channels_close(H, o["H"], what=f"loaded pair {ti}")
+    host = dmb.load_scenario(folder, pin=True)                      # host route: same numbers
+    assert np.array_equal(host[0].compute_channels(p, warn=False), macro[0].compute_channels(p, warn=False))
