@@ -53,7 +53,7 @@ def path_byproducts(dataset, params=None, *, device=None, seed_numpy_rng: bool =
             out[k + "_fov"] = out[k]
     pg = pw.cpu().numpy()
     iso = spec.patterns == (0, 0)
-    out["_power_linear_ant_gain"] = pg.astype(np.float32) if iso else pg     # float32 stays float32 when isotropic
+    out["_power_linear_ant_gain"] = pg.astype(np.float32) if (iso and not plan.f64) else pg     # float32 stays float32 when isotropic
     return out
 
 

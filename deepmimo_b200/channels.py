@@ -239,9 +239,17 @@ class ChannelPlan:
         self.n_users, self.n_cols = int(ref.shape[0]), int(ref.shape[1])
         if self.n_cols > MAX_COLS:
             raise ValueError(f"{self.n_cols} path columns > {MAX_COLS} supported per launch")
+        # float32 is the reference's storage type (deepmimo/consts.py:65); seven float64 matrices select the all-float64
+        # prologue (NumPy's dtype flow for float64 inputs); a mixture follows neither flow
+        kinds = {str(getattr(arrays[k], "dtype", None)).replace("torch.", "") for k in PATH_KEYS}
+        self.f64 = kinds == {"float64"}
+        if not self.f64 and kinds != {"float32"}:
+            raise TypeError(f"the seven path matrices must all be float32 (the reference's storage type, deepmimo/consts.py:65) "
+                            f"or all float64; got {sorted(kinds)}")
+        in_dtype = torch.float64 if self.f64 else torch.float32
         self.t = {}
         for k in PATH_KEYS:
-            self.t[k] = self._to_dev(arrays[k], torch.float32, (self.n_users, self.n_cols), k)
+            self.t[k] = self._to_dev(arrays[k], in_dtype, (self.n_users, self.n_cols), k)
         self.doppler = None if doppler is None else self._to_dev(doppler, torch.float32, (self.n_users, self.n_cols), "doppler")
         self.ue_rot = None
         if spec.ue_rot_users is not None:
@@ -255,11 +263,7 @@ class ChannelPlan:
         if isinstance(a, torch.Tensor):
             t = a
         else:
-            a = np.asarray(a)
-            if dtype == torch.float32 and a.dtype != np.float32:
-                raise TypeError(f"'{name}' is {a.dtype}; this path takes the reference's storage type float32 "
-                                "(deepmimo/consts.py:65) -- float64 inputs follow a different dtype flow in NumPy")
-            t = torch.from_numpy(np.ascontiguousarray(a))
+            t = torch.from_numpy(np.ascontiguousarray(np.asarray(a)))
         if tuple(t.shape) != tuple(shape):
             raise ValueError(f"'{name}' has shape {tuple(t.shape)}, expected {tuple(shape)}")
         if t.dtype != dtype:
@@ -286,6 +290,7 @@ class ChannelPlan:
         d.subc_start, d.subc_step = s.subc_start, s.subc_step
         d.bandwidth = s.bandwidth
         d.rx_filter = s.rx_filter
+        d.flags = _lib.FLAG_F64_INPUTS if self.f64 else 0
         d.n_times = 0 if s.times is None else len(s.times)
         d.times = None if self.times is None else self.times.data_ptr()
         return d
@@ -329,7 +334,7 @@ class ChannelPlan:
         ptr = lambda t, row=start: None if t is None else t.data_ptr() + row * t.stride(0) * t.element_size()
         m = masks or {}
         mp = lambda k: None if m.get(k) is None else m[k].data_ptr()
-        self.desc.flags = _lib.FLAG_INDEPENDENT_LAUNCH if independent else 0
+        self.desc.flags = (_lib.FLAG_INDEPENDENT_LAUNCH if independent else 0) | (_lib.FLAG_F64_INPUTS if self.f64 else 0)
         self.desc.kernel_hint = _lib.kernel_hint_from_env("DMK_FD_KERNEL")
         self.desc.ws_helpers = int(os.environ.get("DMK_WS_HELPERS", "0") or 0)
         common = [ctypes.byref(self.desc)] + [ptr(self.t[k]) for k in PATH_KEYS] + \
@@ -356,7 +361,7 @@ class ChannelPlan:
         st = torch.cuda.current_stream(self.device) if stream is None else stream
         m = masks or {}
         mp = lambda k: None if m.get(k) is None else m[k].data_ptr()
-        self.desc.flags = 0
+        self.desc.flags = _lib.FLAG_F64_INPUTS if self.f64 else 0
         self.desc.kernel_hint = _lib.kernel_hint_from_env("DMK_BF_KERNEL")
         with torch.cuda.device(self.device):
             rc = self.lib.dmk_beam_amplitude_fd(

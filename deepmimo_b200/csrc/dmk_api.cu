@@ -97,6 +97,8 @@ int build_desc(const dmk_desc* h, bool freq_domain, dmk::DevDesc& d)
         if (bmax > 16) bmax = 16;
         d.lpf_batch = (int)bmax;
     }
+    d.in_f64 = (h->flags & DMK_FLAG_F64_INPUTS) ? 1 : 0;
+    d.ts_f64 = 1.0 / h->bandwidth;                          // channel.py:223
     d.ts_f32 = (float)(1.0 / h->bandwidth);                 // channel.py:223 then float32 (NEP 50 weak scalar)
     d.n_f32 = (float)d.N;
     d.inv_n = 1.0 / (double)d.N;

@@ -32,6 +32,8 @@ struct DevDesc {
     double sx[2], cx[2], sy[2], cy[2], rz[2];
     // FoV thresholds exactly as geometry.py:184-190 computes them in float64
     double h_lo[2], h_hi[2], v_lo[2], v_hi[2];
+    int    in_f64;                // 1: the seven path matrices are float64 (DMK_FLAG_F64_INPUTS): all-float64 prologue
+    double ts_f64;                // 1/bandwidth            (channel.py:223)
     float  ts_f32;                // float32(1/bandwidth)   (channel.py:183, R11)
     float  n_f32;                 // float32(N)
     double inv_n;                 // 1/N

@@ -240,11 +240,14 @@ fd_small2_kernel(const __grid_constant__ DevDesc d, const __grid_constant__ Smal
         // ---- 1. window: which columns of the next users need their chain.  All loads first (independent, one latency), then the
         //         ballots; the per-user bit masks go to shared memory so that everything after this is a short rolled loop.
         const int n_in = (int)min((long long)cfg.window, u_end - cur);
-        const float* prow = d.power + cur * (long long)d.ld + lane;
-        float pw[kS2Window];
+        const long long prow = cur * (long long)d.ld + lane;
+        float pw[kS2Window];                                                   // only the NaN-ness of the power is used here
         #pragma unroll
-        for (int ul = 0; ul < kS2Window; ++ul)
-            pw[ul] = (ul < n_in && lane < P0) ? __ldg(prow + ul * d.ld) : __int_as_float(0x7fc00000);
+        for (int ul = 0; ul < kS2Window; ++ul) {
+            pw[ul] = __int_as_float(0x7fc00000);
+            if (ul < n_in && lane < P0)
+                pw[ul] = d.in_f64 ? (float)__ldg(reinterpret_cast<const double*>(d.power) + prow + ul * d.ld) : __ldg(d.power + prow + ul * d.ld);
+        }
         #pragma unroll
         for (int ul = 0; ul < kS2Window; ++ul) {
             const bool in = ul < n_in && lane < P0;
@@ -284,7 +287,7 @@ fd_small2_kernel(const __grid_constant__ DevDesc d, const __grid_constant__ Smal
             if (u < u_end) {
                 const float* base = (arr == 0) ? d.power : (arr == 1) ? d.phase : (arr == 2) ? d.delay : (arr == 3) ? d.az[0] : (arr == 4) ? d.el[0]
                                   : (arr == 5) ? d.az[1] : d.el[1];
-                asm volatile("prefetch.global.L2 [%0];" :: "l"(base + u * (long long)d.ld));
+                asm volatile("prefetch.global.L2 [%0];" :: "l"(reinterpret_cast<const char*>(base) + u * (long long)d.ld * (d.in_f64 ? 8 : 4)));
             }
         }
         // ---- 3. chain rounds: lane = dense pair

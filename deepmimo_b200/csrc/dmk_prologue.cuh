@@ -29,17 +29,10 @@ struct PathState {
 // ~half of the prologue's dependent latency) are computed only when something consumes them -- the FoV compares
 // (geometry.py:180-193), the dipole pattern (ant_patterns.py:57-69) or the by-product kernel.
 template <bool kNeedAngles>
-__device__ __forceinline__ void rotate_side(float el_deg, float az_deg,
-                                            double sx, double cx, double sy, double cy, double rz,
-                                            double& th, double& ph, double& sin_th_sin_ph, double& cos_th, bool steer = true)
+__device__ __forceinline__ void rotate_core(double st, double ct, double dphi,
+                                            double sx, double cx, double sy, double cy,
+                                            double& th, double& ph, double& sin_th_sin_ph, double& cos_th, bool steer)
 {
-    const float d2r = 0x1.1df46ap-6f;                       // float32(pi/180): np.deg2rad on float32 (R1)
-    float th32 = __fmul_rn(el_deg, d2r);                    // :284
-    float ph32 = __fmul_rn(az_deg, d2r);                    // :285
-    float st32, ct32;
-    np_sincosf(th32, st32, ct32);                           // :301-302 float32 SIMD sin/cos (R2)
-    double st = (double)st32, ct = (double)ct32;
-    double dphi = __dsub_rn((double)ph32, rz);              // :294 float32 - float64 -> float64 (R3)
     double sd, cd;
     dsincos_bf(dphi, sd, cd);
     // :305-306  arccos(cy*cx*ct + st*(sy*cx*cd - sx*sd)), same association, no contraction
@@ -67,6 +60,34 @@ __device__ __forceinline__ void rotate_side(float el_deg, float az_deg,
     sin_th_sin_ph = sin_th * sin_ph;
 }
 
+// float32 angles (the reference's storage type): deg2rad and sin/cos of theta in float32 exactly as NumPy does them (R1, R2).
+template <bool kNeedAngles>
+__device__ __forceinline__ void rotate_side(float el_deg, float az_deg,
+                                            double sx, double cx, double sy, double cy, double rz,
+                                            double& th, double& ph, double& sin_th_sin_ph, double& cos_th, bool steer = true)
+{
+    const float d2r = 0x1.1df46ap-6f;                       // float32(pi/180): np.deg2rad on float32 (R1)
+    float th32 = __fmul_rn(el_deg, d2r);                    // :284
+    float ph32 = __fmul_rn(az_deg, d2r);                    // :285
+    float st32, ct32;
+    np_sincosf(th32, st32, ct32);                           // :301-302 float32 SIMD sin/cos (R2)
+    const double dphi = __dsub_rn((double)ph32, rz);        // :294 float32 - float64 -> float64 (R3)
+    rotate_core<kNeedAngles>((double)st32, (double)ct32, dphi, sx, cx, sy, cy, th, ph, sin_th_sin_ph, cos_th, steer);
+}
+
+// float64 angles (last paragraph): every step of geometry.py:284-310 is float64 in NumPy.
+template <bool kNeedAngles>
+__device__ __forceinline__ void rotate_side_f64(double el_deg, double az_deg,
+                                                double sx, double cx, double sy, double cy, double rz,
+                                                double& th, double& ph, double& sin_th_sin_ph, double& cos_th, bool steer = true)
+{
+    const double k = kPi / 180.0;                           // np.deg2rad on float64: x * (pi/180)
+    double st, ct;
+    dsincos_bf(__dmul_rn(el_deg, k), st, ct);               // :301-302
+    const double dphi = __dsub_rn(__dmul_rn(az_deg, k), rz);
+    rotate_core<kNeedAngles>(st, ct, dphi, sx, cx, sy, cy, th, ph, sin_th_sin_ph, cos_th, steer);
+}
+
 // geometry.py:180-193 on one side.  theta in [0, pi] so mod(theta, 2pi) == theta; phi in (-pi, pi].
 __device__ __forceinline__ bool in_fov(const DevDesc& d, int side, double th, double ph)
 {
@@ -91,7 +112,7 @@ __device__ __forceinline__ double dipole_gain(double th)
 // channel kernels give each chain its own warp (lanes = path columns) so the CTA's critical path is one chain.
 // ---------------------------------------------------------------------------------------------------------
 struct SideOut { double th, ph, ss, cc, gain; };           // rotated angles, sin(th)sin(ph), cos(th), element power gain
-struct GainOut { float p_lin, ec, es; double wcyc, fd; unsigned char valid, over; };
+struct GainOut { float p_lin, ec, es; double p_lin64, ec64, es64; double wcyc, fd; unsigned char valid, over; };   // *64: float64 inputs
 
 template <bool kNeedAngles>
 __device__ __forceinline__ void prologue_side(const DevDesc& d, long long user, int p, int side, SideOut& o, bool steer = true)
@@ -105,7 +126,11 @@ __device__ __forceinline__ void prologue_side(const DevDesc& d, long long user, 
         dsincos_bf(__dmul_rn(r[1], k), sy, cy);
         rz = __dmul_rn(r[2], k);
     }
-    rotate_side<kNeedAngles>(d.el[side][off], d.az[side][off], sx, cx, sy, cy, rz, o.th, o.ph, o.ss, o.cc, steer);
+    if (d.in_f64)
+        rotate_side_f64<kNeedAngles>(reinterpret_cast<const double*>(d.el[side])[off], reinterpret_cast<const double*>(d.az[side])[off],
+                                     sx, cx, sy, cy, rz, o.th, o.ph, o.ss, o.cc, steer);
+    else
+        rotate_side<kNeedAngles>(d.el[side][off], d.az[side][off], sx, cx, sy, cy, rz, o.th, o.ph, o.ss, o.cc, steer);
     o.gain = 1.0;
 }
 
@@ -113,6 +138,24 @@ template <bool kFreqDomain>
 __device__ __forceinline__ void prologue_gain(const DevDesc& d, long long user, int p, GainOut& g)
 {
     const long long off = user * (long long)d.ld + p;
+    g.fd = d.doppler ? (double)d.doppler[off] : 0.0;
+    if (d.in_f64) {
+        // float64 path matrices: the whole gain chain is float64 in NumPy (generator_utils.py:35, channel.py:183-192)
+        const double pw_db = reinterpret_cast<const double*>(d.power)[off];
+        g.valid = (p < d.P) && !(pw_db != pw_db);
+        g.p_lin64 = exp10(__ddiv_rn(pw_db, 10.0));
+        g.p_lin = (float)g.p_lin64;
+        sincos(__dmul_rn(reinterpret_cast<const double*>(d.phase)[off], kPi / 180.0), &g.es64, &g.ec64);
+        g.es = (float)g.es64; g.ec = (float)g.ec64;
+        g.over = 0; g.wcyc = 0.0;
+        if (kFreqDomain) {
+            double dn = __ddiv_rn(reinterpret_cast<const double*>(d.delay)[off], d.ts_f64);     // channel.py:183
+            g.over = dn >= (double)d.N;                                                          // :187
+            if (g.over) dn = (double)d.N;                                                        // :189
+            g.wcyc = dn * d.inv_n;
+        }
+        return;
+    }
     const float pw_db = d.power[off];
     g.valid = (p < d.P) && !(pw_db != pw_db);               // channel.py:260, dataset.py:258-261
     // generator_utils.py:35: float32 divide by 10, float32 pow.  The reference's value is itself a float32 libm/SVML result
@@ -129,7 +172,7 @@ __device__ __forceinline__ void prologue_gain(const DevDesc& d, long long user, 
         if (g.over) dn = d.n_f32;                           // :189
         g.wcyc = (double)dn * d.inv_n;
     }
-    g.fd = d.doppler ? (double)d.doppler[off] : 0.0;
+    g.p_lin64 = (double)g.p_lin; g.ec64 = (double)g.ec; g.es64 = (double)g.es;
 }
 
 template <bool kFreqDomain>
@@ -149,9 +192,9 @@ __device__ __forceinline__ void prologue_combine(const DevDesc& d, const SideOut
     o.u[0] = d.sp[0] * s0.ss; o.v[0] = d.sp[0] * s0.cc;
     o.u[1] = d.sp[1] * s1.ss; o.v[1] = d.sp[1] * s1.cc;
     // ---- power with element patterns (ant_patterns.py:167-168): float64 as soon as one side is a dipole
-    const bool f64_power = (d.pat[0] != DMK_PATTERN_ISOTROPIC) || (d.pat[1] != DMK_PATTERN_ISOTROPIC);
-    double pw64 = (double)g.p_lin;
-    if (f64_power) {
+    const bool f64_power = d.in_f64 || (d.pat[0] != DMK_PATTERN_ISOTROPIC) || (d.pat[1] != DMK_PATTERN_ISOTROPIC);
+    double pw64 = g.p_lin64;
+    if (d.pat[0] != DMK_PATTERN_ISOTROPIC || d.pat[1] != DMK_PATTERN_ISOTROPIC) {
         const double nan64 = __longlong_as_double(0x7ff8000000000000LL);
         const double gt = (d.pat[0] == DMK_PATTERN_HALFWAVE_DIPOLE) ? dipole_gain(fov ? s0.th : nan64) : 1.0;
         const double gr = (d.pat[1] == DMK_PATTERN_HALFWAVE_DIPOLE) ? dipole_gain(fov ? s1.th : nan64) : 1.0;
@@ -162,7 +205,7 @@ __device__ __forceinline__ void prologue_combine(const DevDesc& d, const SideOut
     if (kFreqDomain) {
         if (f64_power) {
             const double amp = g.over ? 0.0 : sqrt(__ddiv_rn(pw64, (double)d.N));   // channel.py:188,:192 (float64 branch)
-            o.c = make_float2((float)(amp * (double)g.ec), (float)(amp * (double)g.es));
+            o.c = make_float2((float)(amp * g.ec64), (float)(amp * g.es64));
         } else {
             const float amp = g.over ? 0.0f : __fsqrt_rn(__fdiv_rn(g.p_lin, d.n_f32));  // :188, :192 (R9)
             o.c = make_float2(__fmul_rn(amp, g.ec), __fmul_rn(amp, g.es));
@@ -170,7 +213,7 @@ __device__ __forceinline__ void prologue_combine(const DevDesc& d, const SideOut
     } else {
         if (f64_power) {
             const double amp = sqrt(pw64);                  // channel.py:286
-            o.c = make_float2((float)(amp * (double)g.ec), (float)(amp * (double)g.es));
+            o.c = make_float2((float)(amp * g.ec64), (float)(amp * g.es64));
         } else {
             const float amp = __fsqrt_rn(g.p_lin);
             o.c = make_float2(__fmul_rn(amp, g.ec), __fmul_rn(amp, g.es));
@@ -195,7 +238,7 @@ __device__ __forceinline__ void prefetch_user_rows_shifted(const DevDesc& d, lon
     if (t < 0 || t >= 7 || ahead >= d.n_users) return;
     const float* base = (t == 0) ? d.power : (t == 1) ? d.phase : (t == 2) ? d.delay : (t == 3) ? d.az[0] : (t == 4) ? d.el[0]
                       : (t == 5) ? d.az[1] : d.el[1];
-    asm volatile("prefetch.global.L2 [%0];" :: "l"(base + ahead * (long long)d.ld));
+    asm volatile("prefetch.global.L2 [%0];" :: "l"(reinterpret_cast<const char*>(base) + ahead * (long long)d.ld * (d.in_f64 ? 8 : 4)));
 }
 
 // Cooperative phase 1: warps 0, 1, 2 of the CTA run the three chains for path column `lane` of `user`.

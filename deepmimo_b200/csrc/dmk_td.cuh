@@ -50,7 +50,10 @@ __device__ __forceinline__ void td_cta_prologue(const DevDesc& d, long long user
         if (d.tau_out) {
             // slot j <- ToA of the j-th valid column (sionna_adapter.py:196-198: tau[..., :num_paths] = ToA), zeros behind
             float* tau_u = d.tau_out + user * (long long)d.P;
-            if (active && st.valid) tau_u[j] = d.delay[user * (long long)d.ld + lane];
+            if (active && st.valid) {
+                const long long o = user * (long long)d.ld + lane;
+                tau_u[j] = d.in_f64 ? (float)reinterpret_cast<const double*>(d.delay)[o] : d.delay[o];      // tau is np.single (:178)
+            }
             const int nv = __popc(ballot);
             if (lane >= nv && lane < d.P) tau_u[lane] = 0.f;
         }
@@ -193,7 +196,15 @@ user_byproducts_kernel(const __grid_constant__ DevDesc d, const float* __restric
     }
     if (pl_coh || pl_noncoh) {
         double re = 0.0, im = 0.0, amp_sum = 0.0;
-        if (active) {
+        if (active && d.in_f64) {
+            // float64 matrices: sqrt(p_lin).astype(complex64) * exp(1j * deg2rad(phase)) with the phasor in complex128
+            const float amp = (float)sqrt(exp10(reinterpret_cast<const double*>(d.power)[row + lane] / 10.0));
+            double sn, cs;
+            sincos(reinterpret_cast<const double*>(d.phase)[row + lane] * (kPi / 180.0), &sn, &cs);
+            const double gr = (double)amp * cs, gi = (double)amp * sn;
+            if (!(amp != amp)) amp_sum = (double)amp;
+            if (!(gr != gr) && !(gi != gi)) { re = gr; im = gi; }
+        } else if (active) {
             const float pw_db = d.power[row + lane];
             const float amp = __fsqrt_rn(exp10f(__fdiv_rn(pw_db, 10.0f)));                 // generator_utils.py:35, sqrt in float32
             float sn, cs;

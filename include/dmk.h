@@ -103,6 +103,10 @@ typedef enum dmk_kernel_hint {
  * last unflagged launch's predecessors: with a ring of R output buffers, at most R - 1 consecutive launches may
  * carry the flag before one launch goes without it (deepmimo_b200.iter_channels does exactly that). */
 #define DMK_FLAG_INDEPENDENT_LAUNCH 1
+/* DMK_FLAG_F64_INPUTS (ABI 3): the seven path-matrix arguments of every entry point address float64 arrays (passed through the
+ * `const float *` parameters; `ld` counts float64 elements).  The prologue then follows NumPy's all-float64 flow for float64
+ * inputs: deg2rad, sin/cos, 10**(p/10), toa/Ts and the path gain in float64.  `doppler_hz` stays float32. */
+#define DMK_FLAG_F64_INPUTS 2
 
 /* Frequency-domain channels (freq_domain = 1):
  *   out[u, r, t, k (, it)] = sum_p c_p a_rx[r,p] a_tx[t,p] exp(-j 2 pi k delay_n[p] / N) (* exp(+j 2 pi f_D[p] t_it))

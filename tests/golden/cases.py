@@ -38,8 +38,8 @@ def case_list():
 
     def add(name, n, seed, n_sc, bw, sel, bs_shape=(8, 1), ue_shape=(1, 1), bs_rot=(0, 0, 0), ue_rot=(0, 0, 0),
             bs_pat="isotropic", ue_pat="isotropic", bs_fov=None, ue_fov=None, num_paths=25, fd=1,
-            bs_sp=0.5, ue_sp=0.5, holes=False, n_cols=25, zero_frac=0.10, lpf=0):
-        cases.append(dict(name=name, n=n, seed=seed, n_sc=n_sc, bw=bw, sel=np.asarray(sel), bs_shape=A(bs_shape),
+            bs_sp=0.5, ue_sp=0.5, holes=False, n_cols=25, zero_frac=0.10, lpf=0, f64=False):
+        cases.append(dict(name=name, n=n, seed=seed, n_sc=n_sc, bw=bw, sel=np.asarray(sel), bs_shape=A(bs_shape), f64=f64,
                           ue_shape=A(ue_shape), bs_rot=np.asarray(bs_rot), ue_rot=np.asarray(ue_rot), bs_pat=bs_pat,
                           ue_pat=ue_pat, bs_fov=None if bs_fov is None else A(bs_fov),
                           ue_fov=None if ue_fov is None else A(ue_fov), num_paths=num_paths, fd=fd,
@@ -77,10 +77,27 @@ def case_list():
     add("lpf_n600_sel", 24, 27, 600, 30e6, A([0, 1, 7, 64, 299, 598, 599]), bs_shape=(6, 1), ue_shape=(1, 2), lpf=1, num_paths=10)
     add("lpf_dipole_fov", 32, 28, 128, 10e6, np.arange(0, 128, 3), bs_shape=(8, 1), bs_pat="halfwave-dipole",
         ue_pat="halfwave-dipole", bs_fov=(140, 120), ue_fov=(180, 120), holes=True, lpf=1)
+    # float64 path matrices (last paragraph): NumPy runs every step in float64; the values are NOT
+    # float32-representable, so a float32 flow would miss the reference by ~1e-3 (delay x frequency reaches thousands of cycles)
+    add("f64_fd_rot", 48, 29, 4096, 400e6, np.r_[np.arange(0, 4096, 293), 4095], bs_shape=(16, 4), ue_shape=(2, 1), bs_rot=(30, 40, 30),
+        ue_rot=per_user(48, 45), f64=True)
+    add("f64_small_dipole_fov", 64, 30, 64, 10e6, np.arange(64), bs_shape=(8, 1), bs_pat="halfwave-dipole", ue_pat="halfwave-dipole",
+        bs_fov=(140, 120), ue_fov=(180, 120), holes=True, f64=True)
+    add("f64_td", 32, 31, 512, 10e6, np.arange(1), bs_shape=(4, 2), ue_shape=(2, 2), fd=0, num_paths=12, bs_rot=(5, -10, 100), f64=True)
+    add("f64_lpf", 16, 32, 128, 10e6, np.arange(0, 128, 5), bs_shape=(4, 1), lpf=1, f64=True)
     return cases
 
 
 def case_data(c: dict) -> dict:
+    d = _case_data32(c)
+    if c.get("f64"):
+        rng = np.random.default_rng(c["seed"] + 5000)
+        for k in ("power", "phase", "delay", "aoa_az", "aoa_el", "aod_az", "aod_el"):
+            d[k] = d[k].astype(np.float64) * (1.0 + 1e-6 * rng.standard_normal(d[k].shape))      # NaN padding stays NaN
+    return d
+
+
+def _case_data32(c: dict) -> dict:
     d = make_paths(c["n"], c["seed"], n_sc=c["n_sc"], bandwidth=c["bw"], n_cols=c["n_cols"], zero_frac=c["zero_frac"],
                    clip_frac=0.02)
     if c["holes"]:
