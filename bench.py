@@ -525,8 +525,9 @@ def gpu_main(args):
         names = ["cfg5"] if world > 1 else ["cfg1", "cfg3", "cfg4", "cfg5", "cfg2_dense", "cfg5_dense", "cfg3_nofov"]
         for w in [w for w in names if w != args.workload]:
             try:
-                r = run_workload(w, None, 5, 3, rank, world, dist, flush, want_clocks=False)
+                r = run_workload(w, None, 5, 3, rank, world, dist, flush, want_clocks=True)
                 rec = summarise(r, 5)
+                rec["clocks"] = r["clocks"]
                 if rank == 0:
                     extra[w] = rec
                 del r

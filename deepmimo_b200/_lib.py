@@ -41,6 +41,7 @@ class DmkDesc(ctypes.Structure):
         ("flags", ctypes.c_int32),
         ("kernel_hint", ctypes.c_int32),
         ("ws_helpers", ctypes.c_int32),
+        ("ws_split", ctypes.c_int32),
     ]
 
 

@@ -337,6 +337,7 @@ class ChannelPlan:
         self.desc.flags = (_lib.FLAG_INDEPENDENT_LAUNCH if independent else 0) | (_lib.FLAG_F64_INPUTS if self.f64 else 0)
         self.desc.kernel_hint = _lib.kernel_hint_from_env("DMK_FD_KERNEL")
         self.desc.ws_helpers = int(os.environ.get("DMK_WS_HELPERS", "0") or 0)
+        self.desc.ws_split = int(os.environ.get("DMK_WS_SPLIT", "0") or 0)
         common = [ctypes.byref(self.desc)] + [ptr(self.t[k]) for k in PATH_KEYS] + \
                  [ptr(self.ue_rot), ptr(self.doppler), n, self.n_cols, out.data_ptr()]
         with torch.cuda.device(self.device):

@@ -328,6 +328,7 @@ int dmk_channels_fd(const dmk_desc* desc, const float* power_dbw, const float* p
         else if (smem1 <= (size_t)kSmemWs4) { n_helpers = 1; one_cta = true; }    // wide panels (e.g. 64 x 4): still persistent
         // Few users: split each user's stages over several CTAs so the grid covers >= 4 waves.
         long long wsplit = (want + n_users - 1) / n_users;
+        if (desc->ws_split > 0) wsplit = desc->ws_split;
         if (wsplit > w.n_stages) wsplit = w.n_stages;
         if (wsplit < 1) wsplit = 1;
         const long long items = n_users * wsplit;

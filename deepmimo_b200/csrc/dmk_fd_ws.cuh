@@ -196,6 +196,24 @@ __device__ __noinline__ void ws_helper_prepare(const DevDesc& d, const WsCfg& cf
     for (int e = lane; e < S; e += 32)   wS[np * cfg.sS + e] = zero;
 }
 
+// Drain 32 accumulator columns = 32 consecutive chunks of the output: register i holds, across the lanes of the warp, floats
+// q*32 .. q*32+31 of chunk (first + i).  Chunks are 512 bytes apart, so every store is base + i * 512: an immediate offset, no
+// address arithmetic between the stores (the row-pitch version of round 1 spent two instructions per store on it).
+__device__ __forceinline__ void ws_store_chunks(uint32_t taddr, float* out, int first, int rows, float scale)
+{
+    uint32_t v[32];
+    tmem_ld<32>(taddr, v);
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    if (first + 32 <= rows) {
+        #pragma unroll
+        for (int i = 0; i < 32; ++i) __stcs(out + i * kTcN, __uint_as_float(v[i]) * scale);    // * scale: undo the per-user operand scale
+    } else {
+        #pragma unroll
+        for (int i = 0; i < 32; ++i)
+            if (first + i < rows) __stcs(out + i * kTcN, __uint_as_float(v[i]) * scale);
+    }
+}
+
 // Consumers (drain, builders, issuer) walk the users in the order it = 0, 1, 2, ...: user `it` is prepared by helper it % H into
 // buffer it % (2H) (every helper owns two buffers).  A helper that draws a ticket >= n_items publishes it as a sentinel and stops;
 // its slots are skipped from then on, and the walk ends when every helper of the CTA has stopped.
@@ -410,6 +428,10 @@ fd_ws_kernel(const __grid_constant__ DevDesc d, const __grid_constant__ WsCfg cf
     } else {
         // ------------------------------------------------------------------------------------------ drain warps 0-3
         const int q = warp;                                   // TMEM lane quarter = 32 floats (128 bytes) of every chunk
+#ifdef DMK_TC_TRACE
+        unsigned long long tr_t0 = 0, tr_first = 0, tr_users = 0;
+        if (tid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tr_t0));
+#endif
         if (pdl_wait) asm volatile("griddepcontrol.wait;" ::: "memory");     // everything before this launch has completed and is visible
         unsigned g = 0;
         unsigned it = 0, done = 0;
@@ -422,6 +444,9 @@ fd_ws_kernel(const __grid_constant__ DevDesc d, const __grid_constant__ WsCfg cf
             const int np = ub.sh.np;
             const float scale = ub.scale;
             float* out_u = reinterpret_cast<float*>(d.out) + user * (long long)n_chunks * kTcN;
+#ifdef DMK_TC_TRACE
+            if (tid == 0) { if (!tr_first) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tr_first)); ++tr_users; }
+#endif
             if (q == 0 && ks == 0 && lane < d.P0) {
                 const long long o = user * (long long)d.P0 + lane;
                 if (d.fov_mask)   d.fov_mask[o]   = ub.m_fov[lane];
@@ -445,13 +470,22 @@ fd_ws_kernel(const __grid_constant__ DevDesc d, const __grid_constant__ WsCfg cf
                     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + ab * (uint32_t)kTcN;
                     float* o = out_u + (long long)stg * kTcN * kTcN + q * 32 + lane;        // chunk r of the stage: + r * 128 floats
                     for (int r = 0; r < rows; r += 32)
-                        tc_store_rows<32>(taddr + r, o + r * kTcN, kTcN, r, rows, scale);
+                        ws_store_chunks(taddr + r, o + r * kTcN, r, rows, scale);
                     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                     mbar_arrive(&bars.acc_empty[ab]);
                 }
             }
             mbar_arrive(&bars.ub_empty[cur]);
         }
+#ifdef DMK_TC_TRACE
+        if (tid == 0 && blockIdx.x < 296) {
+            unsigned long long t_end;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_end));
+            const int slot = (int)((ticket - g_tc_ticket) % 3) * 1184 + blockIdx.x * 4;       // three consecutive launches keep their records
+            g_tc_trace[slot + 0] = (long long)tr_t0; g_tc_trace[slot + 1] = (long long)tr_first;
+            g_tc_trace[slot + 2] = (long long)t_end; g_tc_trace[slot + 3] = (long long)tr_users;
+        }
+#endif
     }
 
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");

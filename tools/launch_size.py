@@ -1,5 +1,5 @@
-"""Where chained launches lose against one big launch on the city-scale shape (fd_ws_kernel, 512 KB per user):
-    python tools/launch_size.py"""
+"""Where chained launches lose against one big launch on the city-scale shape (fd_ws_kernel, 512 KB per user), and what the work-item
+granularity (DMK_WS_SPLIT: items per user) does to the tail:  python tools/launch_size.py"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -27,17 +27,14 @@ def report(name, ms, users=N):
     print(f"{name:70s} {ms:.3f} ms  {users * 512 * 1024 / ms * 1e-6:.0f} GB/s", flush=True)
 
 
-report("one launch, 65536 users, one buffer", timed(lambda: plan.run(big, 0, N)))
-for chunk in (16384, 4096):
-    for mode in ("plain", "all"):
-        def step():
+for split in ("0", "2", "4"):
+    os.environ["DMK_WS_SPLIT"] = split
+    print(f"--- DMK_WS_SPLIT={split}")
+    report("one launch, 65536 users, one buffer", timed(lambda: plan.run(big, 0, N)))
+    for chunk in (16384, 8192):
+        def step_ring():
             for i, a in enumerate(range(0, N, chunk)):
-                plan.run(big[a:a + chunk], a, a + chunk, independent=(mode == "all" and i > 0))
-        report(f"{N // chunk} launches of {chunk} into slices of the one buffer, {mode}", timed(step))
-    def step_ring():
-        for i, a in enumerate(range(0, N, chunk)):
-            plan.run(ring[i % 3][:chunk], a, a + chunk, independent=chunk_is_independent(i, 3))
-    report(f"{N // chunk} launches of {chunk} into a ring of 3", timed(step_ring))
-for n1 in (16384, 8192, 4096, 2048):
-    report(f"one launch of {n1} users alone", timed(lambda: plan.run(big[:n1], 0, n1)), n1)
-    report(f"one launch of {n1} users alone, users {N - n1}..", timed(lambda: plan.run(big[:n1], N - n1, N)), n1)
+                plan.run(ring[i % 3][:chunk], a, a + chunk, independent=chunk_is_independent(i, 3))
+        report(f"{N // chunk} launches of {chunk} into a ring of 3", timed(step_ring))
+    for n1 in (8192, 2048):
+        report(f"one launch of {n1} users alone", timed(lambda: plan.run(big[:n1], 0, n1)), n1)
