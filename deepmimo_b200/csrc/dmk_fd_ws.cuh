@@ -28,9 +28,11 @@ constexpr int kWsIssuer   = 8;
 constexpr int kWsHelper0  = 9;     // warps 9 .. 9 + H - 1
 constexpr int kWsBuilders = 128;
 constexpr int kWsMaxHelpers = 4;
+// user buffers: two per helper warp (it prepares user i + H while user i is consumed)
+__host__ __device__ constexpr int ws_bufs(int H) { return 2 * H; }
 
 struct WsBars {
-    uint64_t ub_full[2 * kWsMaxHelpers], ub_empty[2 * kWsMaxHelpers];   // helper -> everyone (1 arrival) ; everyone -> helper (288 arrivals)
+    uint64_t ub_full[2 * 4], ub_empty[2 * 4];   // helper -> everyone (1 arrival) ; everyone -> helper (288 arrivals)
     uint64_t op_full;                   // builders -> issuer (128 arrivals): operand tiles of the next stage are in smem
     uint64_t mma_done[2];               // tcgen05.commit: accumulator g & 1 complete, operand tiles free again
     uint64_t acc_empty[2];              // drain warps -> issuer (128 arrivals): accumulator g & 1 has been read out
@@ -111,6 +113,13 @@ struct WsCfg {
 
 // Helper warp: ticket -> prologue -> per-user tables of one buffer.  lanes = path columns, then lanes = table entries.
 // Row np of every table is zero-filled: the operand builders read it (index min(p, np)) for the padding slots.
+// kSfu: table phasors on the SFU (phasor_cycles_sfu, <= 3.6e-7 absolute per unit phasor -- the class of the FP16 hi/lo operand
+// split the entries go through, 2^-22) instead of the float32 polynomial.  Used by the four-helper instantiation only, i.e. for
+// per-user outputs below ~400 KB, where this warp -- the per-user serial path -- bounds the kernel.
+template <bool kSfu>
+__device__ __forceinline__ float2 ws_phasor(double cyc) { return kSfu ? phasor_cycles_sfu(cyc) : phasor_cycles(cyc); }
+
+template <bool kSfu>
 __device__ __noinline__ void ws_helper_prepare(const DevDesc& d, const WsCfg& cfg, int ksplit, unsigned int n_items, unsigned int n_draw_last,
                                                unsigned int* ticket, TcUserBuf& ub, unsigned char* tab, int lane)
 {
@@ -169,23 +178,23 @@ __device__ __noinline__ void ws_helper_prepare(const DevDesc& d, const WsCfg& cf
     const int bs0 = d.bs0, bs1 = d.bs1, nq = d.Mr * d.bs1, S = cfg.S;
     for (int e = lane; e < np * bs0; e += 32) {
         const int p = e / bs0, y = e - p * bs0;
-        tY[p * cfg.sY + y] = phasor_cycles((double)y * sh.u[0][p]);
+        tY[p * cfg.sY + y] = ws_phasor<kSfu>((double)y * sh.u[0][p]);
     }
     for (int e = lane; e < np * nq; e += 32) {
         const int p = e / nq, q = e - p * nq;
         const int r = q / bs1, z = q - r * bs1;
         const int yr = r % d.ue0, zr = r / d.ue0;
         const float2 cs = make_float2(sh.c[p].x * inv_scale, sh.c[p].y * inv_scale);
-        tQ[p * cfg.sQ + q] = cmul(cs, phasor_cycles((double)z * sh.v[0][p] + (double)yr * sh.u[1][p] + (double)zr * sh.v[1][p]));
+        tQ[p * cfg.sQ + q] = cmul(cs, ws_phasor<kSfu>((double)z * sh.v[0][p] + (double)yr * sh.u[1][p] + (double)zr * sh.v[1][p]));
     }
     for (int e = lane; e < np * 20; e += 32) {                          // fine delay phasors: wB[b], b < 16, and wL[a], a < 4 (j = 16 a + b)
         const int p = e / 20, b = e - p * 20;
-        if (b < 16) wB[p * cfg.sB + b] = phasor_cycles(-(sh.wcyc[p] * (double)(d.subc_step * b)));
-        else        wL[p * cfg.sL + (b - 16)] = phasor_cycles(-(sh.wcyc[p] * (double)(d.subc_step * 16 * (b - 16))));
+        if (b < 16) wB[p * cfg.sB + b] = ws_phasor<kSfu>(-(sh.wcyc[p] * (double)(d.subc_step * b)));
+        else        wL[p * cfg.sL + (b - 16)] = ws_phasor<kSfu>(-(sh.wcyc[p] * (double)(d.subc_step * 16 * (b - 16))));
     }
     for (int e = lane; e < np * S; e += 32) {                           // coarse delay phasors, one per 64-subcarrier segment
         const int p = e / S, sg = e - p * S;
-        wS[p * cfg.sS + sg] = phasor_cycles(-(sh.wcyc[p] * ((double)d.subc_start + (double)d.subc_step * 64.0 * (double)sg)));
+        wS[p * cfg.sS + sg] = ws_phasor<kSfu>(-(sh.wcyc[p] * ((double)d.subc_start + (double)d.subc_step * 64.0 * (double)sg)));
     }
     // row np of every table is the zero row: the operand builders read it for the padding slots np .. nslot-1
     const float2 zero = make_float2(0.f, 0.f);
@@ -221,7 +230,7 @@ template <int H>
 __device__ __forceinline__ bool ws_next_user(WsBars& bars, const unsigned char* bufs, int buf_stride, unsigned n_items,
                                              unsigned& it, unsigned& done, int& b)
 {
-    constexpr unsigned R = 2 * H, kAll = (1u << H) - 1u;
+    constexpr unsigned R = ws_bufs(H), kAll = (1u << H) - 1u;
     for (;;) {
         if (done == kAll) return false;
         const unsigned h = it % H;
@@ -255,7 +264,7 @@ fd_ws_kernel(const __grid_constant__ DevDesc d, const __grid_constant__ WsCfg cf
     unsigned char* sNlo = sNhi + kTcN * 128;
     unsigned char* sMhi = sm + cfg.off_M;                    // [128 rows 2j + s][128 B]: fine delay phasors of the user, 2x2 real form
     unsigned char* sMlo = sMhi + kTcN * 128;
-    unsigned char* bufs = sm + cfg.off_tab;                  // 2H buffers of cfg.tab_bytes: [TcUserBuf][tables]
+    unsigned char* bufs = sm + cfg.off_tab;                  // ws_bufs(H) buffers of cfg.tab_bytes: [TcUserBuf][tables]
     constexpr int kUb = (int)((sizeof(TcUserBuf) + 15) & ~size_t(15));
     auto user_buf = [&](int b) -> TcUserBuf& { return *reinterpret_cast<TcUserBuf*>(bufs + (size_t)b * cfg.tab_bytes); };
     auto user_tab = [&](int b) -> unsigned char* { return bufs + (size_t)b * cfg.tab_bytes + kUb; };
@@ -265,7 +274,7 @@ fd_ws_kernel(const __grid_constant__ DevDesc d, const __grid_constant__ WsCfg cf
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
     }
     if (tid == 64) {
-        for (int b = 0; b < 2 * H; ++b) { mbar_init(&bars.ub_full[b], 1); mbar_init(&bars.ub_empty[b], kWsConsumers); }
+        for (int b = 0; b < ws_bufs(H); ++b) { mbar_init(&bars.ub_full[b], 1); mbar_init(&bars.ub_empty[b], kWsConsumers); }
         mbar_init(&bars.op_full, kWsBuilders);
         mbar_init(&bars.mma_done[0], 1);  mbar_init(&bars.mma_done[1], 1);
         mbar_init(&bars.acc_empty[0], 128); mbar_init(&bars.acc_empty[1], 128);
@@ -282,9 +291,10 @@ fd_ws_kernel(const __grid_constant__ DevDesc d, const __grid_constant__ WsCfg cf
         const int h = warp - kWsHelper0;
         const unsigned int n_draw_last = n_items + gridDim.x * (unsigned)H - 1u;
         for (unsigned k = 0;; ++k) {
-            const int b = h + (int)(k & 1u) * H;                          // this helper's two buffers, alternately
-            mbar_wait(&bars.ub_empty[b], ((k >> 1) & 1u) ^ 1u);          // the readers of this buffer's previous user are done
-            ws_helper_prepare(d, cfg, ksplit, n_items, n_draw_last, ticket, user_buf(b), user_tab(b), lane);
+            constexpr bool two = ws_bufs(H) == 2 * H;
+            const int b = two ? h + (int)(k & 1u) * H : h;                // this helper's two buffers, alternately (or its only one)
+            mbar_wait(&bars.ub_empty[b], ((two ? (k >> 1) : k) & 1u) ^ 1u);   // the readers of this buffer's previous user are done
+            ws_helper_prepare<false>(d, cfg, ksplit, n_items, n_draw_last, ticket, user_buf(b), user_tab(b), lane);
             __syncwarp();
             const unsigned int item = user_buf(b).item;
             if (lane == 0) mbar_arrive(&bars.ub_full[b]);

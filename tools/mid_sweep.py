@@ -1,0 +1,31 @@
+"""Helper-bound shapes (per-user output below ~400 KB) with 4 and 8 helper warps:  python tools/mid_sweep.py"""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+import deepmimo_b200 as dmb
+from deepmimo_b200 import _lib
+from deepmimo_b200.synth import make_paths
+flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")
+shapes = [((8, 8), (1, 1), 64), ((8, 8), (1, 1), 128), ((16, 8), (1, 1), 128), ((8, 4), (1, 1), 256), ((8, 8), (1, 1), 512), ((8, 8), (2, 2), 64), ((8, 8), (1, 1), 1024)]
+for bs, ue, k in shapes:
+    m = bs[0] * bs[1] * ue[0] * ue[1]
+    n = int(min(200000, (6 << 30) // (8 * m * k)))
+    d = make_paths(n, 7, n_sc=max(k, 64), bandwidth=50e6, n_cols=25)
+    p = dmb.ChannelGenParameters()
+    p.bs_antenna.shape = np.array(bs); p.ue_antenna.shape = np.array(ue); p.bs_antenna.rotation = np.array([5, 10, 15])
+    p.ofdm.subcarriers = max(k, 64); p.ofdm.selected_subcarriers = np.arange(k); p.ofdm.bandwidth = 50e6
+    plan, _ = dmb.make_plan(dmb.Dataset(d), p, warn=False)
+    out = plan.alloc_out()
+    row = []
+    for h in ("0", "1", "4", "8"):
+        os.environ["DMK_WS_HELPERS"] = h
+        os.environ["DMK_FD_KERNEL"] = "tc"
+        for _ in range(2): plan.run(out)
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(5)]
+        for a, b in ev:
+            flush.fill_(1); a.record(); plan.run(out); b.record()
+        torch.cuda.synchronize()
+        ms = sorted(a.elapsed_time(b) for a, b in ev)[2]
+        hh = _lib.last_kernel().split(",")[2].split(">")[0]
+        row.append(f"H={h}[{hh}] {ms:.3f} ms {8e-9 * n * m * k / (ms * 1e-3):.0f} GB/s")
+    print(f"bs{bs} ue{ue} K={k} n={n} ({8 * m * k // 1024} KB/user): " + " | ".join(row), flush=True)
