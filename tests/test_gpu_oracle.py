@@ -166,9 +166,9 @@ def test_error_paths_match_reference_behaviour():
     p.bs_antenna.rotation = np.array([1, 2])
     with pytest.raises(AssertionError):
         ds.compute_channels(p)
-    d64 = {k: (v.astype(np.float64) if v.dtype == np.float32 else v) for k, v in s.data.items()}
+    mixed = dict(s.data, delay=s.data["delay"].astype(np.float64))          # all float32 or all float64 (tests/test_gpu_f64.py); not a mixture
     with pytest.raises(TypeError):
-        make_dataset(dmb, d64).compute_channels(dmb.ChannelGenParameters(s.params))
+        make_dataset(dmb, mixed).compute_channels(dmb.ChannelGenParameters(s.params))
     # empty dataset -> empty array of the right shape
     e = {k: v[:0] for k, v in s.data.items() if k != "tx_pos"}
     H = make_dataset(dmb, e).compute_channels(dmb.ChannelGenParameters(s.params))
