@@ -305,3 +305,26 @@ def test_rx_filter_is_ignored_in_time_domain_like_the_reference():
     p.ofdm.rx_filter = 1                              # channel.py:285-287: the TD branch never calls path_gen.generate
     H1 = make_dataset(dmb, s).compute_channels(p, warn=False)
     assert np.array_equal(H0.view(np.float32), H1.view(np.float32))
+
+
+def test_host_memory_modes_agree():
+    """The result may live in page-locked memory (default up to DMK_PINNED_CAP_GIB), in plain pageable memory (D2H staged through
+    two pinned chunk buffers and a host copy thread) or in a caller-provided array of either kind: same bytes every time."""
+    import torch
+    import deepmimo_b200 as dmb
+    from deepmimo_b200.synth import scenario
+    s = scenario(5, 700)
+    p = dmb.ChannelGenParameters(s.params)
+    ref = make_dataset(dmb, s).compute_channels(p, warn=False)
+    H_pg = make_dataset(dmb, s).compute_channels(p, warn=False, host_memory="pageable", chunk_users=97)
+    assert H_pg.flags.c_contiguous and np.array_equal(ref, H_pg)
+    H_pin = make_dataset(dmb, s).compute_channels(p, warn=False, host_memory="pinned")
+    assert np.array_equal(ref, H_pin)
+    mine = np.empty(ref.shape, dtype=np.complex64)                              # pageable caller buffer
+    out = make_dataset(dmb, s).compute_channels(p, warn=False, host_out=mine, chunk_users=256)
+    assert out is mine and np.array_equal(ref, mine)
+    pinned = torch.empty(ref.shape, dtype=torch.complex64, pin_memory=True)
+    out2 = make_dataset(dmb, s).compute_channels(p, warn=False, host_out=pinned)
+    assert np.array_equal(ref, out2)
+    with pytest.raises(ValueError):
+        make_dataset(dmb, s).compute_channels(p, warn=False, host_memory="managed")
