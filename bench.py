@@ -406,7 +406,9 @@ def run_e2e(res, steps, rank, world, dist, cap_bytes=4 << 30):
 
     t_pin = timed(call_pinned, 2)
     t_ceil = timed(call_ceiling, 1)
+    del host_out                            # back to torch's pinned-block cache: the default leg's first result reuses it
     t_def = timed(call_default, 3)          # the first two calls page-lock their result blocks; afterwards they are reused
+    ds._data.pop("channel", None)
     return dict(seconds=t_pin, seconds_default=t_def, seconds_ceiling=t_ceil, steps=steps, users=n,
                 coefs_per_step=int(np.prod(shape)), h2d=h2d, d2h=d2h)
 
