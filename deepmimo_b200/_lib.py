@@ -99,8 +99,8 @@ def load() -> ctypes.CDLL:
     with _lock:
         if _lib is not None:
             return _lib
-        path = _build.LIB
-        if not os.path.exists(path) or _build.is_stale():
+        path = os.environ.get("DMK_LIB_PATH") or _build.LIB        # DMK_LIB_PATH: an alternative build of the library (A/B timing)
+        if path == _build.LIB and (not os.path.exists(path) or _build.is_stale()):
             try:
                 _build.build_lib()
             except Exception as e:  # noqa: BLE001

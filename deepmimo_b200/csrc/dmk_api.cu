@@ -150,9 +150,12 @@ int device_state(const DeviceState*& out)
         if (e == cudaSuccess) e = cudaFuncSetAttribute(fd_small_kernel<4>, a, kSmemSmall);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(fd_small_kernel<8>, a, kSmemSmall);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(fd_small_kernel<16>, a, kSmemSmall);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(fd_small2_kernel<4>, a, kSmemSmall2);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(fd_small2_kernel<8>, a, kSmemSmall2);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(fd_small2_kernel<16>, a, kSmemSmall2);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(fd_small2_kernel<4, false>, a, kSmemSmall2);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(fd_small2_kernel<8, false>, a, kSmemSmall2);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(fd_small2_kernel<16, false>, a, kSmemSmall2);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(fd_small2_kernel<4, true>, a, kSmemSmall2);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(fd_small2_kernel<8, true>, a, kSmemSmall2);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(fd_small2_kernel<16, true>, a, kSmemSmall2);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(fd_ws_kernel<1>, a, kSmemWs1);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(fd_ws_kernel<4>, a, kSmemWs4);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(fd_tc_kernel, a, kSmemTc);
@@ -378,10 +381,11 @@ int dmk_channels_fd(const dmk_desc* desc, const float* power_dbw, const float* p
             sc.strideA = mt * 16 + 16;                         // +16 B: the 32 lanes of a chain round store to 32 different pool rows
             sc.strideW = n_seed | 1;
             const int per_path = sc.strideA + sc.strideW * 8;
-            // 16 warps per SM (4 CTAs): 13.5 KB per warp.  A pool of ~32-40 paths is one dense chain round per pass.
-            const int budget = 13 * 1024 + 512;
+            // 16 warps per SM (4 CTAs of 13.5 KB per warp), 20 when at most 8 rows are held in registers (5 CTAs, 10.5 KB per warp).
+            // A pool of ~32-40 paths is one dense chain round per pass.
+            const int budget = mt <= 8 ? 10 * 1024 + 512 : 13 * 1024 + 512;
             int cap = (budget - 256) / per_path;
-            if (cap > 40) cap = 40;
+            if (cap > (mt <= 8 ? 32 : 40)) cap = mt <= 8 ? 32 : 40;
             if (cap < d.P0) cap = d.P0;                         // one user always fits
             sc.window = kS2Window;
             sc.cap = cap;
@@ -400,9 +404,13 @@ int dmk_channels_fd(const dmk_desc* desc, const float* power_dbw, const float* p
             const size_t small_smem = off * kS2Warps;
             const long long sgrid = (n_users + upw * kS2Warps - 1) / (upw * kS2Warps);
             if (small_smem <= (size_t)kSmemSmall2 && sgrid <= 0x7fffffffLL) {
-                if (mt == 4)      fd_small2_kernel<4><<<(unsigned)sgrid, kS2Warps * 32, small_smem, st>>>(d, sc);
-                else if (mt == 8) fd_small2_kernel<8><<<(unsigned)sgrid, kS2Warps * 32, small_smem, st>>>(d, sc);
-                else              fd_small2_kernel<16><<<(unsigned)sgrid, kS2Warps * 32, small_smem, st>>>(d, sc);
+                const bool l3 = sc.n2 > 0;
+                if (mt == 4)       { if (l3) fd_small2_kernel<4, true><<<(unsigned)sgrid, kS2Warps * 32, small_smem, st>>>(d, sc);
+                                     else    fd_small2_kernel<4, false><<<(unsigned)sgrid, kS2Warps * 32, small_smem, st>>>(d, sc); }
+                else if (mt == 8)  { if (l3) fd_small2_kernel<8, true><<<(unsigned)sgrid, kS2Warps * 32, small_smem, st>>>(d, sc);
+                                     else    fd_small2_kernel<8, false><<<(unsigned)sgrid, kS2Warps * 32, small_smem, st>>>(d, sc); }
+                else               { if (l3) fd_small2_kernel<16, true><<<(unsigned)sgrid, kS2Warps * 32, small_smem, st>>>(d, sc);
+                                     else    fd_small2_kernel<16, false><<<(unsigned)sgrid, kS2Warps * 32, small_smem, st>>>(d, sc); }
                 cudaError_t e = cudaGetLastError();
                 if (e != cudaSuccess) return cuda_fail(e, "fd_small2_kernel launch");
                 g_launches.fetch_add(1);

@@ -193,8 +193,8 @@ struct Small2Cfg {
     unsigned mul_mt, mul_bs0;
 };
 
-template <int MT>
-__global__ void __launch_bounds__(kS2Warps * 32, 4)
+template <int MT, bool kL3>      // rows held in registers; three seed levels (K > 256) or two
+__global__ void __launch_bounds__(kS2Warps * 32, MT <= 8 ? 5 : 4)      // <= 8 rows: 96 registers, 20 warps per SM (measured +10 % on cfg1)
 fd_small2_kernel(const __grid_constant__ DevDesc d, const __grid_constant__ Small2Cfg cfg)
 {   // (occupancy is set by the host through the shared-memory slice per warp; the bound only caps registers at 128)
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -354,7 +354,7 @@ fd_small2_kernel(const __grid_constant__ DevDesc d, const __grid_constant__ Smal
                 const int c0 = col0 + 2 * lane;
                 const int cc = min(c0, K - 1);                                  // idle lanes read valid table entries
                 const float2* w_lo = wU + (cc & (cfg.n0 - 1));
-                const float2* w_m1 = wU + cfg.n0 + (cfg.n2 ? ((cc >> 4) & 15) : (cc >> cfg.log0));
+                const float2* w_m1 = wU + cfg.n0 + (kL3 ? ((cc >> 4) & 15) : (cc >> cfg.log0));
                 const float2* w_m2 = wU + cfg.n0 + cfg.n1 + (cc >> 8);
                 const unsigned char* ar_b = aU;
                 float2 acc[MT][2];
@@ -363,7 +363,7 @@ fd_small2_kernel(const __grid_constant__ DevDesc d, const __grid_constant__ Smal
                 #pragma unroll 1
                 for (int p = 0; p < np; ++p) {
                     float2 hi = *w_m1;
-                    if (cfg.n2) hi = cmul(hi, *w_m2);
+                    if (kL3) hi = cmul(hi, *w_m2);
                     const float2 w0 = cmul(hi, w_lo[0]);
                     const float2 w1 = cmul(hi, w_lo[1]);
                     const float2 w0s = make_float2(w0.y, w0.x), w1s = make_float2(w1.y, w1.x);
@@ -377,7 +377,8 @@ fd_small2_kernel(const __grid_constant__ DevDesc d, const __grid_constant__ Smal
                         acc[m][1] = __ffma2_rn(a1, w1, acc[m][1]);
                         acc[m][1] = __ffma2_rn(a2, w1s, acc[m][1]);
                     }
-                    w_lo += cfg.strideW; w_m1 += cfg.strideW; w_m2 += cfg.strideW; ar_b += cfg.strideA;
+                    w_lo += cfg.strideW; w_m1 += cfg.strideW; ar_b += cfg.strideA;
+                    if (kL3) w_m2 += cfg.strideW;
                 }
                 float2* o = out_u + c0;
                 if (vec_ok && col0 + 64 <= K && M == MT) {                      // whole pass inside the row, every register row is real
