@@ -331,12 +331,17 @@ int dmk_channels_fd(const dmk_desc* desc, const float* power_dbw, const float* p
         else if (smem1 <= (size_t)kSmemWs4) { n_helpers = 1; one_cta = true; }    // wide panels (e.g. 64 x 4): still persistent
         // Few users: split each user's stages over several CTAs so the grid covers >= 4 waves.
         long long wsplit = (want + n_users - 1) / n_users;
-        if (desc->ws_split > 0) wsplit = desc->ws_split;
+        if (desc->ws_split > 0) wsplit = desc->ws_split;          // (-3: two buffers per helper even where three fit -- A/B timing)
         if (wsplit > w.n_stages) wsplit = w.n_stages;
         if (wsplit < 1) wsplit = 1;
         const long long items = n_users * wsplit;
         if (n_helpers && chunk_div_ok && items < 0xffffff00LL) {
-            const size_t ws_smem = n_helpers == 1 ? smem1 : smem4;
+            size_t ws_smem = n_helpers == 1 ? smem1 : smem4;
+            w.bufs_per_helper = 2;
+            if (n_helpers == 4 && 1024 + off + 12 * buf_bytes <= (size_t)kSmemWs4 && desc->ws_split != -3) {     // room for a third buffer per helper
+                w.bufs_per_helper = 3;
+                ws_smem = 1024 + off + 12 * buf_bytes;
+            }
             static std::atomic<unsigned> ticket_seq{0};
             unsigned int* tickets = nullptr;
             cudaError_t e = cudaGetSymbolAddress(reinterpret_cast<void**>(&tickets), g_tc_ticket);

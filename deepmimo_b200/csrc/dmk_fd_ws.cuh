@@ -28,11 +28,13 @@ constexpr int kWsIssuer   = 8;
 constexpr int kWsHelper0  = 9;     // warps 9 .. 9 + H - 1
 constexpr int kWsBuilders = 128;
 constexpr int kWsMaxHelpers = 4;
-// user buffers: two per helper warp (it prepares user i + H while user i is consumed)
-__host__ __device__ constexpr int ws_bufs(int H) { return 2 * H; }
+// user buffers per helper warp: two (it prepares user i + H while user i is consumed) or, where shared memory allows, three --
+// users are consumed in ticket order, so a helper that is slow on a 25-path user holds up the consumers while the other helpers
+// sit on finished users; a third buffer lets them run further ahead
+constexpr int kWsMaxBufs = 12;
 
 struct WsBars {
-    uint64_t ub_full[2 * 4], ub_empty[2 * 4];   // helper -> everyone (1 arrival) ; everyone -> helper (288 arrivals)
+    uint64_t ub_full[kWsMaxBufs], ub_empty[kWsMaxBufs];   // helper -> everyone (1 arrival) ; everyone -> helper (288 arrivals)
     uint64_t op_full;                   // builders -> issuer (128 arrivals): operand tiles of the next stage are in smem
     uint64_t mma_done[2];               // tcgen05.commit: accumulator g & 1 complete, operand tiles free again
     uint64_t acc_empty[2];              // drain warps -> issuer (128 arrivals): accumulator g & 1 has been read out
@@ -108,6 +110,7 @@ struct WsCfg {
     int off_tY, off_tQ, off_wB, off_wL, off_wS;         // byte offsets inside a table buffer
     int sY, sQ, sB, sL, sS;                             // per-path table strides (float2 units), odd
     int S, n_chunks, n_stages;                          // segments per row, chunks per user, ceil(n_chunks / 128)
+    int bufs_per_helper;                                // 2 or 3 user buffers per helper warp
     unsigned mul_mt, mul_bs0, mul_s;                    // ceil(2^32 / d) reciprocals (0: d == 1)
 };
 
@@ -228,9 +231,9 @@ __device__ __forceinline__ void ws_store_chunks(uint32_t taddr, float* out, int 
 // its slots are skipped from then on, and the walk ends when every helper of the CTA has stopped.
 template <int H>
 __device__ __forceinline__ bool ws_next_user(WsBars& bars, const unsigned char* bufs, int buf_stride, unsigned n_items,
-                                             unsigned& it, unsigned& done, int& b)
+                                             unsigned& it, unsigned& done, int& b, unsigned R)
 {
-    constexpr unsigned R = ws_bufs(H), kAll = (1u << H) - 1u;
+    constexpr unsigned kAll = (1u << H) - 1u;
     for (;;) {
         if (done == kAll) return false;
         const unsigned h = it % H;
@@ -264,7 +267,7 @@ fd_ws_kernel(const __grid_constant__ DevDesc d, const __grid_constant__ WsCfg cf
     unsigned char* sNlo = sNhi + kTcN * 128;
     unsigned char* sMhi = sm + cfg.off_M;                    // [128 rows 2j + s][128 B]: fine delay phasors of the user, 2x2 real form
     unsigned char* sMlo = sMhi + kTcN * 128;
-    unsigned char* bufs = sm + cfg.off_tab;                  // ws_bufs(H) buffers of cfg.tab_bytes: [TcUserBuf][tables]
+    unsigned char* bufs = sm + cfg.off_tab;                  // bufs_per_helper * H buffers of cfg.tab_bytes: [TcUserBuf][tables]
     constexpr int kUb = (int)((sizeof(TcUserBuf) + 15) & ~size_t(15));
     auto user_buf = [&](int b) -> TcUserBuf& { return *reinterpret_cast<TcUserBuf*>(bufs + (size_t)b * cfg.tab_bytes); };
     auto user_tab = [&](int b) -> unsigned char* { return bufs + (size_t)b * cfg.tab_bytes + kUb; };
@@ -274,7 +277,7 @@ fd_ws_kernel(const __grid_constant__ DevDesc d, const __grid_constant__ WsCfg cf
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
     }
     if (tid == 64) {
-        for (int b = 0; b < ws_bufs(H); ++b) { mbar_init(&bars.ub_full[b], 1); mbar_init(&bars.ub_empty[b], kWsConsumers); }
+        for (int b = 0; b < cfg.bufs_per_helper * H; ++b) { mbar_init(&bars.ub_full[b], 1); mbar_init(&bars.ub_empty[b], kWsConsumers); }
         mbar_init(&bars.op_full, kWsBuilders);
         mbar_init(&bars.mma_done[0], 1);  mbar_init(&bars.mma_done[1], 1);
         mbar_init(&bars.acc_empty[0], 128); mbar_init(&bars.acc_empty[1], 128);
@@ -291,9 +294,9 @@ fd_ws_kernel(const __grid_constant__ DevDesc d, const __grid_constant__ WsCfg cf
         const int h = warp - kWsHelper0;
         const unsigned int n_draw_last = n_items + gridDim.x * (unsigned)H - 1u;
         for (unsigned k = 0;; ++k) {
-            constexpr bool two = ws_bufs(H) == 2 * H;
-            const int b = two ? h + (int)(k & 1u) * H : h;                // this helper's two buffers, alternately (or its only one)
-            mbar_wait(&bars.ub_empty[b], ((two ? (k >> 1) : k) & 1u) ^ 1u);   // the readers of this buffer's previous user are done
+            const unsigned B = (unsigned)cfg.bufs_per_helper;
+            const int b = h + (int)(k % B) * H;                           // this helper's buffers, round robin
+            mbar_wait(&bars.ub_empty[b], ((k / B) & 1u) ^ 1u);            // the readers of this buffer's previous user are done
             ws_helper_prepare<false>(d, cfg, ksplit, n_items, n_draw_last, ticket, user_buf(b), user_tab(b), lane);
             __syncwarp();
             const unsigned int item = user_buf(b).item;
@@ -313,7 +316,7 @@ fd_ws_kernel(const __grid_constant__ DevDesc d, const __grid_constant__ WsCfg cf
         unsigned g = 0;                                       // global stage counter (identical in every role)
         unsigned it = 0, done = 0;
         int cur = 0;
-        for (; ws_next_user<H>(bars, bufs, cfg.tab_bytes, n_items, it, done, cur); ++it) {
+        for (; ws_next_user<H>(bars, bufs, cfg.tab_bytes, n_items, it, done, cur, (unsigned)(cfg.bufs_per_helper * H)); ++it) {
             const TcUserBuf& ub = user_buf(cur);
             const unsigned int item = ub.item;
             const int ks = (int)(item % (unsigned)ksplit);
@@ -395,7 +398,7 @@ fd_ws_kernel(const __grid_constant__ DevDesc d, const __grid_constant__ WsCfg cf
         unsigned g = 0;
         unsigned it = 0, done = 0;
         int cur = 0;
-        for (; ws_next_user<H>(bars, bufs, cfg.tab_bytes, n_items, it, done, cur); ++it) {
+        for (; ws_next_user<H>(bars, bufs, cfg.tab_bytes, n_items, it, done, cur, (unsigned)(cfg.bufs_per_helper * H)); ++it) {
             const TcUserBuf& ub = user_buf(cur);
             const unsigned int item = ub.item;
             const int ks = (int)(item % (unsigned)ksplit);
@@ -446,7 +449,7 @@ fd_ws_kernel(const __grid_constant__ DevDesc d, const __grid_constant__ WsCfg cf
         unsigned g = 0;
         unsigned it = 0, done = 0;
         int cur = 0;
-        for (; ws_next_user<H>(bars, bufs, cfg.tab_bytes, n_items, it, done, cur); ++it) {
+        for (; ws_next_user<H>(bars, bufs, cfg.tab_bytes, n_items, it, done, cur, (unsigned)(cfg.bufs_per_helper * H)); ++it) {
             const TcUserBuf& ub = user_buf(cur);
             const unsigned int item = ub.item;
             const long long user = item / (unsigned)ksplit;
