@@ -157,6 +157,7 @@ int device_state(const DeviceState*& out)
         if (e == cudaSuccess) e = cudaFuncSetAttribute(fd_small2_kernel<8, true>, a, kSmemSmall2);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(fd_small2_kernel<16, true>, a, kSmemSmall2);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(fd_ws_kernel<1>, a, kSmemWs1);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(fd_ws_kernel<2>, a, kSmemWs1);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(fd_ws_kernel<4>, a, kSmemWs4);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(fd_tc_kernel, a, kSmemTc);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(fd_fast_kernel, a, kSmemFast);
@@ -326,7 +327,9 @@ int dmk_channels_fd(const dmk_desc* desc, const float* power_dbw, const float* p
         const int hf = desc->ws_helpers;                      // 0 = by shape, 1 or 4 pins the instantiation (tests, A/B timing)
         int n_helpers = 0;
         bool one_cta = false;                                 // one helper, but the tables leave room for a single CTA per SM only
-        if ((per_user_bytes <= 384 * 1024 || hf == 4 || smem1 > 113200) && smem4 <= (size_t)kSmemWs4 && hf != 1) n_helpers = 4;
+        const size_t smem2 = 1024 + off + 4 * buf_bytes;      // two helpers, four buffers: still two CTAs per SM when <= 113200
+        if (hf == 2 && smem2 <= 113200) n_helpers = 2;
+        else if ((per_user_bytes <= 384 * 1024 || hf == 4 || smem1 > 113200) && smem4 <= (size_t)kSmemWs4 && hf != 1) n_helpers = 4;
         else if (smem1 <= 113200) n_helpers = 1;              // + static + 1 KB reserve: two CTAs per SM
         else if (smem1 <= (size_t)kSmemWs4) { n_helpers = 1; one_cta = true; }    // wide panels (e.g. 64 x 4): still persistent
         // Few users: split each user's stages over several CTAs so the grid covers >= 4 waves.
@@ -336,7 +339,7 @@ int dmk_channels_fd(const dmk_desc* desc, const float* power_dbw, const float* p
         if (wsplit < 1) wsplit = 1;
         const long long items = n_users * wsplit;
         if (n_helpers && chunk_div_ok && items < 0xffffff00LL) {
-            size_t ws_smem = n_helpers == 1 ? smem1 : smem4;
+            size_t ws_smem = n_helpers == 1 ? smem1 : (n_helpers == 2 ? smem2 : smem4);
             w.bufs_per_helper = 2;
             if (n_helpers == 4 && 1024 + off + 12 * buf_bytes <= (size_t)kSmemWs4 && desc->ws_split != -3) {     // room for a third buffer per helper
                 w.bufs_per_helper = 3;
@@ -346,7 +349,7 @@ int dmk_channels_fd(const dmk_desc* desc, const float* power_dbw, const float* p
             unsigned int* tickets = nullptr;
             cudaError_t e = cudaGetSymbolAddress(reinterpret_cast<void**>(&tickets), g_tc_ticket);
             if (e != cudaSuccess) return cuda_fail(e, "cudaGetSymbolAddress(g_tc_ticket)");
-            const long long resident = ((n_helpers == 1 && !one_cta) ? 2LL : 1LL) * dev->sms;
+            const long long resident = (((n_helpers == 1 && !one_cta) || n_helpers == 2) ? 2LL : 1LL) * dev->sms;
             const long long pgrid = items < resident ? items : resident;
             // Programmatic dependent launch: the kernel releases its dependents at once, so the next libdmk launch can fill SMs
             // as this one's persistent CTAs retire.  Unless the caller set DMK_FLAG_INDEPENDENT_LAUNCH the kernel itself
@@ -360,8 +363,9 @@ int dmk_channels_fd(const dmk_desc* desc, const float* power_dbw, const float* p
             at[0].val.programmaticStreamSerializationAllowed = 1;
             lc.attrs = at; lc.numAttrs = 1;
             unsigned int* tk = tickets + (ticket_seq.fetch_add(1) % kTcTickets);
-            if (n_helpers == 1) e = cudaLaunchKernelEx(&lc, fd_ws_kernel<1>, d, w, (int)wsplit, (unsigned)items, tk, pdl_wait);
-            else                e = cudaLaunchKernelEx(&lc, fd_ws_kernel<4>, d, w, (int)wsplit, (unsigned)items, tk, pdl_wait);
+            if (n_helpers == 1)      e = cudaLaunchKernelEx(&lc, fd_ws_kernel<1>, d, w, (int)wsplit, (unsigned)items, tk, pdl_wait);
+            else if (n_helpers == 2) e = cudaLaunchKernelEx(&lc, fd_ws_kernel<2>, d, w, (int)wsplit, (unsigned)items, tk, pdl_wait);
+            else                     e = cudaLaunchKernelEx(&lc, fd_ws_kernel<4>, d, w, (int)wsplit, (unsigned)items, tk, pdl_wait);
             if (e != cudaSuccess) return cuda_fail(e, "fd_ws_kernel launch");
             g_launches.fetch_add(1);
             snprintf(g_kernel, sizeof(g_kernel), "fd_ws_kernel<128 chunks x 64 sc,3xf16,%d helper%s> grid=%lld items=%lld ksplit=%lld stages=%d smem=%zu",

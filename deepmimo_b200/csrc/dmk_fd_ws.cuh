@@ -248,7 +248,7 @@ __device__ __forceinline__ bool ws_next_user(WsBars& bars, const unsigned char* 
 }
 
 template <int H>        // helper warps per CTA: 1 (two CTAs per SM, large per-user outputs) or 4 (one CTA per SM, helper-bound shapes)
-__global__ void __launch_bounds__((9 + H) * 32, H == 1 ? 2 : 1)
+__global__ void __launch_bounds__((9 + H) * 32, H <= 2 ? 2 : 1)
 fd_ws_kernel(const __grid_constant__ DevDesc d, const __grid_constant__ WsCfg cfg, const int ksplit,
              const unsigned int n_items, unsigned int* ticket, const int pdl_wait)
 {
