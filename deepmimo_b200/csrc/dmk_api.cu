@@ -11,6 +11,7 @@
 #include "dmk_fd_tc.cuh"
 #include "dmk_fd_ws.cuh"
 #include "dmk_fd_small.cuh"
+#include "dmk_fd_mma.cuh"
 #include "dmk_td.cuh"
 #include "dmk_bf.cuh"
 
@@ -128,7 +129,7 @@ int check_arrays(const float* a, const float* b, const float* c, const float* e,
 // one-time opt-in to > 48 KB of dynamic shared memory is tracked per device: a process may call the library on
 // cuda:0 and then on cuda:1 (compute_channels(device=...), MacroDataset over several GPUs).
 constexpr int kMaxDevices = 64;
-constexpr int kSmemSmall = 72 * 1024, kSmemSmall2 = 100 * 1024, kSmemWs1 = 220 * 1024, kSmemWs4 = 220 * 1024, kSmemTc = 112 * 1024,
+constexpr int kSmemSmall = 72 * 1024, kSmemSmall2 = 100 * 1024, kSmemMma = 100 * 1024, kSmemWs1 = 220 * 1024, kSmemWs4 = 220 * 1024, kSmemTc = 112 * 1024,
               kSmemFast = 110 * 1024, kSmemTile = 200 * 1024;
 struct DeviceState { bool ready = false; int sms = 0; };
 DeviceState g_dev[kMaxDevices];
@@ -156,6 +157,12 @@ int device_state(const DeviceState*& out)
         if (e == cudaSuccess) e = cudaFuncSetAttribute(fd_small2_kernel<4, true>, a, kSmemSmall2);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(fd_small2_kernel<8, true>, a, kSmemSmall2);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(fd_small2_kernel<16, true>, a, kSmemSmall2);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(fd_mma_kernel<4, 0>, a, kSmemMma);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(fd_mma_kernel<4, 4>, a, kSmemMma);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(fd_mma_kernel<4, 8>, a, kSmemMma);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(fd_mma_kernel<8, 0>, a, kSmemMma);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(fd_mma_kernel<8, 4>, a, kSmemMma);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(fd_mma_kernel<8, 8>, a, kSmemMma);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(fd_ws_kernel<1>, a, kSmemWs1);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(fd_ws_kernel<2>, a, kSmemWs1);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(fd_ws_kernel<4>, a, kSmemWs4);
@@ -276,7 +283,7 @@ int dmk_channels_fd(const dmk_desc* desc, const float* power_dbw, const float* p
     const long long n_chunks_u = (long long)d.M * (d.K / (kTcN / 2));
     const bool tc_shape = (d.M >= 64 || n_chunks_u >= 128) && !d.fov_any;
     const bool use_tc = affine && !d.has_time_axis && div_ok && (d.K % (kTcN / 2) == 0) && d.K <= 4096 &&
-                        !want_tile && !want_ffma && hint != DMK_KERNEL_SMALL && hint != DMK_KERNEL_SMALL1 && (tc_shape || want_tc);
+                        !want_tile && !want_ffma && hint != DMK_KERNEL_SMALL && hint != DMK_KERNEL_SMALL1 && hint != DMK_KERNEL_MMA && (tc_shape || want_tc);
     const bool use_tc1 = use_tc && tc_smem <= (size_t)kSmemTc;            // one-CTA-per-user tensor-core kernel: fallback of the persistent one
     const bool use_fast = !use_tc1 && affine && !d.has_time_axis && div_ok && fast_smem <= (size_t)kSmemFast && !want_tile;
     const int tile_w_tc1 = (kTcN / 2) * tcfg.nsub;
@@ -371,6 +378,53 @@ int dmk_channels_fd(const dmk_desc* desc, const float* power_dbw, const float* p
             snprintf(g_kernel, sizeof(g_kernel), "fd_ws_kernel<128 chunks x 64 sc,3xf16,%d helper%s> grid=%lld items=%lld ksplit=%lld stages=%d smem=%zu",
                      n_helpers, n_helpers > 1 ? "s" : "", pgrid, items, wsplit, w.n_stages, ws_smem);
             return DMK_OK;
+        }
+    }
+    // Small per-user outputs (M <= 64, K % 16 == 0): warp-level tensor-core kernel, see dmk_fd_mma.cuh.  Default for the small arrays
+    // (M <= 16); DMK_KERNEL_MMA forces it on every eligible shape, DMK_KERNEL_SMALL keeps the CUDA-core fd_small2_kernel.
+    {
+        const bool mma_shape = affine && !d.has_time_axis && d.M <= 64 && (d.K % 16 == 0) && d.K <= 4096 &&
+                               ((reinterpret_cast<uintptr_t>(out_c64) & 15) == 0);
+        const bool mma_wanted = hint == DMK_KERNEL_MMA || (hint == DMK_KERNEL_AUTO && d.M <= 16);
+        if (mma_shape && mma_wanted) {
+            MmaCfg mc;
+            memset(&mc, 0, sizeof(mc));
+            // chunk width J: L rows cost ~14 instructions each per path (R = M K / J of them), F columns ~20 (J of them)
+            int J = (d.K % 32 == 0 && (long long)d.M * d.K / 16 > 46) ? 32 : 16;
+            if (desc->ws_helpers == 16 || (desc->ws_helpers == 32 && d.K % 32 == 0)) J = desc->ws_helpers;      // A/B timing
+            const int nt = J / 4;
+            mc.S = d.K / J;
+            mc.R = d.M * mc.S;
+            mc.n_mt = (mc.R + 15) / 16;
+            mc.mul_s = mc.S > 1 ? (unsigned)((0x100000000ULL + mc.S - 1) / mc.S) : 0u;
+            const int sb = mc.S % 8 == 0 ? 8 : (mc.S % 4 == 0 ? 4 : 0);      // chunks of one antenna row that share a base phasor
+            mc.G = mc.n_mt < 2 ? mc.n_mt : (nt == 4 ? 1 : 2);
+            if (desc->ws_split > 0) mc.G = desc->ws_split < mc.n_mt ? desc->ws_split : mc.n_mt;
+            size_t off = 0;
+            auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 15) & ~size_t(15); return (int)o; };
+            mc.off_A    = take((size_t)2 * mc.G * 8 * 256);
+            mc.off_B    = take((size_t)2 * nt * 8 * 128);
+            mc.off_list = take((size_t)32);
+            mc.off_meta = take((size_t)(5 * kMmWindow + 1) * sizeof(int));
+            mc.warp_bytes = (int)off;
+            mc.off_warps = (int)((((size_t)4 * d.M + mc.S) * sizeof(double) + 15) & ~size_t(15));
+            long long upw = n_users / (2LL * 3 * dev->sms * kMmWarps);
+            upw = upw < 4 ? 4 : (upw > 16 ? 16 : upw);
+            mc.users_per_warp = (int)upw;
+            const size_t mma_smem = (size_t)mc.off_warps + off * kMmWarps;
+            const long long sgrid = (n_users + upw * kMmWarps - 1) / (upw * kMmWarps);
+            if (mma_smem <= (size_t)kSmemMma && sgrid <= 0x7fffffffLL) {
+                const dim3 gr((unsigned)sgrid), bl(kMmWarps * 32);
+                if (nt == 4) { if (sb == 8) fd_mma_kernel<4, 8><<<gr, bl, mma_smem, st>>>(d, mc); else if (sb == 4) fd_mma_kernel<4, 4><<<gr, bl, mma_smem, st>>>(d, mc);
+                               else fd_mma_kernel<4, 0><<<gr, bl, mma_smem, st>>>(d, mc); }
+                else         { if (sb == 8) fd_mma_kernel<8, 8><<<gr, bl, mma_smem, st>>>(d, mc); else if (sb == 4) fd_mma_kernel<8, 4><<<gr, bl, mma_smem, st>>>(d, mc);
+                               else fd_mma_kernel<8, 0><<<gr, bl, mma_smem, st>>>(d, mc); }
+                cudaError_t e = cudaGetLastError();
+                if (e != cudaSuccess) return cuda_fail(e, "fd_mma_kernel launch");
+                g_launches.fetch_add(1);
+                snprintf(g_kernel, sizeof(g_kernel), "fd_mma_kernel<m16n8k16,3xf16,J=%d,SB=%d> grid=%lld users/warp=%lld chunks=%d G=%d smem=%zu", J, sb, sgrid, upw, mc.R, mc.G, mma_smem);
+                return DMK_OK;
+            }
         }
     }
     // Small arrays (M <= 16): warp-level kernels, see dmk_fd_small.cuh.  Default: the densely packed fd_small2_kernel;

@@ -1,0 +1,323 @@
+// dmk_fd_mma.cuh -- FD channel kernel for small per-user outputs (a few KB to ~100 KB): warp-level tensor-core accumulate.
+//
+// fd_small2_kernel (dmk_fd_small.cuh) spends 880 of its 1 670 warp-instructions per user on the CUDA-core accumulate
+// (profiles/r02_ncu_fd_small2_cfg1.txt): 512 complex MACs per path and user is the floor of that formulation.  The persistent
+// tcgen05 kernel (dmk_fd_ws.cuh) cannot take these users either: its per-user operand (128 rows of fine phasors) costs more shared
+// memory traffic than a 4 KB user has output, and below ~400 KB per user it is bound by its helper warps.  Here the accumulate is a
+// warp-level mma.sync (m16n8k16, FP16 hi/lo split, FP32 accumulation) fed from registers:
+//
+//   a user's output is a flat array of R = M * K / J chunks of J subcarriers (J = 16 or 32; chunk r = m * S + seg, S = K / J);
+//   H[chunk r, j] = sum_p L[r, p] * F[p, j],   L[r, p] = c_p * a[m, p] * exp(-j 2 pi wcyc_p k0(seg)),   F[p, j] = exp(-j 2 pi wcyc_p step j)
+//   real form:  D[r, 2 j + s] = sum_{p, e} A[r, 2 p + e] * B[2 p + e, 2 j + s],   A = (Lr, Li),   B = ((Fr, Fi), (-Fi, Fr))
+//   -> MMA rows = chunks, MMA columns = the floats inside a chunk (so an accumulator fragment is a contiguous piece of the output),
+//      MMA k = (path, re/im): 8 paths per k-step.
+//
+// Phases of a pass (one warp, no CTA-wide synchronisation; 1-3 are those of fd_small2_kernel):
+//   1. window: power rows of the next 4 users -> bit masks of the columns whose chain must run;
+//   2. whole users are taken while their (user, column) pairs fit ONE round of 32 lanes;
+//   3. chain round, lane = dense pair: the three float64 chains + combine; the user's largest |c_p| (a power of two, by a masked
+//      warp reduction over the lanes of the same user) scales the operands into FP16 range and is undone at the store;
+//   4. operand rows, still lane = path: F (J columns: products of two phasor levels) and, per group of G m-tiles, L (blocks of SB
+//      consecutive chunks of one antenna row share a base phasor -- gain x steering x coarse delay in ONE float64-reduced argument --
+//      times SB block phasors), each split into FP16 hi + lo and stored in fragment order, path index fastest;
+//   5. per user and m-tile: fragments by 16- and 8-byte shared loads that land in consecutive registers (a lane's two paths of a
+//      k-step are adjacent pool slots), 3 MMAs (hi hi + lo hi + hi lo) per (n-tile, k-step), 16-byte stores.
+// Pool rows are XOR-swizzled (32 slots of 8 or 4 bytes are exactly 256 / 128 bytes: no padding) so that producer stores and fragment
+// loads are both conflict-free.  The pool is zeroed once: slots past a user's last path in its last k-step then hold finite stale
+// values on the B side, and the A side is zeroed in registers.
+#pragma once
+#include <cuda_fp16.h>
+#include "dmk_fd.cuh"
+
+namespace dmk {
+
+constexpr int kMmWarps  = 4;
+constexpr int kMmWindow = 4;                       // users examined per pass
+constexpr int kMmSlots  = 32;                      // pool slots (paths) per pass: one chain round
+
+struct MmaCfg {
+    int warp_bytes;                   // bytes of a warp's shared-memory slice
+    int off_warps;                    // bytes of the CTA-wide tables in front of the warp slices
+    int off_A, off_B, off_list, off_meta;
+    int G;                            // m-tiles (16 chunks each) whose L rows are resident at a time
+    int n_mt;                         // m-tiles per user = ceil(R / 16)
+    int S, R;                         // chunks per antenna row, chunks per user
+    int users_per_warp;
+    unsigned mul_s;                   // ceil(2^32 / S) (S > 1): chunk -> antenna row by a multiply-high
+};
+
+__device__ __forceinline__ void mma_m16n8k16_f16(float (&d)[4], const uint4& a, const uint2& b)
+{
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y));
+}
+
+// (x, y) -> FP16 pairs hi = (f16(x), f16(y)) and lo = (f16(x - hi.x), f16(y - hi.y)); x in the low half.
+__device__ __forceinline__ void split_f16x2(float x, float y, unsigned& hi, unsigned& lo)
+{
+    const __half2 h = __floats2half2_rn(x, y);
+    const float2 hf = __half22float2(h);
+    const __half2 l = __floats2half2_rn(x - hf.x, y - hf.y);
+    hi = *reinterpret_cast<const unsigned*>(&h);
+    lo = *reinterpret_cast<const unsigned*>(&l);
+}
+
+// Pool layout of a warp (bytes).  A side (L): [hi | lo][G * 8 row pairs (m-tile, g)][32 slots] 8 B = chunks g and g + 8 of the slot's
+// path, row = 256 B, 16-byte unit index XOR-ed with (g & 1) << 2.  B side (F): [hi | lo][NT n-tiles][8 fragment columns g][32 slots]
+// 4 B, row = 128 B, byte offset XOR-ed with (g & 3) << 5.
+__device__ __forceinline__ int mm_a_off(int rowpair, int slot) { return rowpair * 256 + ((slot * 8) ^ ((rowpair & 1) << 6)); }
+__device__ __forceinline__ int mm_b_off(int row, int slot)     { return row * 128 + ((slot * 4) ^ ((row & 3) << 5)); }
+
+template <int NT, int SB>      // n-tiles of 8 floats per chunk: J = 4 NT subcarriers; SB: chunks per base phasor (0: one phasor per chunk)
+__global__ void __launch_bounds__(kMmWarps * 32, 4)
+fd_mma_kernel(const __grid_constant__ DevDesc d, const __grid_constant__ MmaCfg cfg)
+{
+    constexpr int J = 4 * NT;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double (*s_coef)[4] = reinterpret_cast<double (*)[4]>(smem_raw);     // [M] element m -> (y_t, z_t, y_r, z_r) panel coordinates
+    double* s_k0 = reinterpret_cast<double*>(smem_raw) + 4 * d.M;        // [S] chunk segment -> subcarrier offset of its first column
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int m = tid; m < d.M; m += kMmWarps * 32) {
+        const int r = m / d.Mt, t = m - r * d.Mt;
+        s_coef[m][0] = (double)(t % d.bs0); s_coef[m][1] = (double)(t / d.bs0);
+        s_coef[m][2] = (double)(r % d.ue0); s_coef[m][3] = (double)(r / d.ue0);
+    }
+    for (int s = tid; s < cfg.S; s += kMmWarps * 32) s_k0[s] = (double)d.subc_start + (double)d.subc_step * (double)(J * s);
+
+    unsigned char* wsm = smem_raw + cfg.off_warps + warp * cfg.warp_bytes;
+    unsigned char* sAh  = wsm + cfg.off_A;                                     // A side, hi halves; lo halves follow
+    unsigned char* sAl  = sAh + cfg.G * 8 * 256;
+    unsigned char* sBh  = wsm + cfg.off_B;                                     // B side, hi halves; lo halves follow
+    unsigned char* sBl  = sBh + NT * 8 * 128;
+    unsigned char* list = wsm + cfg.off_list;                                  // [32] (user in window << 5) | column
+    int* s_base         = reinterpret_cast<int*>(wsm + cfg.off_meta);          // [kMmWindow + 1] first pool slot of the user (even)
+    int* s_cnt          = s_base + kMmWindow + 1;                              // [kMmWindow] contributing paths
+    unsigned* s_need    = reinterpret_cast<unsigned*>(s_cnt + kMmWindow);      // [kMmWindow] columns whose chain runs
+    unsigned* s_valid   = s_need + kMmWindow;                                  // [kMmWindow] columns with a path (valid_mask)
+    float* s_scale      = reinterpret_cast<float*>(s_valid + kMmWindow);       // [kMmWindow] 2^e undoing the operand scale
+    for (int o = lane * 16; o < cfg.off_list; o += 32 * 16) *reinterpret_cast<uint4*>(wsm + o) = make_uint4(0u, 0u, 0u, 0u);
+    __syncthreads();                              // the only CTA-wide barrier: warps are independent from here on
+
+    const long long u_begin = ((long long)blockIdx.x * kMmWarps + warp) * cfg.users_per_warp;
+    const long long u_end = min(u_begin + (long long)cfg.users_per_warp, d.n_users);
+    const unsigned ltmask = (1u << lane) - 1u;
+    const int K = d.K, M = d.M, P0 = d.P0;
+    const bool need_angles = prologue_needs_angles(d);
+    const int g = lane >> 2, t = lane & 3;
+    const double kstep = (double)d.subc_step;
+
+    for (long long cur = u_begin; cur < u_end; ) {
+        // ---- 1. window (as fd_small2_kernel)
+        const int n_in = (int)min((long long)kMmWindow, u_end - cur);
+        const long long prow = cur * (long long)d.ld + lane;
+        float pw[kMmWindow];                                                   // only the NaN-ness of the power is used here
+        #pragma unroll
+        for (int ul = 0; ul < kMmWindow; ++ul) {
+            pw[ul] = __int_as_float(0x7fc00000);
+            if (ul < n_in && lane < P0)
+                pw[ul] = d.in_f64 ? (float)__ldg(reinterpret_cast<const double*>(d.power) + prow + ul * d.ld) : __ldg(d.power + prow + ul * d.ld);
+        }
+        #pragma unroll
+        for (int ul = 0; ul < kMmWindow; ++ul) {
+            const bool in = ul < n_in && lane < P0;
+            const bool valid = in && lane < d.P && !(pw[ul] != pw[ul]);           // channel.py:260, dataset.py:258-261
+            const unsigned vb = __ballot_sync(0xffffffffu, valid);
+            const unsigned nb = d.fov_any ? __ballot_sync(0xffffffffu, in) : vb;
+            if (lane == ul) { s_valid[ul] = vb; s_need[ul] = nb; }
+        }
+        __syncwarp();
+        // ---- 2. whole users while their pairs fit one round of lanes and the pool (a user's first slot is even: a lane loads
+        //         the operands of its two paths of a k-step with one aligned access)
+        int cum = 0, slots = 0, n_take = 0;
+        long long o = cur * (long long)P0 + lane;
+        #pragma unroll 1
+        for (int ul = 0; ul < n_in; ++ul, o += P0) {
+            const unsigned nb = s_need[ul], vb = s_valid[ul];
+            const int c = __popc(nb);
+            const int base = (slots + 1) & ~1;
+            if (ul > 0 && (cum + c > 32 || base + c > kMmSlots)) break;
+            if (lane == 0) { s_base[ul] = base; s_cnt[ul] = 0; s_scale[ul] = 0.f; }
+            const bool run = (nb >> lane) & 1u;
+            if (run) list[cum + __popc(nb & ltmask)] = (unsigned char)((ul << 5) | lane);
+            if (lane < P0) {
+                if (d.valid_mask) d.valid_mask[o] = (vb >> lane) & 1u;
+                if (!run) {                                                     // no FoV mask is built and the column has no power
+                    if (d.fov_mask)  d.fov_mask[o] = 1;
+                    if (d.clip_mask) d.clip_mask[o] = 0;
+                }
+            }
+            cum += c;
+            slots = base + c;
+            ++n_take;
+        }
+        __syncwarp();
+        if (lane < 7 * 4) {                                                     // rows of the users after this pass towards L2
+            const int arr = lane >> 2;
+            const long long u = cur + n_take + (lane & 3);
+            if (u < u_end) {
+                const float* base = (arr == 0) ? d.power : (arr == 1) ? d.phase : (arr == 2) ? d.delay : (arr == 3) ? d.az[0] : (arr == 4) ? d.el[0]
+                                  : (arr == 5) ? d.az[1] : d.el[1];
+                asm volatile("prefetch.global.L2 [%0];" :: "l"(reinterpret_cast<const char*>(base) + u * (long long)d.ld * (d.in_f64 ? 8 : 4)));
+            }
+        }
+        // ---- 3. the chain round: lane = dense pair (cum <= 32)
+        const bool act = lane < cum;
+        int ul = kMmWindow, col = 0;
+        if (act) { const int e = list[lane]; ul = e >> 5; col = e & 31; }
+        PathState st;
+        st.contrib = false; st.valid = false; st.fov = true; st.over = false;
+        st.c = make_float2(0.f, 0.f); st.wcyc = 0.0; st.u[0] = st.u[1] = st.v[0] = st.v[1] = 0.0;
+        if (act) {
+            const long long user = cur + ul;
+            SideOut s0, s1; GainOut gn;
+            if (need_angles) { prologue_side<true>(d, user, col, 0, s0, d.Mt > 1);  prologue_side<true>(d, user, col, 1, s1, d.Mr > 1); }
+            else             { prologue_side<false>(d, user, col, 0, s0, d.Mt > 1); prologue_side<false>(d, user, col, 1, s1, d.Mr > 1); }
+            prologue_gain<true>(d, user, col, gn);
+            prologue_combine<true>(d, s0, s1, gn, st);
+            const long long om = user * (long long)P0 + col;
+            if (d.fov_mask)  d.fov_mask[om]  = st.fov ? 1 : 0;
+            if (d.clip_mask) d.clip_mask[om] = (st.valid && st.over) ? 1 : 0;
+        }
+        const bool contrib = act && st.contrib;
+        const unsigned bc = __ballot_sync(0xffffffffu, contrib);
+        const unsigned same = __match_any_sync(0xffffffffu, ul);                 // lanes of the same user (idle lanes: key kMmWindow)
+        // operand scale: 2^-(e + 1), e = exponent of the user's largest |re|, |im| of a path gain
+        const unsigned amp_bits = contrib ? __float_as_uint(fmaxf(fabsf(st.c.x), fabsf(st.c.y))) : 0u;
+        unsigned ef = __reduce_max_sync(same, amp_bits) >> 23;
+        ef = ef < 1u ? 1u : (ef > 252u ? 252u : ef);
+        const float sc_dn = __uint_as_float((253u - ef) << 23);
+        const int slot = act ? s_base[ul] + __popc(bc & same & ltmask) : 0;      // contributing paths of a user, in column order
+        if (act && lane == __ffs(same) - 1) { s_cnt[ul] = __popc(bc & same); s_scale[ul] = __uint_as_float((ef + 1u) << 23); }
+        const float2 cs = make_float2(st.c.x * sc_dn, st.c.y * sc_dn);
+        // ---- 4a. F: column j = 4 b + i of a chunk -> f4[b] * f1[i]; n-tile 2 (j >> 3) + (j & 1), fragment columns 2 ((j >> 1) & 3) + s
+        //          s = 0: (Fr, -Fi)   s = 1: (Fi, Fr)   = rows (2p, 2p + 1) of B
+        float2 wb[SB > 0 ? SB : 1];                                              // block phasors of the L rows
+        if (contrib) {
+            float2 f1[4], f4[NT];
+            f1[0] = make_float2(1.f, 0.f); f4[0] = f1[0];
+            #pragma unroll
+            for (int i = 1; i < 4; ++i) f1[i] = phasor_cycles_sfu(-(st.wcyc * (kstep * (double)i)));
+            #pragma unroll
+            for (int b = 1; b < NT; ++b) f4[b] = phasor_cycles_sfu(-(st.wcyc * (kstep * (double)(4 * b))));
+            #pragma unroll
+            for (int b = 0; b < NT; ++b) {
+                #pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int j = 4 * b + i;
+                    const float2 f = (b == 0) ? f1[i] : (i == 0 ? f4[b] : cmul(f4[b], f1[i]));
+                    unsigned x, y;                                               // (lo half = re, hi half = im)
+                    split_f16x2(f.x, f.y, x, y);
+                    const int row = (2 * (j >> 3) + (j & 1)) * 8 + 2 * ((j >> 1) & 3);
+                    *reinterpret_cast<unsigned*>(sBh + mm_b_off(row, slot))     = x ^ 0x80000000u;
+                    *reinterpret_cast<unsigned*>(sBh + mm_b_off(row + 1, slot)) = __byte_perm(x, 0, 0x1032);
+                    *reinterpret_cast<unsigned*>(sBl + mm_b_off(row, slot))     = y ^ 0x80000000u;
+                    *reinterpret_cast<unsigned*>(sBl + mm_b_off(row + 1, slot)) = __byte_perm(y, 0, 0x1032);
+                }
+            }
+            if constexpr (SB > 0) {
+                wb[0] = make_float2(1.f, 0.f);
+                #pragma unroll
+                for (int i = 1; i < SB; ++i) wb[i] = phasor_cycles_sfu(-(st.wcyc * (kstep * (double)(J * i))));
+            }
+        }
+        #pragma unroll 1
+        for (int mt0 = 0; mt0 < cfg.n_mt; mt0 += cfg.G) {
+            const int n_g = min(cfg.G, cfg.n_mt - mt0);
+            // ---- 4b. L rows of the m-tiles mt0 .. mt0 + n_g
+            if (contrib) {
+                #pragma unroll 1
+                for (int ml = 0; ml < n_g; ++ml) {
+                    auto chunk_phasor = [&](unsigned r) {                         // gain x steering x coarse delay phasor of chunk r
+                        r = min(r, (unsigned)(cfg.R - 1));
+                        const unsigned m = cfg.mul_s ? __umulhi(r, cfg.mul_s) : r;
+                        const unsigned seg = r - m * (unsigned)cfg.S;
+                        const double cyc = fma(s_coef[m][0], st.u[0], fma(s_coef[m][1], st.v[0], fma(s_coef[m][2], st.u[1],
+                                           fma(s_coef[m][3], st.v[1], -(st.wcyc * s_k0[seg])))));
+                        return cmul(cs, phasor_cycles_sfu(cyc));
+                    };
+                    const unsigned r0 = (unsigned)(mt0 + ml) * 16u;
+                    if constexpr (SB > 0) {
+                        constexpr int SBc = SB, NB = 16 / SBc;
+                        float2 base[NB];
+                        #pragma unroll
+                        for (int b = 0; b < NB; ++b) base[b] = chunk_phasor(r0 + b * SBc);
+                        #pragma unroll
+                        for (int gg = 0; gg < 8; ++gg) {
+                            const float2 l0 = (gg % SBc == 0) ? base[gg / SBc] : cmul(base[gg / SBc], wb[gg % SBc]);
+                            const float2 l1 = ((gg + 8) % SBc == 0) ? base[(gg + 8) / SBc] : cmul(base[(gg + 8) / SBc], wb[(gg + 8) % SBc]);
+                            unsigned h0, q0, h1, q1;
+                            split_f16x2(l0.x, l0.y, h0, q0);
+                            split_f16x2(l1.x, l1.y, h1, q1);
+                            const int off = mm_a_off(ml * 8 + gg, slot);
+                            *reinterpret_cast<uint2*>(sAh + off) = make_uint2(h0, h1);
+                            *reinterpret_cast<uint2*>(sAl + off) = make_uint2(q0, q1);
+                        }
+                    } else {
+                        #pragma unroll 2
+                        for (int gg = 0; gg < 8; ++gg) {
+                            const float2 l0 = chunk_phasor(r0 + gg), l1 = chunk_phasor(r0 + gg + 8);
+                            unsigned h0, q0, h1, q1;
+                            split_f16x2(l0.x, l0.y, h0, q0);
+                            split_f16x2(l1.x, l1.y, h1, q1);
+                            const int off = mm_a_off(ml * 8 + gg, slot);
+                            *reinterpret_cast<uint2*>(sAh + off) = make_uint2(h0, h1);
+                            *reinterpret_cast<uint2*>(sAl + off) = make_uint2(q0, q1);
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+            // ---- 5. per user and m-tile: fragments, MMAs, stores.  k-step = 8 pool slots; this lane's paths are slots 2t, 2t + 1
+            //         (MMA k indices (2t, 2t + 1) = (re, im) of the first, (2t + 8, 2t + 9) of the second).
+            #pragma unroll 1
+            for (int uu = 0; uu < n_take; ++uu) {
+                const int np = s_cnt[uu];
+                const float sc_up = s_scale[uu];
+                float2* out_u = d.out + (cur + uu) * (long long)M * K;
+                const int qb = s_base[uu] + 2 * t;
+                #pragma unroll 1
+                for (int ml = 0; ml < n_g; ++ml) {
+                    float acc[NT][4];
+                    #pragma unroll
+                    for (int n = 0; n < NT; ++n) { acc[n][0] = 0.f; acc[n][1] = 0.f; acc[n][2] = 0.f; acc[n][3] = 0.f; }
+                    #pragma unroll 1
+                    for (int k0 = 0; k0 < np; k0 += 8) {
+                        const int sl = min(qb + k0, kMmSlots - 2);                   // past the row's end only when both paths are >= np (zeroed below)
+                        const int aoff = mm_a_off(ml * 8 + g, sl);
+                        uint4 ah = *reinterpret_cast<const uint4*>(sAh + aoff);       // chunks g, g + 8 of path 2t; of path 2t + 1
+                        uint4 al = *reinterpret_cast<const uint4*>(sAl + aoff);
+                        if (k0 + 2 * t >= np)     { ah.x = 0u; ah.y = 0u; al.x = 0u; al.y = 0u; }
+                        if (k0 + 2 * t + 1 >= np) { ah.z = 0u; ah.w = 0u; al.z = 0u; al.w = 0u; }
+                        #pragma unroll
+                        for (int n = 0; n < NT; ++n) {
+                            const int boff = mm_b_off(n * 8 + g, sl);
+                            const uint2 bh = *reinterpret_cast<const uint2*>(sBh + boff);
+                            const uint2 bl = *reinterpret_cast<const uint2*>(sBl + boff);
+                            mma_m16n8k16_f16(acc[n], ah, bh);
+                            mma_m16n8k16_f16(acc[n], al, bh);
+                            mma_m16n8k16_f16(acc[n], ah, bl);
+                        }
+                    }
+                    // chunk r = 16 mt + g (+ 8): J complex values at r * J; this lane holds columns 8 pair + 2 t, + 1 of both chunks
+                    const int r0 = (mt0 + ml) * 16 + g;
+                    #pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int r = r0 + 8 * h;
+                        if (r < cfg.R) {
+                            float4* o4 = reinterpret_cast<float4*>(out_u + (long long)r * J + 2 * t);
+                            #pragma unroll
+                            for (int np2 = 0; np2 < NT / 2; ++np2)
+                                __stcs(o4 + np2 * 4, make_float4(acc[2 * np2][2 * h] * sc_up, acc[2 * np2][2 * h + 1] * sc_up,
+                                                                 acc[2 * np2 + 1][2 * h] * sc_up, acc[2 * np2 + 1][2 * h + 1] * sc_up));
+                        }
+                    }
+                }
+            }
+            __syncwarp();                                                       // the L rows are rewritten by the next group / pass
+        }
+        cur += n_take;
+    }
+}
+
+}  // namespace dmk
