@@ -282,7 +282,12 @@ int dmk_channels_fd(const dmk_desc* desc, const float* power_dbw, const float* p
     // FoV-sparse scenarios leave few paths per user (per-user overhead dominates): packed-FP32 kernel.  Measured: profiles/README.md.
     const long long n_chunks_u = (long long)d.M * (d.K / (kTcN / 2));
     const bool tc_shape = (d.M >= 64 || n_chunks_u >= 128) && !d.fov_any;
-    const bool use_tc = affine && !d.has_time_axis && div_ok && (d.K % (kTcN / 2) == 0) && d.K <= 4096 &&
+    // Per-user outputs of at most 64 KB go to the warp-level tensor-core kernel (dmk_fd_mma.cuh) instead: the persistent kernel is
+    // bound by its helper warps there (8x8 x K=64: 1.4 against 3.4 TB/s; profiles/README.md).
+    const bool mma_shape = affine && !d.has_time_axis && d.M <= 64 && (d.K % 16 == 0) && d.K <= 4096 &&
+                           ((reinterpret_cast<uintptr_t>(out_c64) & 15) == 0);
+    const bool mma_pref = mma_shape && hint == DMK_KERNEL_AUTO && (long long)d.M * d.K * 8 <= 64 * 1024;
+    const bool use_tc = !mma_pref && affine && !d.has_time_axis && div_ok && (d.K % (kTcN / 2) == 0) && d.K <= 4096 &&
                         !want_tile && !want_ffma && hint != DMK_KERNEL_SMALL && hint != DMK_KERNEL_SMALL1 && hint != DMK_KERNEL_MMA && (tc_shape || want_tc);
     const bool use_tc1 = use_tc && tc_smem <= (size_t)kSmemTc;            // one-CTA-per-user tensor-core kernel: fallback of the persistent one
     const bool use_fast = !use_tc1 && affine && !d.has_time_axis && div_ok && fast_smem <= (size_t)kSmemFast && !want_tile;
@@ -380,17 +385,17 @@ int dmk_channels_fd(const dmk_desc* desc, const float* power_dbw, const float* p
             return DMK_OK;
         }
     }
-    // Small per-user outputs (M <= 64, K % 16 == 0): warp-level tensor-core kernel, see dmk_fd_mma.cuh.  Default for the small arrays
-    // (M <= 16); DMK_KERNEL_MMA forces it on every eligible shape, DMK_KERNEL_SMALL keeps the CUDA-core fd_small2_kernel.
+    // Small per-user outputs (M <= 64, K % 16 == 0): warp-level tensor-core kernel, see dmk_fd_mma.cuh.  Default up to 64 KB per user,
+    // and for every eligible shape the persistent kernel did not take (FoV-filtered scenarios, fewer than 128 chunks per user);
+    // DMK_KERNEL_MMA forces it on every eligible shape, DMK_KERNEL_SMALL keeps the CUDA-core fd_small2_kernel.
     {
-        const bool mma_shape = affine && !d.has_time_axis && d.M <= 64 && (d.K % 16 == 0) && d.K <= 4096 &&
-                               ((reinterpret_cast<uintptr_t>(out_c64) & 15) == 0);
-        const bool mma_wanted = hint == DMK_KERNEL_MMA || (hint == DMK_KERNEL_AUTO && d.M <= 16);
+        const bool mma_wanted = hint == DMK_KERNEL_MMA || mma_pref || (hint == DMK_KERNEL_AUTO && (long long)d.M * d.K * 8 <= 128 * 1024);
         if (mma_shape && mma_wanted) {
             MmaCfg mc;
             memset(&mc, 0, sizeof(mc));
-            // chunk width J: L rows cost ~14 instructions each per path (R = M K / J of them), F columns ~20 (J of them)
-            int J = (d.K % 32 == 0 && (long long)d.M * d.K / 16 > 46) ? 32 : 16;
+            // chunk width J: L rows cost ~12 instructions each per path (M K / J of them) and share base phasors in blocks of 4 or 8
+            // per antenna row, F columns ~20 (J of them) and 2 KB of pool each; measured cross-over at 512 chunks of 16 per user
+            int J = (d.K % 128 == 0 && (long long)d.M * d.K / 16 >= 512) ? 32 : 16;
             if (desc->ws_helpers == 16 || (desc->ws_helpers == 32 && d.K % 32 == 0)) J = desc->ws_helpers;      // A/B timing
             const int nt = J / 4;
             mc.S = d.K / J;

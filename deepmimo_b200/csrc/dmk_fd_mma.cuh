@@ -31,7 +31,7 @@
 
 namespace dmk {
 
-constexpr int kMmWarps  = 4;
+constexpr int kMmWarps  = 3;                       // 12.4 KB of pool per warp: 6 CTAs = 18 warps per SM
 constexpr int kMmWindow = 4;                       // users examined per pass
 constexpr int kMmSlots  = 32;                      // pool slots (paths) per pass: one chain round
 
@@ -70,7 +70,7 @@ __device__ __forceinline__ int mm_a_off(int rowpair, int slot) { return rowpair 
 __device__ __forceinline__ int mm_b_off(int row, int slot)     { return row * 128 + ((slot * 4) ^ ((row & 3) << 5)); }
 
 template <int NT, int SB>      // n-tiles of 8 floats per chunk: J = 4 NT subcarriers; SB: chunks per base phasor (0: one phasor per chunk)
-__global__ void __launch_bounds__(kMmWarps * 32, 4)
+__global__ void __launch_bounds__(kMmWarps * 32, NT == 4 ? 6 : 4)
 fd_mma_kernel(const __grid_constant__ DevDesc d, const __grid_constant__ MmaCfg cfg)
 {
     constexpr int J = 4 * NT;
@@ -107,17 +107,22 @@ fd_mma_kernel(const __grid_constant__ DevDesc d, const __grid_constant__ MmaCfg 
     const int g = lane >> 2, t = lane & 3;
     const double kstep = (double)d.subc_step;
 
-    for (long long cur = u_begin; cur < u_end; ) {
-        // ---- 1. window (as fd_small2_kernel)
-        const int n_in = (int)min((long long)kMmWindow, u_end - cur);
-        const long long prow = cur * (long long)d.ld + lane;
-        float pw[kMmWindow];                                                   // only the NaN-ness of the power is used here
+    // power rows of the users [from, from + kMmWindow): loaded one pass ahead (right after a pass knows how many users it takes), so
+    // that their latency runs under the operand and MMA phases
+    float pw[kMmWindow];                                                       // only the NaN-ness of the power is used
+    auto load_window = [&](long long from) {
+        const long long prow = from * (long long)d.ld + lane;
         #pragma unroll
         for (int ul = 0; ul < kMmWindow; ++ul) {
             pw[ul] = __int_as_float(0x7fc00000);
-            if (ul < n_in && lane < P0)
+            if (from + ul < u_end && lane < P0)
                 pw[ul] = d.in_f64 ? (float)__ldg(reinterpret_cast<const double*>(d.power) + prow + ul * d.ld) : __ldg(d.power + prow + ul * d.ld);
         }
+    };
+    load_window(u_begin);
+    for (long long cur = u_begin; cur < u_end; ) {
+        // ---- 1. window (as fd_small2_kernel)
+        const int n_in = (int)min((long long)kMmWindow, u_end - cur);
         #pragma unroll
         for (int ul = 0; ul < kMmWindow; ++ul) {
             const bool in = ul < n_in && lane < P0;
@@ -152,6 +157,7 @@ fd_mma_kernel(const __grid_constant__ DevDesc d, const __grid_constant__ MmaCfg 
             ++n_take;
         }
         __syncwarp();
+        load_window(cur + n_take);
         if (lane < 7 * 4) {                                                     // rows of the users after this pass towards L2
             const int arr = lane >> 2;
             const long long u = cur + n_take + (lane & 3);
@@ -171,9 +177,17 @@ fd_mma_kernel(const __grid_constant__ DevDesc d, const __grid_constant__ MmaCfg 
         if (act) {
             const long long user = cur + ul;
             SideOut s0, s1; GainOut gn;
-            if (need_angles) { prologue_side<true>(d, user, col, 0, s0, d.Mt > 1);  prologue_side<true>(d, user, col, 1, s1, d.Mr > 1); }
-            else             { prologue_side<false>(d, user, col, 0, s0, d.Mt > 1); prologue_side<false>(d, user, col, 1, s1, d.Mr > 1); }
-            prologue_gain<true>(d, user, col, gn);
+            if (!d.in_f64) {                                                    // the seven entries of the pair in one batch of loads
+                PathIn in;
+                load_path_in(d, user, col, in);
+                if (need_angles) { prologue_side_in<true>(d, user, 0, in, s0, d.Mt > 1);  prologue_side_in<true>(d, user, 1, in, s1, d.Mr > 1); }
+                else             { prologue_side_in<false>(d, user, 0, in, s0, d.Mt > 1); prologue_side_in<false>(d, user, 1, in, s1, d.Mr > 1); }
+                prologue_gain_in<true>(d, col, in, gn);
+            } else {
+                if (need_angles) { prologue_side<true>(d, user, col, 0, s0, d.Mt > 1);  prologue_side<true>(d, user, col, 1, s1, d.Mr > 1); }
+                else             { prologue_side<false>(d, user, col, 0, s0, d.Mt > 1); prologue_side<false>(d, user, col, 1, s1, d.Mr > 1); }
+                prologue_gain<true>(d, user, col, gn);
+            }
             prologue_combine<true>(d, s0, s1, gn, st);
             const long long om = user * (long long)P0 + col;
             if (d.fov_mask)  d.fov_mask[om]  = st.fov ? 1 : 0;
@@ -194,21 +208,20 @@ fd_mma_kernel(const __grid_constant__ DevDesc d, const __grid_constant__ MmaCfg 
         //          s = 0: (Fr, -Fi)   s = 1: (Fi, Fr)   = rows (2p, 2p + 1) of B
         float2 wb[SB > 0 ? SB : 1];                                              // block phasors of the L rows
         if (contrib) {
-            float2 f1[4], f4[NT];
-            f1[0] = make_float2(1.f, 0.f); f4[0] = f1[0];
+            float2 f1[4];
+            f1[0] = make_float2(1.f, 0.f);
             #pragma unroll
             for (int i = 1; i < 4; ++i) f1[i] = phasor_cycles_sfu(-(st.wcyc * (kstep * (double)i)));
-            #pragma unroll
-            for (int b = 1; b < NT; ++b) f4[b] = phasor_cycles_sfu(-(st.wcyc * (kstep * (double)(4 * b))));
-            #pragma unroll
-            for (int b = 0; b < NT; ++b) {
+            #pragma unroll 1
+            for (int b = 0; b < NT; ++b) {                                       // rolled: the pass has to stay inside the instruction cache
+                const float2 f4b = phasor_cycles_sfu(-(st.wcyc * (kstep * (double)(4 * b))));      // b = 0: exactly (1, 0)
+                const int row_b = (2 * (b >> 1)) * 8 + 4 * (b & 1);               // j = 4 b + i: n-tile 2 (b >> 1) + (i & 1), column 2 (2 (b & 1) + (i >> 1)) + s
                 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                    const int j = 4 * b + i;
-                    const float2 f = (b == 0) ? f1[i] : (i == 0 ? f4[b] : cmul(f4[b], f1[i]));
+                    const float2 f = cmul(f4b, f1[i]);
                     unsigned x, y;                                               // (lo half = re, hi half = im)
                     split_f16x2(f.x, f.y, x, y);
-                    const int row = (2 * (j >> 3) + (j & 1)) * 8 + 2 * ((j >> 1) & 3);
+                    const int row = row_b + (i & 1) * 8 + 2 * (i >> 1);
                     *reinterpret_cast<unsigned*>(sBh + mm_b_off(row, slot))     = x ^ 0x80000000u;
                     *reinterpret_cast<unsigned*>(sBh + mm_b_off(row + 1, slot)) = __byte_perm(x, 0, 0x1032);
                     *reinterpret_cast<unsigned*>(sBl + mm_b_off(row, slot))     = y ^ 0x80000000u;
@@ -287,8 +300,10 @@ fd_mma_kernel(const __grid_constant__ DevDesc d, const __grid_constant__ MmaCfg 
                         const int aoff = mm_a_off(ml * 8 + g, sl);
                         uint4 ah = *reinterpret_cast<const uint4*>(sAh + aoff);       // chunks g, g + 8 of path 2t; of path 2t + 1
                         uint4 al = *reinterpret_cast<const uint4*>(sAl + aoff);
-                        if (k0 + 2 * t >= np)     { ah.x = 0u; ah.y = 0u; al.x = 0u; al.y = 0u; }
-                        if (k0 + 2 * t + 1 >= np) { ah.z = 0u; ah.w = 0u; al.z = 0u; al.w = 0u; }
+                        if (k0 + 8 > np) {                                           // the user's last, partial k-step (warp-uniform)
+                            if (k0 + 2 * t >= np)     { ah.x = 0u; ah.y = 0u; al.x = 0u; al.y = 0u; }
+                            if (k0 + 2 * t + 1 >= np) { ah.z = 0u; ah.w = 0u; al.z = 0u; al.w = 0u; }
+                        }
                         #pragma unroll
                         for (int n = 0; n < NT; ++n) {
                             const int boff = mm_b_off(n * 8 + g, sl);

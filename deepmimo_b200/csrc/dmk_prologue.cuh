@@ -114,11 +114,22 @@ __device__ __forceinline__ double dipole_gain(double th)
 struct SideOut { double th, ph, ss, cc, gain; };           // rotated angles, sin(th)sin(ph), cos(th), element power gain
 struct GainOut { float p_lin, ec, es; double p_lin64, ec64, es64; double wcyc, fd; unsigned char valid, over; };   // *64: float64 inputs
 
-template <bool kNeedAngles>
-__device__ __forceinline__ void prologue_side(const DevDesc& d, long long user, int p, int side, SideOut& o, bool steer = true)
+// The float32 entries of one (user, path column), loaded in one batch so that a kernel exposes a single memory latency per path
+// instead of one per chain (the compiler does not hoist the loads out of the chains' branches).
+struct PathIn { float power, phase, delay, az[2], el[2], doppler; };
+
+__device__ __forceinline__ void load_path_in(const DevDesc& d, long long user, int p, PathIn& in)
 {
     const long long off = user * (long long)d.ld + p;
-    double sx = d.sx[side], cx = d.cx[side], sy = d.sy[side], cy = d.cy[side], rz = d.rz[side];
+    in.power = __ldg(d.power + off); in.phase = __ldg(d.phase + off); in.delay = __ldg(d.delay + off);
+    in.az[0] = __ldg(d.az[0] + off); in.el[0] = __ldg(d.el[0] + off);
+    in.az[1] = __ldg(d.az[1] + off); in.el[1] = __ldg(d.el[1] + off);
+    in.doppler = d.doppler ? __ldg(d.doppler + off) : 0.0f;
+}
+
+__device__ __forceinline__ void side_rotation(const DevDesc& d, long long user, int side, double& sx, double& cx, double& sy, double& cy, double& rz)
+{
+    sx = d.sx[side]; cx = d.cx[side]; sy = d.sy[side]; cy = d.cy[side]; rz = d.rz[side];
     if (side == 1 && d.ue_rot) {                            // per-user UE rotation (dataset.py:328-338)
         const double k = kPi / 180.0;                       // np.deg2rad float64: x * (pi/180)
         const double* r = d.ue_rot + user * 3;
@@ -126,6 +137,24 @@ __device__ __forceinline__ void prologue_side(const DevDesc& d, long long user, 
         dsincos_bf(__dmul_rn(r[1], k), sy, cy);
         rz = __dmul_rn(r[2], k);
     }
+}
+
+// float32 inputs, values already loaded
+template <bool kNeedAngles>
+__device__ __forceinline__ void prologue_side_in(const DevDesc& d, long long user, int side, const PathIn& in, SideOut& o, bool steer = true)
+{
+    double sx, cx, sy, cy, rz;
+    side_rotation(d, user, side, sx, cx, sy, cy, rz);
+    rotate_side<kNeedAngles>(in.el[side], in.az[side], sx, cx, sy, cy, rz, o.th, o.ph, o.ss, o.cc, steer);
+    o.gain = 1.0;
+}
+
+template <bool kNeedAngles>
+__device__ __forceinline__ void prologue_side(const DevDesc& d, long long user, int p, int side, SideOut& o, bool steer = true)
+{
+    const long long off = user * (long long)d.ld + p;
+    double sx, cx, sy, cy, rz;
+    side_rotation(d, user, side, sx, cx, sy, cy, rz);
     if (d.in_f64)
         rotate_side_f64<kNeedAngles>(reinterpret_cast<const double*>(d.el[side])[off], reinterpret_cast<const double*>(d.az[side])[off],
                                      sx, cx, sy, cy, rz, o.th, o.ph, o.ss, o.cc, steer);
@@ -134,12 +163,41 @@ __device__ __forceinline__ void prologue_side(const DevDesc& d, long long user, 
     o.gain = 1.0;
 }
 
+// float32 inputs: the gain chain from loaded values
+template <bool kFreqDomain>
+__device__ __forceinline__ void prologue_gain_f32(const DevDesc& d, int p, float pw_db, float phase_deg, float delay_s, float doppler, GainOut& g)
+{
+    g.fd = (double)doppler;
+    g.valid = (p < d.P) && !(pw_db != pw_db);               // channel.py:260, dataset.py:258-261
+    // generator_utils.py:35: float32 divide by 10, float32 pow.  The reference's value is itself a float32 libm/SVML result
+    // (R7: within 1 ulp of correctly rounded); exp10f is within 2 ulp, i.e. <= 1.2e-7 on the amplitude.
+    g.p_lin = exp10f(__fdiv_rn(pw_db, 10.0f));
+    const float d2r = 0x1.1df46ap-6f;
+    const float ph32 = __fmul_rn(phase_deg, d2r);           // np.deg2rad(phase) float32
+    // complex64 exp(1j*x) = (cosf(x), sinf(x)) in the reference (R10, <= 1 ulp); sincosf here is within 2 ulp for |x| <= pi
+    sincosf(ph32, &g.es, &g.ec);
+    g.over = 0; g.wcyc = 0.0;
+    if (kFreqDomain) {
+        float dn = __fdiv_rn(delay_s, d.ts_f32);            // channel.py:183 (R11)
+        g.over = dn >= d.n_f32;                             // :187 (R12)
+        if (g.over) dn = d.n_f32;                           // :189
+        g.wcyc = (double)dn * d.inv_n;
+    }
+    g.p_lin64 = (double)g.p_lin; g.ec64 = (double)g.ec; g.es64 = (double)g.es;
+}
+
+template <bool kFreqDomain>
+__device__ __forceinline__ void prologue_gain_in(const DevDesc& d, int p, const PathIn& in, GainOut& g)
+{
+    prologue_gain_f32<kFreqDomain>(d, p, in.power, in.phase, in.delay, in.doppler, g);
+}
+
 template <bool kFreqDomain>
 __device__ __forceinline__ void prologue_gain(const DevDesc& d, long long user, int p, GainOut& g)
 {
     const long long off = user * (long long)d.ld + p;
-    g.fd = d.doppler ? (double)d.doppler[off] : 0.0;
     if (d.in_f64) {
+        g.fd = d.doppler ? (double)d.doppler[off] : 0.0;
         // float64 path matrices: the whole gain chain is float64 in NumPy (generator_utils.py:35, channel.py:183-192)
         const double pw_db = reinterpret_cast<const double*>(d.power)[off];
         g.valid = (p < d.P) && !(pw_db != pw_db);
@@ -156,23 +214,7 @@ __device__ __forceinline__ void prologue_gain(const DevDesc& d, long long user, 
         }
         return;
     }
-    const float pw_db = d.power[off];
-    g.valid = (p < d.P) && !(pw_db != pw_db);               // channel.py:260, dataset.py:258-261
-    // generator_utils.py:35: float32 divide by 10, float32 pow.  The reference's value is itself a float32 libm/SVML result
-    // (R7: within 1 ulp of correctly rounded); exp10f is within 2 ulp, i.e. <= 1.2e-7 on the amplitude.
-    g.p_lin = exp10f(__fdiv_rn(pw_db, 10.0f));
-    const float d2r = 0x1.1df46ap-6f;
-    const float ph32 = __fmul_rn(d.phase[off], d2r);        // np.deg2rad(phase) float32
-    // complex64 exp(1j*x) = (cosf(x), sinf(x)) in the reference (R10, <= 1 ulp); sincosf here is within 2 ulp for |x| <= pi
-    sincosf(ph32, &g.es, &g.ec);
-    g.over = 0; g.wcyc = 0.0;
-    if (kFreqDomain) {
-        float dn = __fdiv_rn(d.delay[off], d.ts_f32);       // channel.py:183 (R11)
-        g.over = dn >= d.n_f32;                             // :187 (R12)
-        if (g.over) dn = d.n_f32;                           // :189
-        g.wcyc = (double)dn * d.inv_n;
-    }
-    g.p_lin64 = (double)g.p_lin; g.ec64 = (double)g.ec; g.es64 = (double)g.es;
+    prologue_gain_f32<kFreqDomain>(d, p, d.power[off], d.phase[off], d.delay[off], d.doppler ? d.doppler[off] : 0.0f, g);
 }
 
 template <bool kFreqDomain>

@@ -212,7 +212,7 @@ def test_fd_kernel_variants_agree_with_oracle(cfg, n, monkeypatch):
     s = scenario(cfg, n)
     o = orc.compute_channels(s.data, **oracle_kwargs_from_params(s.params, s.bs_fov, s.ue_fov))
     seen = set()
-    for variant in ("tc", "tc1", "ffma", "tile", "small1", "auto"):
+    for variant in ("tc", "tc1", "ffma", "tile", "small1", "small", "mma", "auto"):
         if variant == "auto":
             monkeypatch.delenv("DMK_FD_KERNEL")
         else:
@@ -227,7 +227,8 @@ def test_fd_kernel_variants_agree_with_oracle(cfg, n, monkeypatch):
     if cfg == 2:
         assert "fd_ws_kernel" in seen                # the persistent warp-specialised kernel takes this shape
     if cfg == 1:
-        assert {"fd_small2_kernel", "fd_small_kernel"} <= seen      # small arrays default to the densely packed warp kernel
+        assert {"fd_mma_kernel", "fd_small2_kernel", "fd_small_kernel"} <= seen      # small outputs default to the warp-level tensor-core kernel
+        assert info.kernel.startswith("fd_mma_kernel"), info.kernel
 
 
 def test_per_user_byproducts_match_reference_definitions():

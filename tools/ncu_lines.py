@@ -17,6 +17,10 @@ for r in csv.reader(io.StringIO(txt)):
     if r[iA].startswith("0x"):
         sass.append((int(r[iA], 16), r[iS].strip(), int(r[iI] or 0), int(r[iSm] or 0), cur_file, cur_line))
 sass.sort()
+seen = {}
+for rec in sass:                      # an instruction can be listed under several lines of its inline stack: keep the main file's
+    if rec[0] not in seen or (rec[4] == main_file and seen[rec[0]][4] != main_file): seen[rec[0]] = rec
+sass = [seen[a] for a in sorted(seen)]
 tot_i = sum(s[2] for s in sass); tot_s = sum(s[3] for s in sass)
 agg = collections.OrderedDict(); label = 0
 for a, ins, n, smp, f, l in sass:
