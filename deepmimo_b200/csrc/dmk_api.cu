@@ -282,11 +282,11 @@ int dmk_channels_fd(const dmk_desc* desc, const float* power_dbw, const float* p
     // FoV-sparse scenarios leave few paths per user (per-user overhead dominates): packed-FP32 kernel.  Measured: profiles/README.md.
     const long long n_chunks_u = (long long)d.M * (d.K / (kTcN / 2));
     const bool tc_shape = (d.M >= 64 || n_chunks_u >= 128) && !d.fov_any;
-    // Per-user outputs of at most 64 KB go to the warp-level tensor-core kernel (dmk_fd_mma.cuh) instead: the persistent kernel is
-    // bound by its helper warps there (8x8 x K=64: 1.4 against 3.4 TB/s; profiles/README.md).
+    // Per-user outputs of at most 128 KB go to the warp-level tensor-core kernel (dmk_fd_mma.cuh) instead: the persistent kernel is
+    // bound by its helper warps there (8x8 x K=64: 1.4 against 3.5 TB/s, 16x1 x K=1024: 3.46 against 3.61; profiles/README.md).
     const bool mma_shape = affine && !d.has_time_axis && d.M <= 64 && (d.K % 16 == 0) && d.K <= 4096 &&
                            ((reinterpret_cast<uintptr_t>(out_c64) & 15) == 0);
-    const bool mma_pref = mma_shape && hint == DMK_KERNEL_AUTO && (long long)d.M * d.K * 8 <= 64 * 1024;
+    const bool mma_pref = mma_shape && hint == DMK_KERNEL_AUTO && (long long)d.M * d.K * 8 <= 128 * 1024;
     const bool use_tc = !mma_pref && affine && !d.has_time_axis && div_ok && (d.K % (kTcN / 2) == 0) && d.K <= 4096 &&
                         !want_tile && !want_ffma && hint != DMK_KERNEL_SMALL && hint != DMK_KERNEL_SMALL1 && hint != DMK_KERNEL_MMA && (tc_shape || want_tc);
     const bool use_tc1 = use_tc && tc_smem <= (size_t)kSmemTc;            // one-CTA-per-user tensor-core kernel: fallback of the persistent one
@@ -385,17 +385,17 @@ int dmk_channels_fd(const dmk_desc* desc, const float* power_dbw, const float* p
             return DMK_OK;
         }
     }
-    // Small per-user outputs (M <= 64, K % 16 == 0): warp-level tensor-core kernel, see dmk_fd_mma.cuh.  Default up to 64 KB per user,
+    // Small per-user outputs (M <= 64, K % 16 == 0): warp-level tensor-core kernel, see dmk_fd_mma.cuh.  Default up to 128 KB per user,
     // and for every eligible shape the persistent kernel did not take (FoV-filtered scenarios, fewer than 128 chunks per user);
     // DMK_KERNEL_MMA forces it on every eligible shape, DMK_KERNEL_SMALL keeps the CUDA-core fd_small2_kernel.
     {
-        const bool mma_wanted = hint == DMK_KERNEL_MMA || mma_pref || (hint == DMK_KERNEL_AUTO && (long long)d.M * d.K * 8 <= 128 * 1024);
+        const bool mma_wanted = hint == DMK_KERNEL_MMA || mma_pref || (hint == DMK_KERNEL_AUTO && (long long)d.M * d.K * 8 <= 256 * 1024);
         if (mma_shape && mma_wanted) {
             MmaCfg mc;
             memset(&mc, 0, sizeof(mc));
-            // chunk width J: L rows cost ~12 instructions each per path (M K / J of them) and share base phasors in blocks of 4 or 8
-            // per antenna row, F columns ~20 (J of them) and 2 KB of pool each; measured cross-over at 512 chunks of 16 per user
-            int J = (d.K % 128 == 0 && (long long)d.M * d.K / 16 >= 512) ? 32 : 16;
+            // chunk width J = 32 where the chunks of an antenna row still share base phasors in blocks of >= 4 (K / 32 a multiple of 4)
+            // and a user has >= 256 chunks of 16; else 16 (measured: tools/mma_sweep.py, profiles/README.md)
+            int J = (d.K % 128 == 0 && (long long)d.M * d.K / 16 >= 256) ? 32 : 16;
             if (desc->ws_helpers == 16 || (desc->ws_helpers == 32 && d.K % 32 == 0)) J = desc->ws_helpers;      // A/B timing
             const int nt = J / 4;
             mc.S = d.K / J;
@@ -403,12 +403,12 @@ int dmk_channels_fd(const dmk_desc* desc, const float* power_dbw, const float* p
             mc.n_mt = (mc.R + 15) / 16;
             mc.mul_s = mc.S > 1 ? (unsigned)((0x100000000ULL + mc.S - 1) / mc.S) : 0u;
             const int sb = mc.S % 8 == 0 ? 8 : (mc.S % 4 == 0 ? 4 : 0);      // chunks of one antenna row that share a base phasor
-            mc.G = mc.n_mt < 2 ? mc.n_mt : (nt == 4 ? 1 : 2);
+            mc.G = mc.n_mt < 2 ? mc.n_mt : 2;                        // two m-tiles per group: measured best for both chunk widths
             if (desc->ws_split > 0) mc.G = desc->ws_split < mc.n_mt ? desc->ws_split : mc.n_mt;
             size_t off = 0;
             auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 15) & ~size_t(15); return (int)o; };
             mc.off_A    = take((size_t)2 * mc.G * 8 * 256);
-            mc.off_B    = take((size_t)2 * nt * 8 * 128);
+            mc.off_B    = take((size_t)2 * (nt / 2) * 8 * 128);
             mc.off_list = take((size_t)32);
             mc.off_meta = take((size_t)(5 * kMmWindow + 1) * sizeof(int));
             mc.warp_bytes = (int)off;

@@ -8,8 +8,10 @@
 //
 //   a user's output is a flat array of R = M * K / J chunks of J subcarriers (J = 16 or 32; chunk r = m * S + seg, S = K / J);
 //   H[chunk r, j] = sum_p L[r, p] * F[p, j],   L[r, p] = c_p * a[m, p] * exp(-j 2 pi wcyc_p k0(seg)),   F[p, j] = exp(-j 2 pi wcyc_p step j)
-//   real form:  D[r, 2 j + s] = sum_{p, e} A[r, 2 p + e] * B[2 p + e, 2 j + s],   A = (Lr, Li),   B = ((Fr, Fi), (-Fi, Fr))
-//   -> MMA rows = chunks, MMA columns = the floats inside a chunk (so an accumulator fragment is a contiguous piece of the output),
+//   real form:  Re H[r, j] = sum_p Lr Fr + Li (-Fi),   Im H[r, j] = sum_p Lr Fi + Li Fr:   A = (Lr, Li) per (chunk, path); an n-tile is
+//   8 columns j of a chunk, once with B = (Fr, -Fi) (real parts) and once with B = (Fi, Fr) (imaginary parts) -- the second is the
+//   first with its halves swapped and one sign flipped, formed in registers, so the pool holds every F once
+//   -> MMA rows = chunks, the two accumulators of a column group interleave to a contiguous piece of the output,
 //      MMA k = (path, re/im): 8 paths per k-step.
 //
 // Phases of a pass (one warp, no CTA-wide synchronisation; 1-3 are those of fd_small2_kernel):
@@ -31,7 +33,7 @@
 
 namespace dmk {
 
-constexpr int kMmWarps  = 3;                       // 12.4 KB of pool per warp: 6 CTAs = 18 warps per SM
+constexpr int kMmWarps  = 3;                       // 8.4 KB of pool per warp (J = 16): 7 CTAs = 21 warps per SM at 96 registers
 constexpr int kMmWindow = 4;                       // users examined per pass
 constexpr int kMmSlots  = 32;                      // pool slots (paths) per pass: one chain round
 
@@ -64,13 +66,15 @@ __device__ __forceinline__ void split_f16x2(float x, float y, unsigned& hi, unsi
 }
 
 // Pool layout of a warp (bytes).  A side (L): [hi | lo][G * 8 row pairs (m-tile, g)][32 slots] 8 B = chunks g and g + 8 of the slot's
-// path, row = 256 B, 16-byte unit index XOR-ed with (g & 1) << 2.  B side (F): [hi | lo][NT n-tiles][8 fragment columns g][32 slots]
-// 4 B, row = 128 B, byte offset XOR-ed with (g & 3) << 5.
+// path, row = 256 B, 16-byte unit index XOR-ed with (g & 1) << 2.  B side (F): [hi | lo][NT / 2 column groups][8 columns][32 slots]
+// 4 B = (Fr, -Fi) of the slot's path, row = 128 B, byte offset XOR-ed with (column & 3) << 5.
 __device__ __forceinline__ int mm_a_off(int rowpair, int slot) { return rowpair * 256 + ((slot * 8) ^ ((rowpair & 1) << 6)); }
 __device__ __forceinline__ int mm_b_off(int row, int slot)     { return row * 128 + ((slot * 4) ^ ((row & 3) << 5)); }
 
 template <int NT, int SB>      // n-tiles of 8 floats per chunk: J = 4 NT subcarriers; SB: chunks per base phasor (0: one phasor per chunk)
-__global__ void __launch_bounds__(kMmWarps * 32, NT == 4 ? 6 : 4)
+// 96 registers: 7 CTAs = 21 warps per SM with the 8.4 KB pools of J = 16 (a minimum-blocks launch bound makes ptxas stop at 80 and
+// spill: measured 13 % slower); J = 32 is limited by its pools, not by registers.
+__global__ void __maxnreg__(NT == 4 ? 96 : 168)
 fd_mma_kernel(const __grid_constant__ DevDesc d, const __grid_constant__ MmaCfg cfg)
 {
     constexpr int J = 4 * NT;
@@ -89,7 +93,7 @@ fd_mma_kernel(const __grid_constant__ DevDesc d, const __grid_constant__ MmaCfg 
     unsigned char* sAh  = wsm + cfg.off_A;                                     // A side, hi halves; lo halves follow
     unsigned char* sAl  = sAh + cfg.G * 8 * 256;
     unsigned char* sBh  = wsm + cfg.off_B;                                     // B side, hi halves; lo halves follow
-    unsigned char* sBl  = sBh + NT * 8 * 128;
+    unsigned char* sBl  = sBh + (NT / 2) * 8 * 128;
     unsigned char* list = wsm + cfg.off_list;                                  // [32] (user in window << 5) | column
     int* s_base         = reinterpret_cast<int*>(wsm + cfg.off_meta);          // [kMmWindow + 1] first pool slot of the user (even)
     int* s_cnt          = s_base + kMmWindow + 1;                              // [kMmWindow] contributing paths
@@ -104,6 +108,7 @@ fd_mma_kernel(const __grid_constant__ DevDesc d, const __grid_constant__ MmaCfg 
     const unsigned ltmask = (1u << lane) - 1u;
     const int K = d.K, M = d.M, P0 = d.P0;
     const bool need_angles = prologue_needs_angles(d);
+    const bool triv0 = side_angles_trivial(d, 0), triv1 = side_angles_trivial(d, 1);
     const int g = lane >> 2, t = lane & 3;
     const double kstep = (double)d.subc_step;
 
@@ -132,8 +137,9 @@ fd_mma_kernel(const __grid_constant__ DevDesc d, const __grid_constant__ MmaCfg 
             if (lane == ul) { s_valid[ul] = vb; s_need[ul] = nb; }
         }
         __syncwarp();
-        // ---- 2. whole users while their pairs fit one round of lanes and the pool (a user's first slot is even: a lane loads
-        //         the operands of its two paths of a k-step with one aligned access)
+        // ---- 2. whole users, in order, while their pairs fit one round of lanes and the pool (a user's first slot is even: a lane
+        //         loads the operands of its two paths of a k-step with one aligned access).  Measured and left out: first fit over a
+        //         window of 8 pending users fills 27 instead of 23 lanes but costs more in the window than it saves in the chains.
         int cum = 0, slots = 0, n_take = 0;
         long long o = cur * (long long)P0 + lane;
         #pragma unroll 1
@@ -157,10 +163,11 @@ fd_mma_kernel(const __grid_constant__ DevDesc d, const __grid_constant__ MmaCfg 
             ++n_take;
         }
         __syncwarp();
-        load_window(cur + n_take);
+        const long long next_cur = cur + n_take;
+        load_window(next_cur);
         if (lane < 7 * 4) {                                                     // rows of the users after this pass towards L2
             const int arr = lane >> 2;
-            const long long u = cur + n_take + (lane & 3);
+            const long long u = next_cur + (lane & 3);
             if (u < u_end) {
                 const float* base = (arr == 0) ? d.power : (arr == 1) ? d.phase : (arr == 2) ? d.delay : (arr == 3) ? d.az[0] : (arr == 4) ? d.el[0]
                                   : (arr == 5) ? d.az[1] : d.el[1];
@@ -181,7 +188,10 @@ fd_mma_kernel(const __grid_constant__ DevDesc d, const __grid_constant__ MmaCfg 
                 PathIn in;
                 load_path_in(d, user, col, in);
                 if (need_angles) { prologue_side_in<true>(d, user, 0, in, s0, d.Mt > 1);  prologue_side_in<true>(d, user, 1, in, s1, d.Mr > 1); }
-                else             { prologue_side_in<false>(d, user, 0, in, s0, d.Mt > 1); prologue_side_in<false>(d, user, 1, in, s1, d.Mr > 1); }
+                else {
+                    if (triv0) prologue_side_trivial(in.el[0], in.az[0], s0); else prologue_side_in<false>(d, user, 0, in, s0, d.Mt > 1);
+                    if (triv1) prologue_side_trivial(in.el[1], in.az[1], s1); else prologue_side_in<false>(d, user, 1, in, s1, d.Mr > 1);
+                }
                 prologue_gain_in<true>(d, col, in, gn);
             } else {
                 if (need_angles) { prologue_side<true>(d, user, col, 0, s0, d.Mt > 1);  prologue_side<true>(d, user, col, 1, s1, d.Mr > 1); }
@@ -204,8 +214,7 @@ fd_mma_kernel(const __grid_constant__ DevDesc d, const __grid_constant__ MmaCfg 
         const int slot = act ? s_base[ul] + __popc(bc & same & ltmask) : 0;      // contributing paths of a user, in column order
         if (act && lane == __ffs(same) - 1) { s_cnt[ul] = __popc(bc & same); s_scale[ul] = __uint_as_float((ef + 1u) << 23); }
         const float2 cs = make_float2(st.c.x * sc_dn, st.c.y * sc_dn);
-        // ---- 4a. F: column j = 4 b + i of a chunk -> f4[b] * f1[i]; n-tile 2 (j >> 3) + (j & 1), fragment columns 2 ((j >> 1) & 3) + s
-        //          s = 0: (Fr, -Fi)   s = 1: (Fi, Fr)   = rows (2p, 2p + 1) of B
+        // ---- 4a. F: column j = 4 b + i of a chunk -> f4[b] * f1[i], stored once as (Fr, -Fi) = rows (2p, 2p + 1) of B for the real parts
         float2 wb[SB > 0 ? SB : 1];                                              // block phasors of the L rows
         if (contrib) {
             float2 f1[4];
@@ -215,17 +224,14 @@ fd_mma_kernel(const __grid_constant__ DevDesc d, const __grid_constant__ MmaCfg 
             #pragma unroll 1
             for (int b = 0; b < NT; ++b) {                                       // rolled: the pass has to stay inside the instruction cache
                 const float2 f4b = phasor_cycles_sfu(-(st.wcyc * (kstep * (double)(4 * b))));      // b = 0: exactly (1, 0)
-                const int row_b = (2 * (b >> 1)) * 8 + 4 * (b & 1);               // j = 4 b + i: n-tile 2 (b >> 1) + (i & 1), column 2 (2 (b & 1) + (i >> 1)) + s
+                const int row_b = (b >> 1) * 8 + 4 * (b & 1);                       // j = 4 b + i: column group j >> 3, column j & 7
                 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     const float2 f = cmul(f4b, f1[i]);
-                    unsigned x, y;                                               // (lo half = re, hi half = im)
-                    split_f16x2(f.x, f.y, x, y);
-                    const int row = row_b + (i & 1) * 8 + 2 * (i >> 1);
-                    *reinterpret_cast<unsigned*>(sBh + mm_b_off(row, slot))     = x ^ 0x80000000u;
-                    *reinterpret_cast<unsigned*>(sBh + mm_b_off(row + 1, slot)) = __byte_perm(x, 0, 0x1032);
-                    *reinterpret_cast<unsigned*>(sBl + mm_b_off(row, slot))     = y ^ 0x80000000u;
-                    *reinterpret_cast<unsigned*>(sBl + mm_b_off(row + 1, slot)) = __byte_perm(y, 0, 0x1032);
+                    unsigned x, y;                                               // (lo half = Fr, hi half = -Fi): rows (2p, 2p + 1) of B for the real parts
+                    split_f16x2(f.x, -f.y, x, y);
+                    *reinterpret_cast<unsigned*>(sBh + mm_b_off(row_b + i, slot)) = x;
+                    *reinterpret_cast<unsigned*>(sBl + mm_b_off(row_b + i, slot)) = y;
                 }
             }
             if constexpr (SB > 0) {
@@ -234,6 +240,7 @@ fd_mma_kernel(const __grid_constant__ DevDesc d, const __grid_constant__ MmaCfg 
                 for (int i = 1; i < SB; ++i) wb[i] = phasor_cycles_sfu(-(st.wcyc * (kstep * (double)(J * i))));
             }
         }
+        float2* out_pass = d.out + cur * (long long)M * K;
         #pragma unroll 1
         for (int mt0 = 0; mt0 < cfg.n_mt; mt0 += cfg.G) {
             const int n_g = min(cfg.G, cfg.n_mt - mt0);
@@ -283,55 +290,65 @@ fd_mma_kernel(const __grid_constant__ DevDesc d, const __grid_constant__ MmaCfg 
             __syncwarp();
             // ---- 5. per user and m-tile: fragments, MMAs, stores.  k-step = 8 pool slots; this lane's paths are slots 2t, 2t + 1
             //         (MMA k indices (2t, 2t + 1) = (re, im) of the first, (2t + 8, 2t + 9) of the second).
+            const unsigned a_sw = (unsigned)(g & 1) << 6, b_sw = (unsigned)(g & 3) << 5;        // swizzles of this lane's fragment rows
+            const unsigned char* bh_row = sBh + g * 128;
+            const unsigned char* bl_row = sBl + g * 128;
             #pragma unroll 1
             for (int uu = 0; uu < n_take; ++uu) {
                 const int np = s_cnt[uu];
                 const float sc_up = s_scale[uu];
-                float2* out_u = d.out + (cur + uu) * (long long)M * K;
+                float2* out_u = out_pass + (size_t)uu * (size_t)(M * K) + 2 * t;
                 const int qb = s_base[uu] + 2 * t;
                 #pragma unroll 1
                 for (int ml = 0; ml < n_g; ++ml) {
                     float acc[NT][4];
                     #pragma unroll
                     for (int n = 0; n < NT; ++n) { acc[n][0] = 0.f; acc[n][1] = 0.f; acc[n][2] = 0.f; acc[n][3] = 0.f; }
+                    const unsigned char* ah_row = sAh + (ml * 8 + g) * 256;
+                    const unsigned char* al_row = sAl + (ml * 8 + g) * 256;
                     #pragma unroll 1
                     for (int k0 = 0; k0 < np; k0 += 8) {
-                        const int sl = min(qb + k0, kMmSlots - 2);                   // past the row's end only when both paths are >= np (zeroed below)
-                        const int aoff = mm_a_off(ml * 8 + g, sl);
-                        uint4 ah = *reinterpret_cast<const uint4*>(sAh + aoff);       // chunks g, g + 8 of path 2t; of path 2t + 1
-                        uint4 al = *reinterpret_cast<const uint4*>(sAl + aoff);
+                        const unsigned sl = (unsigned)min(qb + k0, kMmSlots - 2);       // past the row's end only when both paths are >= np (zeroed below)
+                        const unsigned ao = (sl * 8u) ^ a_sw, bo = (sl * 4u) ^ b_sw;
+                        uint4 ah = *reinterpret_cast<const uint4*>(ah_row + ao);        // chunks g, g + 8 of path 2t; of path 2t + 1
+                        uint4 al = *reinterpret_cast<const uint4*>(al_row + ao);
                         if (k0 + 8 > np) {                                           // the user's last, partial k-step (warp-uniform)
                             if (k0 + 2 * t >= np)     { ah.x = 0u; ah.y = 0u; al.x = 0u; al.y = 0u; }
                             if (k0 + 2 * t + 1 >= np) { ah.z = 0u; ah.w = 0u; al.z = 0u; al.w = 0u; }
                         }
+                        uint2 bh[NT], bl[NT];                                        // [2 q]: (Fr, -Fi) of column group q, [2 q + 1]: (Fi, Fr)
                         #pragma unroll
-                        for (int n = 0; n < NT; ++n) {
-                            const int boff = mm_b_off(n * 8 + g, sl);
-                            const uint2 bh = *reinterpret_cast<const uint2*>(sBh + boff);
-                            const uint2 bl = *reinterpret_cast<const uint2*>(sBl + boff);
-                            mma_m16n8k16_f16(acc[n], ah, bh);
-                            mma_m16n8k16_f16(acc[n], al, bh);
-                            mma_m16n8k16_f16(acc[n], ah, bl);
+                        for (int q = 0; q < NT / 2; ++q) {
+                            bh[2 * q] = *reinterpret_cast<const uint2*>(bh_row + q * 1024 + bo);
+                            bl[2 * q] = *reinterpret_cast<const uint2*>(bl_row + q * 1024 + bo);
+                            bh[2 * q + 1] = make_uint2(__byte_perm(bh[2 * q].x, 0, 0x1032) ^ 0x8000u, __byte_perm(bh[2 * q].y, 0, 0x1032) ^ 0x8000u);
+                            bl[2 * q + 1] = make_uint2(__byte_perm(bl[2 * q].x, 0, 0x1032) ^ 0x8000u, __byte_perm(bl[2 * q].y, 0, 0x1032) ^ 0x8000u);
                         }
+                        #pragma unroll
+                        for (int n = 0; n < NT; ++n) mma_m16n8k16_f16(acc[n], ah, bh[n]);       // NT independent accumulators between
+                        #pragma unroll
+                        for (int n = 0; n < NT; ++n) mma_m16n8k16_f16(acc[n], al, bh[n]);       // two MMAs into the same one
+                        #pragma unroll
+                        for (int n = 0; n < NT; ++n) mma_m16n8k16_f16(acc[n], ah, bl[n]);
                     }
-                    // chunk r = 16 mt + g (+ 8): J complex values at r * J; this lane holds columns 8 pair + 2 t, + 1 of both chunks
+                    // chunk r = 16 mt + g (+ 8): J complex values at r * J; this lane holds columns 8 q + 2 t, + 1 of both chunks
                     const int r0 = (mt0 + ml) * 16 + g;
                     #pragma unroll
                     for (int h = 0; h < 2; ++h) {
                         const int r = r0 + 8 * h;
                         if (r < cfg.R) {
-                            float4* o4 = reinterpret_cast<float4*>(out_u + (long long)r * J + 2 * t);
+                            float4* o4 = reinterpret_cast<float4*>(out_u + (size_t)r * J);
                             #pragma unroll
-                            for (int np2 = 0; np2 < NT / 2; ++np2)
-                                __stcs(o4 + np2 * 4, make_float4(acc[2 * np2][2 * h] * sc_up, acc[2 * np2][2 * h + 1] * sc_up,
-                                                                 acc[2 * np2 + 1][2 * h] * sc_up, acc[2 * np2 + 1][2 * h + 1] * sc_up));
+                            for (int q = 0; q < NT / 2; ++q)                        // columns 8 q + 2 t, + 1: (re, im, re, im)
+                                __stcs(o4 + q * 4, make_float4(acc[2 * q][2 * h] * sc_up, acc[2 * q + 1][2 * h] * sc_up,
+                                                               acc[2 * q][2 * h + 1] * sc_up, acc[2 * q + 1][2 * h + 1] * sc_up));
                         }
                     }
                 }
             }
             __syncwarp();                                                       // the L rows are rewritten by the next group / pass
         }
-        cur += n_take;
+        cur = next_cur;
     }
 }
 

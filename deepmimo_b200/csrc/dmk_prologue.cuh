@@ -139,6 +139,25 @@ __device__ __forceinline__ void side_rotation(const DevDesc& d, long long user, 
     }
 }
 
+// A side whose rotated angles enter the result only through their NaN-ness: a single element (no steering), no FoV filter, no
+// element pattern, and the identity rotation about x and y (the reference's default UE: shape [1, 1], rotation [0, 0, 0]).  Then
+// geometry.py:305-310 reduce to x = cos(theta) EXACTLY (cy cx = 1, the other products are exact zeros) and re, im = st cd, st sd,
+// so theta', phi' are NaN exactly when an input angle is not finite: NumPy's float32 cos stays inside [-1, 1] for every finite
+// float32 (checked exhaustively, tests/test_np_trig_emul.py::test_float32_sin_cos_stay_inside_unit_interval).  The rotation about
+// z only shifts phi.  Saves the whole float64 chain of that side.
+__device__ __forceinline__ bool side_angles_trivial(const DevDesc& d, int side)
+{
+    const int m = side == 0 ? d.Mt : d.Mr;
+    return m == 1 && !d.fov_any && d.pat[0] == DMK_PATTERN_ISOTROPIC && d.pat[1] == DMK_PATTERN_ISOTROPIC && !(side == 1 && d.ue_rot) &&
+           d.sx[side] == 0.0 && d.cx[side] == 1.0 && d.sy[side] == 0.0 && d.cy[side] == 1.0 && !d.in_f64;
+}
+
+__device__ __forceinline__ void prologue_side_trivial(float el_deg, float az_deg, SideOut& o)
+{
+    const float z = (el_deg - el_deg) + (az_deg - az_deg);           // 0 for finite angles, NaN otherwise
+    o.th = (double)z; o.ph = (double)z; o.ss = 0.0; o.cc = 0.0; o.gain = 1.0;
+}
+
 // float32 inputs, values already loaded
 template <bool kNeedAngles>
 __device__ __forceinline__ void prologue_side_in(const DevDesc& d, long long user, int side, const PathIn& in, SideOut& o, bool steer = true)

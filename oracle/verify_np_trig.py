@@ -35,7 +35,24 @@ def mismatches(lib, bits):
     return bs, bc
 
 
+def unit_interval():
+    """|np.sin(x)|, |np.cos(x)| <= 1 for EVERY finite float32 (all 2^32 bit patterns; ~3 min).  dmk_prologue.cuh:
+    side_angles_trivial relies on it.  Result with NumPy 2.3.5: maxima 1.0 and 1.0, no violation."""
+    t0 = time.time(); worst_c = worst_s = 0.0; bad = 0
+    for b0 in range(0, 1 << 32, 1 << 26):
+        x = np.arange(b0, b0 + (1 << 26), dtype=np.uint64).astype(np.uint32).view(np.float32)
+        fin = np.isfinite(x)
+        with np.errstate(invalid="ignore"):
+            c = np.cos(x); s = np.sin(x)
+        bad += int(((np.abs(c) > 1) | (np.abs(s) > 1) | np.isnan(c) | np.isnan(s))[fin].sum())
+        worst_c = max(worst_c, float(np.abs(c[fin]).max())); worst_s = max(worst_s, float(np.abs(s[fin]).max()))
+    print(f"numpy {np.__version__}: every finite float32: max |cos| {worst_c}, max |sin| {worst_s}, violations {bad}  [{time.time() - t0:.0f}s]")
+    return 0 if bad == 0 else 1
+
+
 def main():
+    if "--unit-interval" in sys.argv:
+        return unit_interval()
     quick = "--quick" in sys.argv
     lib = load()
     hi = int(np.float32(2 * np.pi).view(np.uint32)) + 1

@@ -90,3 +90,33 @@ def test_mma_kernel_handles_a_hundred_db_of_power_range():
     assert info.kernel.startswith("fd_mma_kernel"), info.kernel
     o = orc.compute_channels(d, **oracle_kwargs_from_params(p))
     assert_channels_close(H, o["H"], what="power range")
+
+
+@pytest.mark.parametrize("bs_rot,ue_shape", [((0, 0, 0), (1, 1)), ((0, 0, 25), (1, 1)), ((5, 0, 0), (1, 1)), ((0, 0, 0), (2, 1))])
+def test_single_element_unrotated_side_takes_the_short_chain(bs_rot, ue_shape, monkeypatch):
+    """The reference's default UE (one element, rotation [0, 0, 0], isotropic, no FoV): its rotated angles enter the result only
+    through their NaN-ness, and the kernel skips that side's float64 chain (dmk_prologue.cuh: side_angles_trivial).  Paths whose
+    arrival angles are NaN / Inf while their power is finite must still drop out exactly as in the reference; a rotation about z
+    alone keeps the short chain, a rotation about x or a second element does not (same results either way)."""
+    import deepmimo_b200 as dmb
+    from deepmimo_b200.synth import make_paths
+    from oracle import channel_oracle as orc
+    n = 300
+    d = make_paths(n, 4242, n_sc=64, bandwidth=10e6, zero_frac=0.1)
+    rng = np.random.default_rng(9)
+    for key, val in (("aoa_az", np.nan), ("aoa_el", np.inf), ("aod_el", np.nan)):
+        a = d[key].copy()
+        hit = (rng.random(a.shape) < 0.05) & ~np.isnan(d["power"])
+        a[hit] = val
+        d[key] = a
+    p = {"bs_antenna": {"shape": np.array([8, 1]), "spacing": 0.5, "rotation": np.array(bs_rot), "radiation_pattern": "isotropic"},
+         "ue_antenna": {"shape": np.array(ue_shape), "spacing": 0.5, "rotation": np.array([0, 0, 0]), "radiation_pattern": "isotropic"},
+         "enable_doppler": 0, "enable_dual_polar": 0, "num_paths": 25, "freq_domain": 1,
+         "ofdm": {"subcarriers": 64, "selected_subcarriers": np.arange(64), "bandwidth": 10e6, "rx_filter": 0}}
+    monkeypatch.setenv("DMK_FD_KERNEL", "mma")
+    with np.errstate(invalid="ignore"):
+        o = orc.compute_channels(d, **oracle_kwargs_from_params(p))
+    H, info = make_dataset(dmb, d).compute_channels(dmb.ChannelGenParameters(p), return_info=True, warn=False)
+    assert info.kernel.startswith("fd_mma_kernel"), info.kernel
+    assert_channels_close(H, o["H"], what=f"trivial side {bs_rot} {ue_shape}")
+    assert np.array_equal(info.valid, o["valid"]) and np.array_equal(info.clip, o["clip"])

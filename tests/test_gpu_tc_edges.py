@@ -91,7 +91,7 @@ def test_ws_many_users_per_cta_chunked_independent_launches_and_ticket_reuse():
     import torch
     import deepmimo_b200 as dmb
     from oracle import channel_oracle as orc
-    d, p = _case(2500, (8, 8), (1, 1), 1024, np.arange(256), 41, zero_frac=0.2)      # 128 KB per user: above the fd_mma_kernel range
+    d, p = _case(2500, (8, 8), (1, 1), 1024, np.arange(512), 41, zero_frac=0.2)      # 256 KB per user: above the fd_mma_kernel range
     o = orc.compute_channels(d, bs_shape=p["bs_antenna"]["shape"], ue_shape=p["ue_antenna"]["shape"],
                              bs_rotation=p["bs_antenna"]["rotation"], num_paths=p["num_paths"],
                              subcarriers=p["ofdm"]["subcarriers"], selected_subcarriers=p["ofdm"]["selected_subcarriers"],

@@ -48,3 +48,13 @@ def test_degree_grid_and_fused_quadrant_case(lib):
     assert np.array_equal(c.view(np.uint32), np.cos(x).view(np.uint32))
     s, c = _both(lib, np.array([np.nan], np.float32))
     assert np.isnan(s[0]) and np.isnan(c[0])
+
+
+def test_float32_sin_cos_stay_inside_unit_interval():
+    """dmk_prologue.cuh: side_angles_trivial relies on |cos(x)| <= 1 for NumPy's float32 cos (then arccos of it is never NaN for a
+    finite angle).  Strided sweep over every finite float32 here; the exhaustive sweep (all 2^32 bit patterns, ~1 min) is
+    `python oracle/verify_np_trig.py --unit-interval`."""
+    bits = np.arange(0, 1 << 32, 4099, dtype=np.uint64).astype(np.uint32)
+    x = bits.view(np.float32)
+    x = x[np.isfinite(x)]
+    assert np.abs(np.cos(x)).max() <= 1.0 and np.abs(np.sin(x)).max() <= 1.0

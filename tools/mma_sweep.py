@@ -32,7 +32,7 @@ for dense in (False, True):
     s = scenario(1, 80000, dense=dense)
     plan, _ = dmb.make_plan(dmb.Dataset(dict(s.data)), dmb.ChannelGenParameters(s.params), warn=False)
     out = plan.alloc_out()
-    print(f"cfg1{' dense' if dense else ''} (8x1, K=64, 80k users): " + timed(plan, out, ("mma", "mma/16:2", "mma/32", "mma/16:-32", "small")), flush=True)
+    print(f"cfg1{' dense' if dense else ''} (8x1, K=64, 80k users): " + timed(plan, out, ("mma/16:1", "mma/16:2", "mma/32", "small")), flush=True)
     print("   ", _lib.last_kernel(), flush=True)
 shapes = [((8, 2), (1, 1), 64), ((4, 4), (1, 1), 64), ((16, 1), (1, 1), 1024), ((4, 2), (2, 1), 256), ((8, 4), (1, 1), 64),
           ((8, 8), (1, 1), 64), ((8, 8), (1, 1), 128), ((8, 4), (1, 1), 256), ((8, 8), (1, 1), 512)]
@@ -45,4 +45,4 @@ for bs, ue, k in (shapes[:1] + shapes[5:6] if quick else shapes):
     p.ofdm.subcarriers = max(k, 64); p.ofdm.selected_subcarriers = np.arange(k); p.ofdm.bandwidth = 50e6
     plan, _ = dmb.make_plan(dmb.Dataset(d), p, warn=False)
     out = plan.alloc_out()
-    print(f"bs{bs} ue{ue} K={k} n={n} (M={m}, {8 * m * k // 1024} KB/user): " + timed(plan, out, ("mma/16", "mma/32", "mma/32:4", "auto")), flush=True)
+    print(f"bs{bs} ue{ue} K={k} n={n} (M={m}, {8 * m * k // 1024} KB/user): " + timed(plan, out, ("mma/16:1", "mma/16:2", "mma/16:4", "mma/32:1", "mma/32:2", "mma/32:4", "auto")), flush=True)
