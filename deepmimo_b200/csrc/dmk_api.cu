@@ -157,12 +157,15 @@ int device_state(const DeviceState*& out)
         if (e == cudaSuccess) e = cudaFuncSetAttribute(fd_small2_kernel<4, true>, a, kSmemSmall2);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(fd_small2_kernel<8, true>, a, kSmemSmall2);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(fd_small2_kernel<16, true>, a, kSmemSmall2);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(fd_mma_kernel<4, 0>, a, kSmemMma);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(fd_mma_kernel<4, 4>, a, kSmemMma);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(fd_mma_kernel<4, 8>, a, kSmemMma);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(fd_mma_kernel<8, 0>, a, kSmemMma);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(fd_mma_kernel<8, 4>, a, kSmemMma);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(fd_mma_kernel<8, 8>, a, kSmemMma);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(fd_mma_kernel<4, 0, 1>, a, kSmemMma);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(fd_mma_kernel<4, 4, 1>, a, kSmemMma);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(fd_mma_kernel<4, 8, 1>, a, kSmemMma);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(fd_mma_kernel<4, 0, 2>, a, kSmemMma);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(fd_mma_kernel<4, 4, 2>, a, kSmemMma);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(fd_mma_kernel<4, 8, 2>, a, kSmemMma);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(fd_mma_kernel<8, 0, 1>, a, kSmemMma);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(fd_mma_kernel<8, 4, 1>, a, kSmemMma);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(fd_mma_kernel<8, 8, 1>, a, kSmemMma);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(fd_ws_kernel<1>, a, kSmemWs1);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(fd_ws_kernel<2>, a, kSmemWs1);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(fd_ws_kernel<4>, a, kSmemWs4);
@@ -420,14 +423,17 @@ int dmk_channels_fd(const dmk_desc* desc, const float* power_dbw, const float* p
             const long long sgrid = (n_users + upw * kMmWarps - 1) / (upw * kMmWarps);
             if (mma_smem <= (size_t)kSmemMma && sgrid <= 0x7fffffffLL) {
                 const dim3 gr((unsigned)sgrid), bl(kMmWarps * 32);
-                if (nt == 4) { if (sb == 8) fd_mma_kernel<4, 8><<<gr, bl, mma_smem, st>>>(d, mc); else if (sb == 4) fd_mma_kernel<4, 4><<<gr, bl, mma_smem, st>>>(d, mc);
-                               else fd_mma_kernel<4, 0><<<gr, bl, mma_smem, st>>>(d, mc); }
-                else         { if (sb == 8) fd_mma_kernel<8, 8><<<gr, bl, mma_smem, st>>>(d, mc); else if (sb == 4) fd_mma_kernel<8, 4><<<gr, bl, mma_smem, st>>>(d, mc);
-                               else fd_mma_kernel<8, 0><<<gr, bl, mma_smem, st>>>(d, mc); }
+                const bool pair = nt == 4 && mc.n_mt >= 4 && mc.G >= 2;           // two m-tiles per k-step share the B fragments (123 registers)
+                if (nt == 4 && pair) { if (sb == 8) fd_mma_kernel<4, 8, 2><<<gr, bl, mma_smem, st>>>(d, mc); else if (sb == 4) fd_mma_kernel<4, 4, 2><<<gr, bl, mma_smem, st>>>(d, mc);
+                                       else fd_mma_kernel<4, 0, 2><<<gr, bl, mma_smem, st>>>(d, mc); }
+                else if (nt == 4)    { if (sb == 8) fd_mma_kernel<4, 8, 1><<<gr, bl, mma_smem, st>>>(d, mc); else if (sb == 4) fd_mma_kernel<4, 4, 1><<<gr, bl, mma_smem, st>>>(d, mc);
+                                       else fd_mma_kernel<4, 0, 1><<<gr, bl, mma_smem, st>>>(d, mc); }
+                else                 { if (sb == 8) fd_mma_kernel<8, 8, 1><<<gr, bl, mma_smem, st>>>(d, mc); else if (sb == 4) fd_mma_kernel<8, 4, 1><<<gr, bl, mma_smem, st>>>(d, mc);
+                                       else fd_mma_kernel<8, 0, 1><<<gr, bl, mma_smem, st>>>(d, mc); }
                 cudaError_t e = cudaGetLastError();
                 if (e != cudaSuccess) return cuda_fail(e, "fd_mma_kernel launch");
                 g_launches.fetch_add(1);
-                snprintf(g_kernel, sizeof(g_kernel), "fd_mma_kernel<m16n8k16,3xf16,J=%d,SB=%d> grid=%lld users/warp=%lld chunks=%d G=%d smem=%zu", J, sb, sgrid, upw, mc.R, mc.G, mma_smem);
+                snprintf(g_kernel, sizeof(g_kernel), "fd_mma_kernel<m16n8k16,3xf16,J=%d,SB=%d,MP=%d> grid=%lld users/warp=%lld chunks=%d G=%d smem=%zu", J, sb, pair ? 2 : 1, sgrid, upw, mc.R, mc.G, mma_smem);
                 return DMK_OK;
             }
         }

@@ -71,10 +71,74 @@ __device__ __forceinline__ void split_f16x2(float x, float y, unsigned& hi, unsi
 __device__ __forceinline__ int mm_a_off(int rowpair, int slot) { return rowpair * 256 + ((slot * 8) ^ ((rowpair & 1) << 6)); }
 __device__ __forceinline__ int mm_b_off(int row, int slot)     { return row * 128 + ((slot * 4) ^ ((row & 3) << 5)); }
 
-template <int NT, int SB>      // n-tiles of 8 floats per chunk: J = 4 NT subcarriers; SB: chunks per base phasor (0: one phasor per chunk)
-// 96 registers: 7 CTAs = 21 warps per SM with the 8.4 KB pools of J = 16 (a minimum-blocks launch bound makes ptxas stop at 80 and
+// Phase 5 for MP consecutive m-tiles of one user: they share the B fragments of a k-step (loaded once, imaginary-part operand formed
+// once).  k-step = 8 pool slots; this lane's paths are slots 2t, 2t + 1 (MMA k indices (2t, 2t + 1) = (re, im) of the first,
+// (2t + 8, 2t + 9) of the second).
+template <int NT, int MP>
+__device__ __forceinline__ void mm_consume(const unsigned char* sAh, const unsigned char* sAl, const unsigned char* bh_row, const unsigned char* bl_row,
+                                           int rowpair0, unsigned a_sw, unsigned b_sw, int qb, int np, int t, float sc_up,
+                                           float2* out_u, int r0, int R)
+{
+    constexpr int J = 4 * NT;
+    float acc[MP][NT][4];
+    #pragma unroll
+    for (int i = 0; i < MP; ++i)
+        #pragma unroll
+        for (int n = 0; n < NT; ++n) { acc[i][n][0] = 0.f; acc[i][n][1] = 0.f; acc[i][n][2] = 0.f; acc[i][n][3] = 0.f; }
+    const unsigned char* ah_row = sAh + rowpair0 * 256;
+    const unsigned char* al_row = sAl + rowpair0 * 256;
+    #pragma unroll 1
+    for (int k0 = 0; k0 < np; k0 += 8) {
+        const unsigned sl = (unsigned)min(qb + k0, kMmSlots - 2);       // past the row's end only when both paths are >= np (zeroed below)
+        const unsigned ao = (sl * 8u) ^ a_sw, bo = (sl * 4u) ^ b_sw;
+        uint2 bh[NT], bl[NT];                                        // [2 q]: (Fr, -Fi) of column group q, [2 q + 1]: (Fi, Fr)
+        #pragma unroll
+        for (int q = 0; q < NT / 2; ++q) {
+            bh[2 * q] = *reinterpret_cast<const uint2*>(bh_row + q * 1024 + bo);
+            bl[2 * q] = *reinterpret_cast<const uint2*>(bl_row + q * 1024 + bo);
+            bh[2 * q + 1] = make_uint2(__byte_perm(bh[2 * q].x, 0, 0x1032) ^ 0x8000u, __byte_perm(bh[2 * q].y, 0, 0x1032) ^ 0x8000u);
+            bl[2 * q + 1] = make_uint2(__byte_perm(bl[2 * q].x, 0, 0x1032) ^ 0x8000u, __byte_perm(bl[2 * q].y, 0, 0x1032) ^ 0x8000u);
+        }
+        const bool z0 = k0 + 2 * t >= np, z1 = k0 + 2 * t + 1 >= np;     // the user's last, partial k-step
+        #pragma unroll
+        for (int i = 0; i < MP; ++i) {
+            uint4 ah = *reinterpret_cast<const uint4*>(ah_row + i * 2048 + ao);        // chunks g, g + 8 of path 2t; of path 2t + 1
+            uint4 al = *reinterpret_cast<const uint4*>(al_row + i * 2048 + ao);
+            if (k0 + 8 > np) {                                           // warp-uniform
+                if (z0) { ah.x = 0u; ah.y = 0u; al.x = 0u; al.y = 0u; }
+                if (z1) { ah.z = 0u; ah.w = 0u; al.z = 0u; al.w = 0u; }
+            }
+            #pragma unroll
+            for (int n = 0; n < NT; ++n) mma_m16n8k16_f16(acc[i][n], ah, bh[n]);       // NT independent accumulators between
+            #pragma unroll
+            for (int n = 0; n < NT; ++n) mma_m16n8k16_f16(acc[i][n], al, bh[n]);       // two MMAs into the same one
+            #pragma unroll
+            for (int n = 0; n < NT; ++n) mma_m16n8k16_f16(acc[i][n], ah, bl[n]);
+        }
+    }
+    // chunk r = 16 mt + g (+ 8): J complex values at r * J; this lane holds columns 8 q + 2 t, + 1 of both chunks
+    #pragma unroll
+    for (int i = 0; i < MP; ++i)
+        #pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int r = r0 + 16 * i + 8 * h;
+            if (r < R) {
+                float4* o4 = reinterpret_cast<float4*>(out_u + (size_t)r * J);
+                #pragma unroll
+                for (int q = 0; q < NT / 2; ++q)                        // columns 8 q + 2 t, + 1: (re, im, re, im)
+                    __stcs(o4 + q * 4, make_float4(acc[i][2 * q][2 * h] * sc_up, acc[i][2 * q + 1][2 * h] * sc_up,
+                                                   acc[i][2 * q][2 * h + 1] * sc_up, acc[i][2 * q + 1][2 * h + 1] * sc_up));
+            }
+        }
+}
+
+// NT: n-tiles of 8 floats per chunk, J = 4 NT subcarriers.  SB: chunks per base phasor (0: one phasor per chunk).  MP: m-tiles per
+// k-step in phase 5 (2: they share the B fragments -- 8 % faster on users of >= 4 m-tiles, but 123 instead of 96 registers, which
+// costs the small users more than it saves: cfg1 0.241 against 0.214 ms).
+template <int NT, int SB, int MP>
+// MP = 1: 96 registers: 7 CTAs = 21 warps per SM with the 8.4 KB pools of J = 16 (a minimum-blocks launch bound makes ptxas stop at 80 and
 // spill: measured 13 % slower); J = 32 is limited by its pools, not by registers.
-__global__ void __maxnreg__(NT == 4 ? 96 : 168)
+__global__ void __maxnreg__(NT == 4 ? (MP == 2 ? 128 : 96) : 168)
 fd_mma_kernel(const __grid_constant__ DevDesc d, const __grid_constant__ MmaCfg cfg)
 {
     constexpr int J = 4 * NT;
@@ -288,8 +352,7 @@ fd_mma_kernel(const __grid_constant__ DevDesc d, const __grid_constant__ MmaCfg 
                 }
             }
             __syncwarp();
-            // ---- 5. per user and m-tile: fragments, MMAs, stores.  k-step = 8 pool slots; this lane's paths are slots 2t, 2t + 1
-            //         (MMA k indices (2t, 2t + 1) = (re, im) of the first, (2t + 8, 2t + 9) of the second).
+            // ---- 5. per user: fragments, MMAs, stores; two m-tiles at a time share the B fragments where the accumulators fit (J = 16)
             const unsigned a_sw = (unsigned)(g & 1) << 6, b_sw = (unsigned)(g & 3) << 5;        // swizzles of this lane's fragment rows
             const unsigned char* bh_row = sBh + g * 128;
             const unsigned char* bl_row = sBl + g * 128;
@@ -299,52 +362,15 @@ fd_mma_kernel(const __grid_constant__ DevDesc d, const __grid_constant__ MmaCfg 
                 const float sc_up = s_scale[uu];
                 float2* out_u = out_pass + (size_t)uu * (size_t)(M * K) + 2 * t;
                 const int qb = s_base[uu] + 2 * t;
-                #pragma unroll 1
-                for (int ml = 0; ml < n_g; ++ml) {
-                    float acc[NT][4];
-                    #pragma unroll
-                    for (int n = 0; n < NT; ++n) { acc[n][0] = 0.f; acc[n][1] = 0.f; acc[n][2] = 0.f; acc[n][3] = 0.f; }
-                    const unsigned char* ah_row = sAh + (ml * 8 + g) * 256;
-                    const unsigned char* al_row = sAl + (ml * 8 + g) * 256;
+                int ml = 0;
+                if constexpr (MP == 2) {
                     #pragma unroll 1
-                    for (int k0 = 0; k0 < np; k0 += 8) {
-                        const unsigned sl = (unsigned)min(qb + k0, kMmSlots - 2);       // past the row's end only when both paths are >= np (zeroed below)
-                        const unsigned ao = (sl * 8u) ^ a_sw, bo = (sl * 4u) ^ b_sw;
-                        uint4 ah = *reinterpret_cast<const uint4*>(ah_row + ao);        // chunks g, g + 8 of path 2t; of path 2t + 1
-                        uint4 al = *reinterpret_cast<const uint4*>(al_row + ao);
-                        if (k0 + 8 > np) {                                           // the user's last, partial k-step (warp-uniform)
-                            if (k0 + 2 * t >= np)     { ah.x = 0u; ah.y = 0u; al.x = 0u; al.y = 0u; }
-                            if (k0 + 2 * t + 1 >= np) { ah.z = 0u; ah.w = 0u; al.z = 0u; al.w = 0u; }
-                        }
-                        uint2 bh[NT], bl[NT];                                        // [2 q]: (Fr, -Fi) of column group q, [2 q + 1]: (Fi, Fr)
-                        #pragma unroll
-                        for (int q = 0; q < NT / 2; ++q) {
-                            bh[2 * q] = *reinterpret_cast<const uint2*>(bh_row + q * 1024 + bo);
-                            bl[2 * q] = *reinterpret_cast<const uint2*>(bl_row + q * 1024 + bo);
-                            bh[2 * q + 1] = make_uint2(__byte_perm(bh[2 * q].x, 0, 0x1032) ^ 0x8000u, __byte_perm(bh[2 * q].y, 0, 0x1032) ^ 0x8000u);
-                            bl[2 * q + 1] = make_uint2(__byte_perm(bl[2 * q].x, 0, 0x1032) ^ 0x8000u, __byte_perm(bl[2 * q].y, 0, 0x1032) ^ 0x8000u);
-                        }
-                        #pragma unroll
-                        for (int n = 0; n < NT; ++n) mma_m16n8k16_f16(acc[n], ah, bh[n]);       // NT independent accumulators between
-                        #pragma unroll
-                        for (int n = 0; n < NT; ++n) mma_m16n8k16_f16(acc[n], al, bh[n]);       // two MMAs into the same one
-                        #pragma unroll
-                        for (int n = 0; n < NT; ++n) mma_m16n8k16_f16(acc[n], ah, bl[n]);
-                    }
-                    // chunk r = 16 mt + g (+ 8): J complex values at r * J; this lane holds columns 8 q + 2 t, + 1 of both chunks
-                    const int r0 = (mt0 + ml) * 16 + g;
-                    #pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        const int r = r0 + 8 * h;
-                        if (r < cfg.R) {
-                            float4* o4 = reinterpret_cast<float4*>(out_u + (size_t)r * J);
-                            #pragma unroll
-                            for (int q = 0; q < NT / 2; ++q)                        // columns 8 q + 2 t, + 1: (re, im, re, im)
-                                __stcs(o4 + q * 4, make_float4(acc[2 * q][2 * h] * sc_up, acc[2 * q + 1][2 * h] * sc_up,
-                                                               acc[2 * q][2 * h + 1] * sc_up, acc[2 * q + 1][2 * h + 1] * sc_up));
-                        }
-                    }
+                    for (; ml + 1 < n_g; ml += 2)
+                        mm_consume<NT, 2>(sAh, sAl, bh_row, bl_row, ml * 8 + g, a_sw, b_sw, qb, np, t, sc_up, out_u, (mt0 + ml) * 16 + g, cfg.R);
                 }
+                #pragma unroll 1
+                for (; ml < n_g; ++ml)
+                    mm_consume<NT, 1>(sAh, sAl, bh_row, bl_row, ml * 8 + g, a_sw, b_sw, qb, np, t, sc_up, out_u, (mt0 + ml) * 16 + g, cfg.R);
             }
             __syncwarp();                                                       // the L rows are rewritten by the next group / pass
         }

@@ -155,10 +155,10 @@ def _scenario(cfg: int, n_ue: Optional[int], bs_index: int, so: int, dense: bool
                         notes="city-scale shard: one BS x 200k users, 8x8 BS UPA, 1 UE antenna, N=K=1024, B=100 MHz")
     if cfg == 6:
         n = 131_072 if n_ue is None else n_ue
-        d = make_paths(n, 1006 + so, n_sc=64, bandwidth=20e6, dense=dense)
-        return Scenario("mid_8x8_K64", d, _params([8, 8], [1, 1], 64, 64, 20e6, bs_rot=[5, 10, 15]),
+        d = make_paths(n, 1006 + so, n_sc=64, bandwidth=10e6, dense=dense)
+        return Scenario("mid_8x8_K64", d, _params([8, 8], [1, 1], 64, 64, 10e6, bs_rot=[5, 10, 15]),
                         notes="not a BASELINE config: the common 64 antennas x 64 subcarriers dataset (32 KB per user), 8x8 rotated BS UPA, "
-                              "1 UE antenna, N=K=64, B=20 MHz")
+                              "1 UE antenna, N=K=64, B=10 MHz (no path beyond the OFDM symbol)")
     raise ValueError(f"unknown config {cfg}")
 
 

@@ -6,10 +6,11 @@ import deepmimo_b200 as dmb
 from deepmimo_b200 import _lib
 from deepmimo_b200.synth import make_paths
 b0, b1, k, n = (int(v) for v in sys.argv[1:5])
-d = make_paths(n, 7, n_sc=max(k, 64), bandwidth=50e6, n_cols=25)
+bw = min(50e6, max(k, 64) / 4.2e-6)
+d = make_paths(n, 7, n_sc=max(k, 64), bandwidth=bw, n_cols=25)
 p = dmb.ChannelGenParameters()
 p.bs_antenna.shape = np.array([b0, b1]); p.bs_antenna.rotation = np.array([5, 10, 15])
-p.ofdm.subcarriers = max(k, 64); p.ofdm.selected_subcarriers = np.arange(k); p.ofdm.bandwidth = 50e6
+p.ofdm.subcarriers = max(k, 64); p.ofdm.selected_subcarriers = np.arange(k); p.ofdm.bandwidth = bw
 plan, _ = dmb.make_plan(dmb.Dataset(d), p, warn=False)
 out = plan.alloc_out()
 for _ in range(4): plan.run(out)

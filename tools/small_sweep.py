@@ -35,10 +35,11 @@ shapes = [((8, 2), (1, 1), 64), ((4, 4), (1, 1), 64), ((16, 1), (1, 1), 1024), (
 for bs, ue, k in shapes:
     m = bs[0] * bs[1] * ue[0] * ue[1]
     n = int(min(200000, (4 << 30) // (8 * m * k)))
-    d = make_paths(n, 7, n_sc=max(k, 64), bandwidth=50e6, n_cols=25)
+    bw = min(50e6, max(k, 64) / 4.2e-6)      # delays reach 4e-6 s: keep delay * bandwidth < N, else the paths are clipped to zero power
+    d = make_paths(n, 7, n_sc=max(k, 64), bandwidth=bw, n_cols=25)
     p = dmb.ChannelGenParameters()
     p.bs_antenna.shape = np.array(bs); p.ue_antenna.shape = np.array(ue); p.bs_antenna.rotation = np.array([5, 10, 15])
-    p.ofdm.subcarriers = max(k, 64); p.ofdm.selected_subcarriers = np.arange(k); p.ofdm.bandwidth = 50e6
+    p.ofdm.subcarriers = max(k, 64); p.ofdm.selected_subcarriers = np.arange(k); p.ofdm.bandwidth = bw
     plan, _ = dmb.make_plan(dmb.Dataset(d), p, warn=False)
     out = plan.alloc_out()
     print(f"bs{bs} ue{ue} K={k} n={n} (M={m}): " + timed(plan, out), flush=True)
