@@ -19,6 +19,7 @@ namespace {
 
 thread_local char g_err[512] = "";
 thread_local char g_kernel[192] = "";
+std::atomic<unsigned> ticket_seq{0};          // launches in flight use different slots of g_tc_ticket
 std::atomic<long long> g_launches{0};
 
 int fail(int code, const char* fmt, ...)
@@ -360,7 +361,6 @@ int dmk_channels_fd(const dmk_desc* desc, const float* power_dbw, const float* p
                 w.bufs_per_helper = 3;
                 ws_smem = 1024 + off + 12 * buf_bytes;
             }
-            static std::atomic<unsigned> ticket_seq{0};
             unsigned int* tickets = nullptr;
             cudaError_t e = cudaGetSymbolAddress(reinterpret_cast<void**>(&tickets), g_tc_ticket);
             if (e != cudaSuccess) return cuda_fail(e, "cudaGetSymbolAddress(g_tc_ticket)");
@@ -416,20 +416,29 @@ int dmk_channels_fd(const dmk_desc* desc, const float* power_dbw, const float* p
             mc.off_meta = take((size_t)(5 * kMmWindow + 1) * sizeof(int));
             mc.warp_bytes = (int)off;
             mc.off_warps = (int)((((size_t)4 * d.M + mc.S) * sizeof(double) + 15) & ~size_t(15));
-            long long upw = n_users / (2LL * 3 * dev->sms * kMmWarps);
-            upw = upw < 4 ? 4 : (upw > 16 ? 16 : upw);
-            mc.users_per_warp = (int)upw;
             const size_t mma_smem = (size_t)mc.off_warps + off * kMmWarps;
-            const long long sgrid = (n_users + upw * kMmWarps - 1) / (upw * kMmWarps);
-            if (mma_smem <= (size_t)kSmemMma && sgrid <= 0x7fffffffLL) {
-                const dim3 gr((unsigned)sgrid), bl(kMmWarps * 32);
-                const bool pair = nt == 4 && mc.n_mt >= 4 && mc.G >= 2;           // two m-tiles per k-step share the B fragments (123 registers)
-                if (nt == 4 && pair) { if (sb == 8) fd_mma_kernel<4, 8, 2><<<gr, bl, mma_smem, st>>>(d, mc); else if (sb == 4) fd_mma_kernel<4, 4, 2><<<gr, bl, mma_smem, st>>>(d, mc);
-                                       else fd_mma_kernel<4, 0, 2><<<gr, bl, mma_smem, st>>>(d, mc); }
-                else if (nt == 4)    { if (sb == 8) fd_mma_kernel<4, 8, 1><<<gr, bl, mma_smem, st>>>(d, mc); else if (sb == 4) fd_mma_kernel<4, 4, 1><<<gr, bl, mma_smem, st>>>(d, mc);
-                                       else fd_mma_kernel<4, 0, 1><<<gr, bl, mma_smem, st>>>(d, mc); }
-                else                 { if (sb == 8) fd_mma_kernel<8, 8, 1><<<gr, bl, mma_smem, st>>>(d, mc); else if (sb == 4) fd_mma_kernel<8, 4, 1><<<gr, bl, mma_smem, st>>>(d, mc);
-                                       else fd_mma_kernel<8, 0, 1><<<gr, bl, mma_smem, st>>>(d, mc); }
+            const bool pair = nt == 4 && mc.n_mt >= 4 && mc.G >= 2;               // two m-tiles per k-step share the B fragments (123 registers)
+            void (*kern)(DevDesc, MmaCfg, unsigned int*) = nullptr;
+            if (nt == 4 && pair) kern = sb == 8 ? fd_mma_kernel<4, 8, 2> : (sb == 4 ? fd_mma_kernel<4, 4, 2> : fd_mma_kernel<4, 0, 2>);
+            else if (nt == 4)    kern = sb == 8 ? fd_mma_kernel<4, 8, 1> : (sb == 4 ? fd_mma_kernel<4, 4, 1> : fd_mma_kernel<4, 0, 1>);
+            else                 kern = sb == 8 ? fd_mma_kernel<8, 8, 1> : (sb == 4 ? fd_mma_kernel<8, 4, 1> : fd_mma_kernel<8, 0, 1>);
+            int ctas_per_sm = 0;
+            if (mma_smem <= (size_t)kSmemMma &&
+                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, kMmWarps * 32, mma_smem) == cudaSuccess && ctas_per_sm > 0) {
+                // persistent grid; chunks of 8 users (about four passes) unless the range is too short to give every warp one
+                const long long warps = (long long)ctas_per_sm * dev->sms * kMmWarps;
+                long long upw = (n_users + warps - 1) / warps;
+                upw = upw < 2 ? 2 : (upw > 8 ? 8 : upw);
+                mc.users_per_warp = (int)upw;
+                const long long n_chunks = (n_users + upw - 1) / upw;
+                mc.n_chunks = (unsigned)n_chunks;
+                long long sgrid = (n_chunks + kMmWarps - 1) / kMmWarps;
+                if (sgrid > (long long)ctas_per_sm * dev->sms) sgrid = (long long)ctas_per_sm * dev->sms;
+                unsigned int* tickets = nullptr;
+                cudaError_t e0 = cudaGetSymbolAddress(reinterpret_cast<void**>(&tickets), g_tc_ticket);
+                if (e0 != cudaSuccess) return cuda_fail(e0, "cudaGetSymbolAddress(g_tc_ticket)");
+                if (n_chunks >= 0xffff0000LL) return fail(DMK_ERR_INVALID_ARG, "grid too large: split the user range");
+                kern<<<(unsigned)sgrid, kMmWarps * 32, mma_smem, st>>>(d, mc, tickets + (ticket_seq.fetch_add(1) % kTcTickets));
                 cudaError_t e = cudaGetLastError();
                 if (e != cudaSuccess) return cuda_fail(e, "fd_mma_kernel launch");
                 g_launches.fetch_add(1);

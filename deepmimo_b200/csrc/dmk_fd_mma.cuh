@@ -44,7 +44,8 @@ struct MmaCfg {
     int G;                            // m-tiles (16 chunks each) whose L rows are resident at a time
     int n_mt;                         // m-tiles per user = ceil(R / 16)
     int S, R;                         // chunks per antenna row, chunks per user
-    int users_per_warp;
+    int users_per_warp;               // users per chunk (a warp draws chunks from the ticket counter)
+    unsigned n_chunks;
     unsigned mul_s;                   // ceil(2^32 / S) (S > 1): chunk -> antenna row by a multiply-high
 };
 
@@ -139,7 +140,7 @@ template <int NT, int SB, int MP>
 // MP = 1: 96 registers: 7 CTAs = 21 warps per SM with the 8.4 KB pools of J = 16 (a minimum-blocks launch bound makes ptxas stop at 80 and
 // spill: measured 13 % slower); J = 32 is limited by its pools, not by registers.
 __global__ void __maxnreg__(NT == 4 ? (MP == 2 ? 128 : 96) : 168)
-fd_mma_kernel(const __grid_constant__ DevDesc d, const __grid_constant__ MmaCfg cfg)
+fd_mma_kernel(const __grid_constant__ DevDesc d, const __grid_constant__ MmaCfg cfg, unsigned int* ticket)
 {
     constexpr int J = 4 * NT;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -167,8 +168,12 @@ fd_mma_kernel(const __grid_constant__ DevDesc d, const __grid_constant__ MmaCfg 
     for (int o = lane * 16; o < cfg.off_list; o += 32 * 16) *reinterpret_cast<uint4*>(wsm + o) = make_uint4(0u, 0u, 0u, 0u);
     __syncthreads();                              // the only CTA-wide barrier: warps are independent from here on
 
-    const long long u_begin = ((long long)blockIdx.x * kMmWarps + warp) * cfg.users_per_warp;
-    const long long u_end = min(u_begin + (long long)cfg.users_per_warp, d.n_users);
+    // Work distribution: the grid is the resident CTAs; every warp draws chunks of users_per_warp consecutive users from a device
+    // counter until its draw is past the last chunk (every warp draws exactly one such ticket, so the draw that returns
+    // n_chunks + warps - 1 is the launch's last and resets the counter for the next launch).  A static split left the second wave
+    // of CTAs 60 % full (cfg1: 14.5 of 21 warps active on average).
+    long long u_begin = 0, u_end = 0;
+    const unsigned n_draw_last = cfg.n_chunks + gridDim.x * (unsigned)kMmWarps - 1u;
     const unsigned ltmask = (1u << lane) - 1u;
     const int K = d.K, M = d.M, P0 = d.P0;
     const bool need_angles = prologue_needs_angles(d);
@@ -188,6 +193,13 @@ fd_mma_kernel(const __grid_constant__ DevDesc d, const __grid_constant__ MmaCfg 
                 pw[ul] = d.in_f64 ? (float)__ldg(reinterpret_cast<const double*>(d.power) + prow + ul * d.ld) : __ldg(d.power + prow + ul * d.ld);
         }
     };
+    for (;;) {
+    unsigned tk = 0;
+    if (lane == 0) { tk = atomicAdd(ticket, 1u); if (tk == n_draw_last) atomicExch(ticket, 0u); }
+    tk = __shfl_sync(0xffffffffu, tk, 0);
+    if (tk >= cfg.n_chunks) break;
+    u_begin = (long long)tk * cfg.users_per_warp;
+    u_end = min(u_begin + (long long)cfg.users_per_warp, d.n_users);
     load_window(u_begin);
     for (long long cur = u_begin; cur < u_end; ) {
         // ---- 1. window (as fd_small2_kernel)
@@ -375,6 +387,7 @@ fd_mma_kernel(const __grid_constant__ DevDesc d, const __grid_constant__ MmaCfg 
             __syncwarp();                                                       // the L rows are rewritten by the next group / pass
         }
         cur = next_cur;
+    }
     }
 }
 
