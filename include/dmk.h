@@ -77,9 +77,9 @@ typedef struct dmk_desc {
     int32_t flags;              /* DMK_FLAG_* (ABI 2); 0 = plain stream-ordered launch                   */
     int32_t kernel_hint;        /* dmk_kernel_hint (ABI 3); 0 = the library picks the kernel by shape     */
     int32_t ws_helpers;         /* 0 = by shape; 1, 2 or 4 pins the helper-warp count of the persistent tensor-core kernel; with
-                                 * DMK_KERNEL_MMA: 16 or 32 pins the chunk width of the warp-level kernel (tests, A/B timing) */
+                                 * the warp-level-kernel hint (7): 16 or 32 pins the chunk width of the warp-level kernel (tests, A/B timing) */
     int32_t ws_split;           /* 0 = by shape; >= 1 pins how many work items a user's stages are dealt into; with
-                                 * DMK_KERNEL_MMA: m-tiles resident per group (tests, A/B timing) */
+                                 * the warp-level-kernel hint (7): m-tiles resident per group (tests, A/B timing) */
 } dmk_desc;
 
 /* dmk_desc.kernel_hint: force a kernel family where the shape is eligible for it (parity tests run every family on the same
