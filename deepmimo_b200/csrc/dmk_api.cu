@@ -158,15 +158,21 @@ int device_state(const DeviceState*& out)
         if (e == cudaSuccess) e = cudaFuncSetAttribute(fd_small2_kernel<4, true>, a, kSmemSmall2);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(fd_small2_kernel<8, true>, a, kSmemSmall2);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(fd_small2_kernel<16, true>, a, kSmemSmall2);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(fd_mma_kernel<4, 0, 1>, a, kSmemMma);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(fd_mma_kernel<4, 4, 1>, a, kSmemMma);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(fd_mma_kernel<4, 8, 1>, a, kSmemMma);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(fd_mma_kernel<4, 0, 2>, a, kSmemMma);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(fd_mma_kernel<4, 4, 2>, a, kSmemMma);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(fd_mma_kernel<4, 8, 2>, a, kSmemMma);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(fd_mma_kernel<8, 0, 1>, a, kSmemMma);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(fd_mma_kernel<8, 4, 1>, a, kSmemMma);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(fd_mma_kernel<8, 8, 1>, a, kSmemMma);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(fd_mma_kernel<4, 0, 1, false>, a, kSmemMma);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(fd_mma_kernel<4, 4, 1, false>, a, kSmemMma);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(fd_mma_kernel<4, 4, 1, true>, a, kSmemMma);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(fd_mma_kernel<4, 8, 1, false>, a, kSmemMma);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(fd_mma_kernel<4, 8, 1, true>, a, kSmemMma);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(fd_mma_kernel<4, 0, 2, false>, a, kSmemMma);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(fd_mma_kernel<4, 4, 2, false>, a, kSmemMma);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(fd_mma_kernel<4, 4, 2, true>, a, kSmemMma);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(fd_mma_kernel<4, 8, 2, false>, a, kSmemMma);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(fd_mma_kernel<4, 8, 2, true>, a, kSmemMma);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(fd_mma_kernel<8, 0, 1, false>, a, kSmemMma);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(fd_mma_kernel<8, 4, 1, false>, a, kSmemMma);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(fd_mma_kernel<8, 4, 1, true>, a, kSmemMma);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(fd_mma_kernel<8, 8, 1, false>, a, kSmemMma);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(fd_mma_kernel<8, 8, 1, true>, a, kSmemMma);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(fd_ws_kernel<1>, a, kSmemWs1);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(fd_ws_kernel<2>, a, kSmemWs1);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(fd_ws_kernel<4>, a, kSmemWs4);
@@ -418,10 +424,18 @@ int dmk_channels_fd(const dmk_desc* desc, const float* power_dbw, const float* p
             mc.off_warps = (int)((((size_t)4 * d.M + mc.S) * sizeof(double) + 15) & ~size_t(15));
             const size_t mma_smem = (size_t)mc.off_warps + off * kMmWarps;
             const bool pair = nt == 4 && mc.n_mt >= 4 && mc.G >= 2;               // two m-tiles per k-step share the B fragments (123 registers)
+            // float32 inputs, no FoV filter, isotropic patterns: instantiation without the float64-input / angle / dipole code
+            const bool plain = !d.in_f64 && !d.fov_any && d.pat[0] == DMK_PATTERN_ISOTROPIC && d.pat[1] == DMK_PATTERN_ISOTROPIC && sb != 0;
             void (*kern)(DevDesc, MmaCfg, unsigned int*) = nullptr;
-            if (nt == 4 && pair) kern = sb == 8 ? fd_mma_kernel<4, 8, 2> : (sb == 4 ? fd_mma_kernel<4, 4, 2> : fd_mma_kernel<4, 0, 2>);
-            else if (nt == 4)    kern = sb == 8 ? fd_mma_kernel<4, 8, 1> : (sb == 4 ? fd_mma_kernel<4, 4, 1> : fd_mma_kernel<4, 0, 1>);
-            else                 kern = sb == 8 ? fd_mma_kernel<8, 8, 1> : (sb == 4 ? fd_mma_kernel<8, 4, 1> : fd_mma_kernel<8, 0, 1>);
+            if (plain) {
+                if (nt == 4 && pair) kern = sb == 8 ? fd_mma_kernel<4, 8, 2, true> : fd_mma_kernel<4, 4, 2, true>;
+                else if (nt == 4)    kern = sb == 8 ? fd_mma_kernel<4, 8, 1, true> : fd_mma_kernel<4, 4, 1, true>;
+                else                 kern = sb == 8 ? fd_mma_kernel<8, 8, 1, true> : fd_mma_kernel<8, 4, 1, true>;
+            } else {
+                if (nt == 4 && pair) kern = sb == 8 ? fd_mma_kernel<4, 8, 2, false> : (sb == 4 ? fd_mma_kernel<4, 4, 2, false> : fd_mma_kernel<4, 0, 2, false>);
+                else if (nt == 4)    kern = sb == 8 ? fd_mma_kernel<4, 8, 1, false> : (sb == 4 ? fd_mma_kernel<4, 4, 1, false> : fd_mma_kernel<4, 0, 1, false>);
+                else                 kern = sb == 8 ? fd_mma_kernel<8, 8, 1, false> : (sb == 4 ? fd_mma_kernel<8, 4, 1, false> : fd_mma_kernel<8, 0, 1, false>);
+            }
             int ctas_per_sm = 0;
             if (mma_smem <= (size_t)kSmemMma &&
                 cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, kMmWarps * 32, mma_smem) == cudaSuccess && ctas_per_sm > 0) {
@@ -442,7 +456,7 @@ int dmk_channels_fd(const dmk_desc* desc, const float* power_dbw, const float* p
                 cudaError_t e = cudaGetLastError();
                 if (e != cudaSuccess) return cuda_fail(e, "fd_mma_kernel launch");
                 g_launches.fetch_add(1);
-                snprintf(g_kernel, sizeof(g_kernel), "fd_mma_kernel<m16n8k16,3xf16,J=%d,SB=%d,MP=%d> grid=%lld users/warp=%lld chunks=%d G=%d smem=%zu", J, sb, pair ? 2 : 1, sgrid, upw, mc.R, mc.G, mma_smem);
+                snprintf(g_kernel, sizeof(g_kernel), "fd_mma_kernel<m16n8k16,3xf16,J=%d,SB=%d,MP=%d%s> grid=%lld users/warp=%lld chunks=%d G=%d smem=%zu", J, sb, pair ? 2 : 1, plain ? ",plain" : "", sgrid, upw, mc.R, mc.G, mma_smem);
                 return DMK_OK;
             }
         }

@@ -135,8 +135,10 @@ __device__ __forceinline__ void mm_consume(const unsigned char* sAh, const unsig
 
 // NT: n-tiles of 8 floats per chunk, J = 4 NT subcarriers.  SB: chunks per base phasor (0: one phasor per chunk).  MP: m-tiles per
 // k-step in phase 5 (2: they share the B fragments -- 8 % faster on users of >= 4 m-tiles, but 123 instead of 96 registers, which
-// costs the small users more than it saves: cfg1 0.241 against 0.214 ms).
-template <int NT, int SB, int MP>
+// costs the small users more than it saves: cfg1 0.241 against 0.214 ms).  kPlain: float32 inputs, no FoV filter, isotropic patterns --
+// the instantiation without the float64-input, angle (acos / atan2) and dipole code is half the size, which the instruction fetch of
+// 18 warps in different phases of a ~2 500-instruction pass feels.
+template <int NT, int SB, int MP, bool kPlain>
 // MP = 1: 96 registers: 7 CTAs = 21 warps per SM with the 8.4 KB pools of J = 16 (a minimum-blocks launch bound makes ptxas stop at 80 and
 // spill: measured 13 % slower); J = 32 is limited by its pools, not by registers.
 __global__ void __maxnreg__(NT == 4 ? (MP == 2 ? 128 : 96) : 168)
@@ -176,7 +178,9 @@ fd_mma_kernel(const __grid_constant__ DevDesc d, const __grid_constant__ MmaCfg 
     const unsigned n_draw_last = cfg.n_chunks + gridDim.x * (unsigned)kMmWarps - 1u;
     const unsigned ltmask = (1u << lane) - 1u;
     const int K = d.K, M = d.M, P0 = d.P0;
-    const bool need_angles = prologue_needs_angles(d);
+    const bool need_angles = kPlain ? false : prologue_needs_angles(d);
+    const bool in_f64 = kPlain ? false : (d.in_f64 != 0);
+    const bool fov_any = kPlain ? false : (d.fov_any != 0);
     const bool triv0 = side_angles_trivial(d, 0), triv1 = side_angles_trivial(d, 1);
     const int g = lane >> 2, t = lane & 3;
     const double kstep = (double)d.subc_step;
@@ -190,7 +194,7 @@ fd_mma_kernel(const __grid_constant__ DevDesc d, const __grid_constant__ MmaCfg 
         for (int ul = 0; ul < kMmWindow; ++ul) {
             pw[ul] = __int_as_float(0x7fc00000);
             if (from + ul < u_end && lane < P0)
-                pw[ul] = d.in_f64 ? (float)__ldg(reinterpret_cast<const double*>(d.power) + prow + ul * d.ld) : __ldg(d.power + prow + ul * d.ld);
+                pw[ul] = in_f64 ? (float)__ldg(reinterpret_cast<const double*>(d.power) + prow + ul * d.ld) : __ldg(d.power + prow + ul * d.ld);
         }
     };
     for (;;) {
@@ -209,7 +213,7 @@ fd_mma_kernel(const __grid_constant__ DevDesc d, const __grid_constant__ MmaCfg 
             const bool in = ul < n_in && lane < P0;
             const bool valid = in && lane < d.P && !(pw[ul] != pw[ul]);           // channel.py:260, dataset.py:258-261
             const unsigned vb = __ballot_sync(0xffffffffu, valid);
-            const unsigned nb = d.fov_any ? __ballot_sync(0xffffffffu, in) : vb;
+            const unsigned nb = fov_any ? __ballot_sync(0xffffffffu, in) : vb;
             if (lane == ul) { s_valid[ul] = vb; s_need[ul] = nb; }
         }
         __syncwarp();
@@ -247,7 +251,7 @@ fd_mma_kernel(const __grid_constant__ DevDesc d, const __grid_constant__ MmaCfg 
             if (u < u_end) {
                 const float* base = (arr == 0) ? d.power : (arr == 1) ? d.phase : (arr == 2) ? d.delay : (arr == 3) ? d.az[0] : (arr == 4) ? d.el[0]
                                   : (arr == 5) ? d.az[1] : d.el[1];
-                asm volatile("prefetch.global.L2 [%0];" :: "l"(reinterpret_cast<const char*>(base) + u * (long long)d.ld * (d.in_f64 ? 8 : 4)));
+                asm volatile("prefetch.global.L2 [%0];" :: "l"(reinterpret_cast<const char*>(base) + u * (long long)d.ld * (in_f64 ? 8 : 4)));
             }
         }
         // ---- 3. the chain round: lane = dense pair (cum <= 32)
@@ -260,7 +264,7 @@ fd_mma_kernel(const __grid_constant__ DevDesc d, const __grid_constant__ MmaCfg 
         if (act) {
             const long long user = cur + ul;
             SideOut s0, s1; GainOut gn;
-            if (!d.in_f64) {                                                    // the seven entries of the pair in one batch of loads
+            if (!in_f64) {                                                      // the seven entries of the pair in one batch of loads
                 PathIn in;
                 load_path_in(d, user, col, in);
                 if (need_angles) { prologue_side_in<true>(d, user, 0, in, s0, d.Mt > 1);  prologue_side_in<true>(d, user, 1, in, s1, d.Mr > 1); }
@@ -274,7 +278,7 @@ fd_mma_kernel(const __grid_constant__ DevDesc d, const __grid_constant__ MmaCfg 
                 else             { prologue_side<false>(d, user, col, 0, s0, d.Mt > 1); prologue_side<false>(d, user, col, 1, s1, d.Mr > 1); }
                 prologue_gain<true>(d, user, col, gn);
             }
-            prologue_combine<true>(d, s0, s1, gn, st);
+            prologue_combine<true, kPlain>(d, s0, s1, gn, st);
             const long long om = user * (long long)P0 + col;
             if (d.fov_mask)  d.fov_mask[om]  = st.fov ? 1 : 0;
             if (d.clip_mask) d.clip_mask[om] = (st.valid && st.over) ? 1 : 0;

@@ -236,14 +236,16 @@ __device__ __forceinline__ void prologue_gain(const DevDesc& d, long long user, 
     prologue_gain_f32<kFreqDomain>(d, p, d.power[off], d.phase[off], d.delay[off], d.doppler ? d.doppler[off] : 0.0f, g);
 }
 
-template <bool kFreqDomain>
+// kPlain: the caller knows that no FoV filter is set, both patterns are isotropic and the inputs are float32 (the common case gets a
+// kernel instantiation without the dipole / float64-power code).
+template <bool kFreqDomain, bool kPlain = false>
 __device__ __forceinline__ void prologue_combine(const DevDesc& d, const SideOut& s0, const SideOut& s1, const GainOut& g, PathState& o)
 {
     o.valid = g.valid; o.over = g.over; o.wcyc = g.wcyc; o.fd = g.fd;
     o.th[0] = s0.th; o.ph[0] = s0.ph; o.th[1] = s1.th; o.ph[1] = s1.ph;
     // ---- FoV (dataset.py:493-512)
     bool fov = true;
-    if (d.fov_any) {
+    if (!kPlain && d.fov_any) {
         if (d.fov_side[0]) fov = fov && in_fov(d, 0, s0.th, s0.ph);
         if (d.fov_side[1]) fov = fov && in_fov(d, 1, s1.th, s1.ph);
     }
@@ -253,9 +255,9 @@ __device__ __forceinline__ void prologue_combine(const DevDesc& d, const SideOut
     o.u[0] = d.sp[0] * s0.ss; o.v[0] = d.sp[0] * s0.cc;
     o.u[1] = d.sp[1] * s1.ss; o.v[1] = d.sp[1] * s1.cc;
     // ---- power with element patterns (ant_patterns.py:167-168): float64 as soon as one side is a dipole
-    const bool f64_power = d.in_f64 || (d.pat[0] != DMK_PATTERN_ISOTROPIC) || (d.pat[1] != DMK_PATTERN_ISOTROPIC);
+    const bool f64_power = !kPlain && (d.in_f64 || (d.pat[0] != DMK_PATTERN_ISOTROPIC) || (d.pat[1] != DMK_PATTERN_ISOTROPIC));
     double pw64 = g.p_lin64;
-    if (d.pat[0] != DMK_PATTERN_ISOTROPIC || d.pat[1] != DMK_PATTERN_ISOTROPIC) {
+    if (!kPlain && (d.pat[0] != DMK_PATTERN_ISOTROPIC || d.pat[1] != DMK_PATTERN_ISOTROPIC)) {
         const double nan64 = __longlong_as_double(0x7ff8000000000000LL);
         const double gt = (d.pat[0] == DMK_PATTERN_HALFWAVE_DIPOLE) ? dipole_gain(fov ? s0.th : nan64) : 1.0;
         const double gr = (d.pat[1] == DMK_PATTERN_HALFWAVE_DIPOLE) ? dipole_gain(fov ? s1.th : nan64) : 1.0;
