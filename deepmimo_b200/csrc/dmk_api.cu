@@ -413,7 +413,7 @@ int dmk_channels_fd(const dmk_desc* desc, const float* power_dbw, const float* p
             mc.mul_s = mc.S > 1 ? (unsigned)((0x100000000ULL + mc.S - 1) / mc.S) : 0u;
             const int sb = mc.S % 8 == 0 ? 8 : (mc.S % 4 == 0 ? 4 : 0);      // chunks of one antenna row that share a base phasor
             mc.G = mc.n_mt < 2 ? mc.n_mt : 2;                        // two m-tiles per group: measured best for both chunk widths
-            if (desc->ws_split > 0) mc.G = desc->ws_split < mc.n_mt ? desc->ws_split : mc.n_mt;
+            if (desc->ws_split > 0 && desc->ws_split < 100) mc.G = desc->ws_split < mc.n_mt ? desc->ws_split : mc.n_mt;
             size_t off = 0;
             auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 15) & ~size_t(15); return (int)o; };
             mc.off_A    = take((size_t)2 * mc.G * 8 * 256);
@@ -439,20 +439,21 @@ int dmk_channels_fd(const dmk_desc* desc, const float* power_dbw, const float* p
             int ctas_per_sm = 0;
             if (mma_smem <= (size_t)kSmemMma &&
                 cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, kMmWarps * 32, mma_smem) == cudaSuccess && ctas_per_sm > 0) {
-                // persistent grid; chunks of 8 users (about four passes) unless the range is too short to give every warp one
-                const long long warps = (long long)ctas_per_sm * dev->sms * kMmWarps;
-                long long upw = (n_users + warps - 1) / warps;
-                upw = upw < 2 ? 2 : (upw > 8 ? 8 : upw);
-                mc.users_per_warp = (int)upw;
-                const long long n_chunks = (n_users + upw - 1) / upw;
-                mc.n_chunks = (unsigned)n_chunks;
-                long long sgrid = (n_chunks + kMmWarps - 1) / kMmWarps;
+                // persistent grid; guided draws of 8 / 4 / 2 users (see the kernel)
+                const long long warps_res = (long long)ctas_per_sm * dev->sms * kMmWarps;
+                long long sgrid = (n_users + 2 * kMmWarps - 1) / (2 * kMmWarps);
                 if (sgrid > (long long)ctas_per_sm * dev->sms) sgrid = (long long)ctas_per_sm * dev->sms;
+                const long long warps = sgrid * kMmWarps;
+                mc.users_per_warp = desc->ws_split >= 100 ? desc->ws_split - 100 : 0;         // A/B timing of the draw size
+                mc.draw8_above = (unsigned)(12 * warps);
+                mc.draw4_above = (unsigned)(3 * warps);
+                const long long upw = mc.users_per_warp;
+                (void)warps_res;
+                if (n_users >= 0xfffff000LL) return fail(DMK_ERR_INVALID_ARG, "grid too large: split the user range");
                 unsigned int* tickets = nullptr;
                 cudaError_t e0 = cudaGetSymbolAddress(reinterpret_cast<void**>(&tickets), g_tc_ticket);
                 if (e0 != cudaSuccess) return cuda_fail(e0, "cudaGetSymbolAddress(g_tc_ticket)");
-                if (n_chunks >= 0xffff0000LL) return fail(DMK_ERR_INVALID_ARG, "grid too large: split the user range");
-                kern<<<(unsigned)sgrid, kMmWarps * 32, mma_smem, st>>>(d, mc, tickets + (ticket_seq.fetch_add(1) % kTcTickets));
+                kern<<<(unsigned)sgrid, kMmWarps * 32, mma_smem, st>>>(d, mc, tickets + 2 * (ticket_seq.fetch_add(1) % (kTcTickets / 2)));
                 cudaError_t e = cudaGetLastError();
                 if (e != cudaSuccess) return cuda_fail(e, "fd_mma_kernel launch");
                 g_launches.fetch_add(1);

@@ -44,8 +44,8 @@ struct MmaCfg {
     int G;                            // m-tiles (16 chunks each) whose L rows are resident at a time
     int n_mt;                         // m-tiles per user = ceil(R / 16)
     int S, R;                         // chunks per antenna row, chunks per user
-    int users_per_warp;               // users per chunk (a warp draws chunks from the ticket counter)
-    unsigned n_chunks;
+    int users_per_warp;               // 0: guided draws (8 / 4 / 2 users); > 0 pins the draw size
+    unsigned draw8_above, draw4_above; // users left in the launch above which a warp draws 8 / 4 users
     unsigned mul_s;                   // ceil(2^32 / S) (S > 1): chunk -> antenna row by a multiply-high
 };
 
@@ -170,12 +170,13 @@ fd_mma_kernel(const __grid_constant__ DevDesc d, const __grid_constant__ MmaCfg 
     for (int o = lane * 16; o < cfg.off_list; o += 32 * 16) *reinterpret_cast<uint4*>(wsm + o) = make_uint4(0u, 0u, 0u, 0u);
     __syncthreads();                              // the only CTA-wide barrier: warps are independent from here on
 
-    // Work distribution: the grid is the resident CTAs; every warp draws chunks of users_per_warp consecutive users from a device
-    // counter until its draw is past the last chunk (every warp draws exactly one such ticket, so the draw that returns
-    // n_chunks + warps - 1 is the launch's last and resets the counter for the next launch).  A static split left the second wave
-    // of CTAs 60 % full (cfg1: 14.5 of 21 warps active on average).
+    // Work distribution: the grid is the resident CTAs; every warp draws runs of consecutive users from a device counter
+    // (ticket[0] = next user) until its draw starts past the last user.  The draws shrink towards the end of the launch (8, 4, then 2
+    // users: long draws fill the rounds of 32 lanes better, short ones even out the tail).  ticket[1] counts the warps that are
+    // through; the last one resets both for the next launch.  A static split left the second wave of CTAs 60 % full (cfg1: 14.5 of 21
+    // warps active on average).
     long long u_begin = 0, u_end = 0;
-    const unsigned n_draw_last = cfg.n_chunks + gridDim.x * (unsigned)kMmWarps - 1u;
+    const unsigned n_users32 = (unsigned)d.n_users;
     const unsigned ltmask = (1u << lane) - 1u;
     const int K = d.K, M = d.M, P0 = d.P0;
     const bool need_angles = kPlain ? false : prologue_needs_angles(d);
@@ -198,49 +199,58 @@ fd_mma_kernel(const __grid_constant__ DevDesc d, const __grid_constant__ MmaCfg 
         }
     };
     for (;;) {
-    unsigned tk = 0;
-    if (lane == 0) { tk = atomicAdd(ticket, 1u); if (tk == n_draw_last) atomicExch(ticket, 0u); }
-    tk = __shfl_sync(0xffffffffu, tk, 0);
-    if (tk >= cfg.n_chunks) break;
-    u_begin = (long long)tk * cfg.users_per_warp;
-    u_end = min(u_begin + (long long)cfg.users_per_warp, d.n_users);
+    unsigned first = 0, cnt = 0;
+    if (lane == 0) {
+        const unsigned seen = *reinterpret_cast<volatile unsigned int*>(ticket);      // may be stale: it only sizes the draw
+        const unsigned left = seen < n_users32 ? n_users32 - seen : 0u;
+        cnt = left > cfg.draw8_above ? 8u : (left > cfg.draw4_above ? 4u : 2u);
+        if (cfg.users_per_warp > 0) cnt = (unsigned)cfg.users_per_warp;                 // pinned draw size (A/B timing)
+        first = atomicAdd(ticket, cnt);
+    }
+    first = __shfl_sync(0xffffffffu, first, 0);
+    cnt = __shfl_sync(0xffffffffu, cnt, 0);
+    if (first >= n_users32) break;
+    u_begin = (long long)first;
+    u_end = min(u_begin + (long long)cnt, d.n_users);
     load_window(u_begin);
     for (long long cur = u_begin; cur < u_end; ) {
-        // ---- 1. window (as fd_small2_kernel)
+        // ---- 1. window: which columns of the next users run their chain (every lane holds the four masks)
         const int n_in = (int)min((long long)kMmWindow, u_end - cur);
+        unsigned vbs[kMmWindow], nbs[kMmWindow];
         #pragma unroll
         for (int ul = 0; ul < kMmWindow; ++ul) {
             const bool in = ul < n_in && lane < P0;
             const bool valid = in && lane < d.P && !(pw[ul] != pw[ul]);           // channel.py:260, dataset.py:258-261
-            const unsigned vb = __ballot_sync(0xffffffffu, valid);
-            const unsigned nb = fov_any ? __ballot_sync(0xffffffffu, in) : vb;
-            if (lane == ul) { s_valid[ul] = vb; s_need[ul] = nb; }
+            vbs[ul] = __ballot_sync(0xffffffffu, valid);
+            nbs[ul] = fov_any ? __ballot_sync(0xffffffffu, in) : vbs[ul];
         }
-        __syncwarp();
         // ---- 2. whole users, in order, while their pairs fit one round of lanes and the pool (a user's first slot is even: a lane
         //         loads the operands of its two paths of a k-step with one aligned access).  Measured and left out: first fit over a
         //         window of 8 pending users fills 27 instead of 23 lanes but costs more in the window than it saves in the chains.
         int cum = 0, slots = 0, n_take = 0;
-        long long o = cur * (long long)P0 + lane;
-        #pragma unroll 1
-        for (int ul = 0; ul < n_in; ++ul, o += P0) {
-            const unsigned nb = s_need[ul], vb = s_valid[ul];
+        bool open = true;
+        #pragma unroll
+        for (int ul = 0; ul < kMmWindow; ++ul) {
+            const unsigned nb = nbs[ul], vb = vbs[ul];
             const int c = __popc(nb);
             const int base = (slots + 1) & ~1;
-            if (ul > 0 && (cum + c > 32 || base + c > kMmSlots)) break;
-            if (lane == 0) { s_base[ul] = base; s_cnt[ul] = 0; s_scale[ul] = 0.f; }
-            const bool run = (nb >> lane) & 1u;
-            if (run) list[cum + __popc(nb & ltmask)] = (unsigned char)((ul << 5) | lane);
-            if (lane < P0) {
-                if (d.valid_mask) d.valid_mask[o] = (vb >> lane) & 1u;
-                if (!run) {                                                     // no FoV mask is built and the column has no power
-                    if (d.fov_mask)  d.fov_mask[o] = 1;
-                    if (d.clip_mask) d.clip_mask[o] = 0;
+            open = open && ul < n_in && (ul == 0 || (cum + c <= 32 && base + c <= kMmSlots));
+            if (open) {                                                         // warp-uniform
+                if (lane == 0) { s_base[ul] = base; s_cnt[ul] = 0; s_scale[ul] = 0.f; }
+                const bool run = (nb >> lane) & 1u;
+                if (run) list[cum + __popc(nb & ltmask)] = (unsigned char)((ul << 5) | lane);
+                if (lane < P0) {
+                    const long long o = (cur + ul) * (long long)P0 + lane;
+                    if (d.valid_mask) d.valid_mask[o] = (vb >> lane) & 1u;
+                    if (!run) {                                                 // no FoV mask is built and the column has no power
+                        if (d.fov_mask)  d.fov_mask[o] = 1;
+                        if (d.clip_mask) d.clip_mask[o] = 0;
+                    }
                 }
+                cum += c;
+                slots = base + c;
+                ++n_take;
             }
-            cum += c;
-            slots = base + c;
-            ++n_take;
         }
         __syncwarp();
         const long long next_cur = cur + n_take;
@@ -303,7 +313,8 @@ fd_mma_kernel(const __grid_constant__ DevDesc d, const __grid_constant__ MmaCfg 
             for (int i = 1; i < 4; ++i) f1[i] = phasor_cycles_sfu(-(st.wcyc * (kstep * (double)i)));
             #pragma unroll 1
             for (int b = 0; b < NT; ++b) {                                       // rolled: the pass has to stay inside the instruction cache
-                const float2 f4b = phasor_cycles_sfu(-(st.wcyc * (kstep * (double)(4 * b))));      // b = 0: exactly (1, 0)
+                float2 f4b = make_float2(1.f, 0.f);
+                if (b) f4b = phasor_cycles_sfu(-(st.wcyc * (kstep * (double)(4 * b))));
                 const int row_b = (b >> 1) * 8 + 4 * (b & 1);                       // j = 4 b + i: column group j >> 3, column j & 7
                 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
@@ -392,6 +403,10 @@ fd_mma_kernel(const __grid_constant__ DevDesc d, const __grid_constant__ MmaCfg 
         }
         cur = next_cur;
     }
+    }
+    if (lane == 0 && atomicAdd(ticket + 1, 1u) == gridDim.x * (unsigned)kMmWarps - 1u) {      // the last warp of the launch
+        atomicExch(ticket, 0u);
+        atomicExch(ticket + 1, 0u);
     }
 }
 
