@@ -419,7 +419,7 @@ int dmk_channels_fd(const dmk_desc* desc, const float* power_dbw, const float* p
             mc.off_A    = take((size_t)2 * mc.G * 8 * 256);
             mc.off_B    = take((size_t)2 * (nt / 2) * 8 * 128);
             mc.off_list = take((size_t)32);
-            mc.off_meta = take((size_t)(5 * kMmWindow + 1) * sizeof(int));
+            mc.off_meta = take((size_t)(3 * kMmWindow + 1) * sizeof(int));
             mc.warp_bytes = (int)off;
             mc.off_warps = (int)((((size_t)4 * d.M + mc.S) * sizeof(double) + 15) & ~size_t(15));
             const size_t mma_smem = (size_t)mc.off_warps + off * kMmWarps;

@@ -164,9 +164,7 @@ fd_mma_kernel(const __grid_constant__ DevDesc d, const __grid_constant__ MmaCfg 
     unsigned char* list = wsm + cfg.off_list;                                  // [32] (user in window << 5) | column
     int* s_base         = reinterpret_cast<int*>(wsm + cfg.off_meta);          // [kMmWindow + 1] first pool slot of the user (even)
     int* s_cnt          = s_base + kMmWindow + 1;                              // [kMmWindow] contributing paths
-    unsigned* s_need    = reinterpret_cast<unsigned*>(s_cnt + kMmWindow);      // [kMmWindow] columns whose chain runs
-    unsigned* s_valid   = s_need + kMmWindow;                                  // [kMmWindow] columns with a path (valid_mask)
-    float* s_scale      = reinterpret_cast<float*>(s_valid + kMmWindow);       // [kMmWindow] 2^e undoing the operand scale
+    float* s_scale      = reinterpret_cast<float*>(s_cnt + kMmWindow);         // [kMmWindow] 2^e undoing the operand scale
     for (int o = lane * 16; o < cfg.off_list; o += 32 * 16) *reinterpret_cast<uint4*>(wsm + o) = make_uint4(0u, 0u, 0u, 0u);
     __syncthreads();                              // the only CTA-wide barrier: warps are independent from here on
 

@@ -28,6 +28,18 @@ struct PathState {
 // which are the same functions of (x, re, im) evaluated to a few float64 ulps, so the angles themselves (acos, atan2:
 // ~half of the prologue's dependent latency) are computed only when something consumes them -- the FoV compares
 // (geometry.py:180-193), the dipole pattern (ant_patterns.py:57-69) or the by-product kernel.
+// 1 / sqrt(v) for v in (0, 4]: MUFU.RSQ on the float32 value (22 good bits), two Newton steps in float64 (relative error
+// ~1e-16 after the second; the first alone would leave 1e-13).  v < 0 -> NaN, NaN -> NaN.  Callers handle v == 0.
+__device__ __forceinline__ double drsqrt_nr(double v)
+{
+    if (v < 1e-30) return __ddiv_rn(1.0, sqrt(v));          // below float32's normal range (a direction within 1e-15 rad of the pole)
+    double y = (double)rsqrtf((float)v);
+    const double hv = 0.5 * v;
+    y = y * fma(-hv * y, y, 1.5);
+    y = y * fma(-hv * y, y, 1.5);
+    return y;
+}
+
 template <bool kNeedAngles>
 __device__ __forceinline__ void rotate_core(double st, double ct, double dphi,
                                             double sx, double cx, double sy, double cy,
@@ -54,10 +66,13 @@ __device__ __forceinline__ void rotate_core(double st, double ct, double dphi,
     cos_th = x;
     sin_th_sin_ph = 0.0;
     if (!steer) return;        // single-element panel (e.g. one UE antenna): only the NaN-ness of the angles is consumed
-    const double sin_th = sqrt(__dmul_rn(__dsub_rn(1.0, x), __dadd_rn(1.0, x)));     // sin(arccos(x)); NaN for |x| > 1
-    const double h = sqrt(__dadd_rn(__dmul_rn(re, re), __dmul_rn(im, im)));
-    const double sin_ph = (h > 0.0) ? __ddiv_rn(im, h) : 0.0;                        // sin(atan2(im, re)); atan2(0, +0) = 0
-    sin_th_sin_ph = sin_th * sin_ph;
+    // sin(arccos(x)) sin(atan2(im, re)) = sqrt(a) * im / sqrt(b),  a = (1 - x)(1 + x) (negative, hence NaN, for |x| > 1),
+    // b = re^2 + im^2 (atan2(0, +0) = 0: the product is 0 when b == 0).  Both roots come from drsqrt_nr: two library square roots
+    // and a division were a third of this chain's instructions and the longest part of its dependent latency.
+    const double a = __dmul_rn(__dsub_rn(1.0, x), __dadd_rn(1.0, x));
+    const double b = __dadd_rn(__dmul_rn(re, re), __dmul_rn(im, im));
+    const double sin_th = (a == 0.0) ? 0.0 : a * drsqrt_nr(a);
+    sin_th_sin_ph = (b > 0.0) ? sin_th * (im * drsqrt_nr(b)) : ((b == b) ? 0.0 : b);
 }
 
 // float32 angles (the reference's storage type): deg2rad and sin/cos of theta in float32 exactly as NumPy does them (R1, R2).
