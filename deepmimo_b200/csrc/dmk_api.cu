@@ -294,7 +294,7 @@ int dmk_channels_fd(const dmk_desc* desc, const float* power_dbw, const float* p
     const bool tc_shape = (d.M >= 64 || n_chunks_u >= 128) && !d.fov_any;
     // Per-user outputs of at most 128 KB go to the warp-level tensor-core kernel (dmk_fd_mma.cuh) instead: the persistent kernel is
     // bound by its helper warps there (8x8 x K=64: 1.4 against 3.5 TB/s, 16x1 x K=1024: 3.46 against 3.61; profiles/README.md).
-    const bool mma_shape = affine && !d.has_time_axis && d.M <= 64 && (d.K % 16 == 0) && d.K <= 4096 &&
+    const bool mma_shape = affine && !d.has_time_axis && d.M <= 256 && (d.K % 16 == 0) && d.K <= 4096 &&
                            ((reinterpret_cast<uintptr_t>(out_c64) & 15) == 0);
     const bool mma_pref = mma_shape && hint == DMK_KERNEL_AUTO && (long long)d.M * d.K * 8 <= 128 * 1024;
     const bool use_tc = !mma_pref && affine && !d.has_time_axis && div_ok && (d.K % (kTcN / 2) == 0) && d.K <= 4096 &&
@@ -394,7 +394,7 @@ int dmk_channels_fd(const dmk_desc* desc, const float* power_dbw, const float* p
             return DMK_OK;
         }
     }
-    // Small per-user outputs (M <= 64, K % 16 == 0): warp-level tensor-core kernel, see dmk_fd_mma.cuh.  Default up to 128 KB per user,
+    // Small per-user outputs (M <= 256, K % 16 == 0): warp-level tensor-core kernel, see dmk_fd_mma.cuh.  Default up to 128 KB per user,
     // and for every eligible shape the persistent kernel did not take (FoV-filtered scenarios, fewer than 128 chunks per user);
     // DMK_KERNEL_MMA forces it on every eligible shape, DMK_KERNEL_SMALL keeps the CUDA-core fd_small2_kernel.
     {

@@ -23,6 +23,8 @@ CASES = [
     ((8, 4), (1, 1), 256, np.arange(256), 77, ((120, 90), (180, 120)), ("isotropic", "halfwave-dipole"), 25, True, True, 25, False),
     ((8, 1), (1, 1), 64, np.arange(64), 90, None, ("isotropic", "isotropic"), 32, False, False, 32, True),
     ((4, 4), (2, 2), 128, np.arange(96), 45, None, ("isotropic", "isotropic"), 25, True, False, 25, True),
+    ((16, 8), (1, 1), 64, np.arange(64), 70, None, ("isotropic", "isotropic"), 25, False, False, 25, False),                     # M = 128
+    ((8, 8), (2, 2), 128, 3 + np.arange(64), 41, ((150, 100), (180, 120)), ("isotropic", "isotropic"), 25, True, True, 25, False),   # M = 256
 ]
 
 
