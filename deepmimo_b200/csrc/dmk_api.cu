@@ -294,7 +294,7 @@ int dmk_channels_fd(const dmk_desc* desc, const float* power_dbw, const float* p
     const bool tc_shape = (d.M >= 64 || n_chunks_u >= 128) && !d.fov_any;
     // Per-user outputs of at most 128 KB go to the warp-level tensor-core kernel (dmk_fd_mma.cuh) instead: the persistent kernel is
     // bound by its helper warps there (8x8 x K=64: 1.4 against 3.5 TB/s, 16x1 x K=1024: 3.46 against 3.61; profiles/README.md).
-    const bool mma_shape = affine && !d.has_time_axis && d.M <= 256 && (d.K % 16 == 0) && d.K <= 4096 &&
+    const bool mma_shape = affine && !d.has_time_axis && d.M <= 256 && d.K <= 4096 &&
                            ((reinterpret_cast<uintptr_t>(out_c64) & 15) == 0);
     const bool mma_pref = mma_shape && hint == DMK_KERNEL_AUTO && (long long)d.M * d.K * 8 <= 128 * 1024;
     const bool use_tc = !mma_pref && affine && !d.has_time_axis && div_ok && (d.K % (kTcN / 2) == 0) && d.K <= 4096 &&
@@ -394,7 +394,7 @@ int dmk_channels_fd(const dmk_desc* desc, const float* power_dbw, const float* p
             return DMK_OK;
         }
     }
-    // Small per-user outputs (M <= 256, K % 16 == 0): warp-level tensor-core kernel, see dmk_fd_mma.cuh.  Default up to 128 KB per user,
+    // Small per-user outputs (M <= 256, K <= 4096): warp-level tensor-core kernel, see dmk_fd_mma.cuh.  Default up to 128 KB per user,
     // and for every eligible shape the persistent kernel did not take (FoV-filtered scenarios, fewer than 128 chunks per user);
     // DMK_KERNEL_MMA forces it on every eligible shape, DMK_KERNEL_SMALL keeps the CUDA-core fd_small2_kernel.
     {
@@ -407,7 +407,12 @@ int dmk_channels_fd(const dmk_desc* desc, const float* power_dbw, const float* p
             int J = (d.K % 128 == 0 && (long long)d.M * d.K / 16 >= 256) ? 32 : 16;
             if (desc->ws_helpers == 16 || (desc->ws_helpers == 32 && d.K % 32 == 0)) J = desc->ws_helpers;      // A/B timing
             const int nt = J / 4;
-            mc.S = d.K / J;
+            mc.S = (d.K + J - 1) / J;                                // the last chunk of a row may be cut off (K % J != 0)
+            mc.ragged = d.K % J != 0;
+            // Rows of 3, 6, 7, 9, 10, 11 ... chunks are padded to a multiple of 4 chunks (the padding chunks are computed and never
+            // stored): blocks of 4 chunks then share a base phasor, which costs less than a float64-reduced phasor for every chunk
+            // (measured, tools/mma_ragged.py: pays up to a third of padding -- K = 300: 2.2 -> 3.1 TB/s -- not for 5 -> 8 chunks)
+            if (mc.S % 4 != 0 && 3 * ((mc.S + 3) & ~3) <= 4 * mc.S) { mc.S = (mc.S + 3) & ~3; mc.ragged = 1; }
             mc.R = d.M * mc.S;
             mc.n_mt = (mc.R + 15) / 16;
             mc.mul_s = mc.S > 1 ? (unsigned)((0x100000000ULL + mc.S - 1) / mc.S) : 0u;
@@ -425,7 +430,7 @@ int dmk_channels_fd(const dmk_desc* desc, const float* power_dbw, const float* p
             const size_t mma_smem = (size_t)mc.off_warps + off * kMmWarps;
             const bool pair = nt == 4 && mc.n_mt >= 4 && mc.G >= 2;               // two m-tiles per k-step share the B fragments (123 registers)
             // float32 inputs, no FoV filter, isotropic patterns: instantiation without the float64-input / angle / dipole code
-            const bool plain = !d.in_f64 && !d.fov_any && d.pat[0] == DMK_PATTERN_ISOTROPIC && d.pat[1] == DMK_PATTERN_ISOTROPIC && sb != 0;
+            const bool plain = !d.in_f64 && !d.fov_any && d.pat[0] == DMK_PATTERN_ISOTROPIC && d.pat[1] == DMK_PATTERN_ISOTROPIC && sb != 0 && !mc.ragged;
             void (*kern)(DevDesc, MmaCfg, unsigned int*) = nullptr;
             if (plain) {
                 if (nt == 4 && pair) kern = sb == 8 ? fd_mma_kernel<4, 8, 2, true> : fd_mma_kernel<4, 4, 2, true>;

@@ -43,7 +43,8 @@ struct MmaCfg {
     int off_A, off_B, off_list, off_meta;
     int G;                            // m-tiles (16 chunks each) whose L rows are resident at a time
     int n_mt;                         // m-tiles per user = ceil(R / 16)
-    int S, R;                         // chunks per antenna row, chunks per user
+    int S, R;                         // chunks per antenna row (ceil(K / J)), chunks per user
+    int ragged;                       // K % J != 0
     int users_per_warp;               // 0: guided draws (8 / 4 / 2 users); > 0 pins the draw size
     unsigned draw8_above, draw4_above; // users left in the launch above which a warp draws 8 / 4 users
     unsigned mul_s;                   // ceil(2^32 / S) (S > 1): chunk -> antenna row by a multiply-high
@@ -72,13 +73,17 @@ __device__ __forceinline__ void split_f16x2(float x, float y, unsigned& hi, unsi
 __device__ __forceinline__ int mm_a_off(int rowpair, int slot) { return rowpair * 256 + ((slot * 8) ^ ((rowpair & 1) << 6)); }
 __device__ __forceinline__ int mm_b_off(int row, int slot)     { return row * 128 + ((slot * 4) ^ ((row & 3) << 5)); }
 
+// K not a multiple of the chunk width: the chunks of an antenna row are S = ceil(K / J), the last one is stored up to column K only.
+// Compiled into the generic instantiations only (carrying it costs the plain ones 4 %): such shapes take the generic family.
+struct MmRagged { int on, K, S, vec2; unsigned mul_s; };
+
 // Phase 5 for MP consecutive m-tiles of one user: they share the B fragments of a k-step (loaded once, imaginary-part operand formed
 // once).  k-step = 8 pool slots; this lane's paths are slots 2t, 2t + 1 (MMA k indices (2t, 2t + 1) = (re, im) of the first,
 // (2t + 8, 2t + 9) of the second).
-template <int NT, int MP>
+template <int NT, int MP, bool kRag>
 __device__ __forceinline__ void mm_consume(const unsigned char* sAh, const unsigned char* sAl, const unsigned char* bh_row, const unsigned char* bl_row,
                                            int rowpair0, unsigned a_sw, unsigned b_sw, int qb, int np, int t, float sc_up,
-                                           float2* out_u, int r0, int R)
+                                           float2* out_u, int r0, int R, const MmRagged& rg)
 {
     constexpr int J = 4 * NT;
     float acc[MP][NT][4];
@@ -123,12 +128,28 @@ __device__ __forceinline__ void mm_consume(const unsigned char* sAh, const unsig
         #pragma unroll
         for (int h = 0; h < 2; ++h) {
             const int r = r0 + 16 * i + 8 * h;
-            if (r < R) {
+            if (r >= R) continue;
+            if (!kRag || !rg.on) {                                      // K a multiple of J: chunk r starts at r * J
                 float4* o4 = reinterpret_cast<float4*>(out_u + (size_t)r * J);
                 #pragma unroll
                 for (int q = 0; q < NT / 2; ++q)                        // columns 8 q + 2 t, + 1: (re, im, re, im)
                     __stcs(o4 + q * 4, make_float4(acc[i][2 * q][2 * h] * sc_up, acc[i][2 * q + 1][2 * h] * sc_up,
                                                    acc[i][2 * q][2 * h + 1] * sc_up, acc[i][2 * q + 1][2 * h + 1] * sc_up));
+            } else {                                                    // the last chunk of an antenna row is cut off at column K
+                const unsigned m = rg.mul_s ? __umulhi((unsigned)r, rg.mul_s) : (unsigned)r;
+                const int col0 = (r - (int)m * rg.S) * J + 2 * t;       // out_u already points at this lane's column 2 t
+                float2* row = out_u + (size_t)m * rg.K + (col0 - 2 * t);
+                #pragma unroll
+                for (int q = 0; q < NT / 2; ++q) {
+                    const int col = col0 + 8 * q;
+                    const float2 v0 = make_float2(acc[i][2 * q][2 * h] * sc_up, acc[i][2 * q + 1][2 * h] * sc_up);
+                    const float2 v1 = make_float2(acc[i][2 * q][2 * h + 1] * sc_up, acc[i][2 * q + 1][2 * h + 1] * sc_up);
+                    if (rg.vec2 && col + 1 < rg.K) __stcs(reinterpret_cast<float4*>(row + 8 * q), make_float4(v0.x, v0.y, v1.x, v1.y));
+                    else {
+                        if (col < rg.K)     __stcs(row + 8 * q, v0);
+                        if (col + 1 < rg.K) __stcs(row + 8 * q + 1, v1);
+                    }
+                }
             }
         }
 }
@@ -379,6 +400,7 @@ fd_mma_kernel(const __grid_constant__ DevDesc d, const __grid_constant__ MmaCfg 
             __syncwarp();
             // ---- 5. per user: fragments, MMAs, stores; two m-tiles at a time share the B fragments where the accumulators fit (J = 16)
             const unsigned a_sw = (unsigned)(g & 1) << 6, b_sw = (unsigned)(g & 3) << 5;        // swizzles of this lane's fragment rows
+            const MmRagged rg = {cfg.ragged, K, cfg.S, (K & 1) == 0, cfg.mul_s};
             const unsigned char* bh_row = sBh + g * 128;
             const unsigned char* bl_row = sBl + g * 128;
             #pragma unroll 1
@@ -391,11 +413,11 @@ fd_mma_kernel(const __grid_constant__ DevDesc d, const __grid_constant__ MmaCfg 
                 if constexpr (MP == 2) {
                     #pragma unroll 1
                     for (; ml + 1 < n_g; ml += 2)
-                        mm_consume<NT, 2>(sAh, sAl, bh_row, bl_row, ml * 8 + g, a_sw, b_sw, qb, np, t, sc_up, out_u, (mt0 + ml) * 16 + g, cfg.R);
+                        mm_consume<NT, 2, !kPlain>(sAh, sAl, bh_row, bl_row, ml * 8 + g, a_sw, b_sw, qb, np, t, sc_up, out_u, (mt0 + ml) * 16 + g, cfg.R, rg);
                 }
                 #pragma unroll 1
                 for (; ml < n_g; ++ml)
-                    mm_consume<NT, 1>(sAh, sAl, bh_row, bl_row, ml * 8 + g, a_sw, b_sw, qb, np, t, sc_up, out_u, (mt0 + ml) * 16 + g, cfg.R);
+                    mm_consume<NT, 1, !kPlain>(sAh, sAl, bh_row, bl_row, ml * 8 + g, a_sw, b_sw, qb, np, t, sc_up, out_u, (mt0 + ml) * 16 + g, cfg.R, rg);
             }
             __syncwarp();                                                       // the L rows are rewritten by the next group / pass
         }

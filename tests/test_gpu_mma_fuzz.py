@@ -1,5 +1,5 @@
 """fd_mma_kernel (warp-level tensor-core accumulate for small per-user outputs, dmk_fd_mma.cuh) against the oracle over random
-shapes.  Cases cover: both chunk widths (J = 16 / 32 subcarriers, forced through DMK_WS_HELPERS), several groups of m-tiles
+shapes.  Cases cover: both chunk widths, K not a multiple of the chunk width (even and odd K, K = 1), panels up to 256 elements (J = 16 / 32 subcarriers, forced through DMK_WS_HELPERS), several groups of m-tiles
 (DMK_WS_SPLIT = m-tiles resident at a time), partial m-tiles (chunks per user not a multiple of 16), a non-power-of-two number of
 chunks per antenna row, FoV masks (every column runs its chain), dipole patterns, NaN holes, num_paths < n_cols, per-user UE
 rotation, strided selections with an offset, 32 dense path columns (one user per pass), user counts that leave partial windows."""
@@ -25,6 +25,13 @@ CASES = [
     ((4, 4), (2, 2), 128, np.arange(96), 45, None, ("isotropic", "isotropic"), 25, True, False, 25, True),
     ((16, 8), (1, 1), 64, np.arange(64), 70, None, ("isotropic", "isotropic"), 25, False, False, 25, False),                     # M = 128
     ((8, 8), (2, 2), 128, 3 + np.arange(64), 41, ((150, 100), (180, 120)), ("isotropic", "isotropic"), 25, True, True, 25, False),   # M = 256
+    # K not a multiple of the chunk width: the last chunk of every antenna row is cut off (even K: 16-byte stores, odd K: 8-byte)
+    ((8, 8), (1, 1), 128, np.arange(72), 60, None, ("isotropic", "isotropic"), 25, False, False, 25, False),
+    ((4, 2), (2, 1), 512, np.arange(130), 97, None, ("isotropic", "isotropic"), 25, True, True, 25, False),
+    ((3, 1), (1, 1), 64, np.arange(7), 40, ((180, 90), (360, 180)), ("halfwave-dipole", "halfwave-dipole"), 25, True, False, 25, False),
+    ((2, 2), (2, 2), 2048, 5 + 3 * np.arange(301), 75, None, ("halfwave-dipole", "isotropic"), 10, True, True, 25, False),
+    ((1, 1), (1, 1), 512, np.arange(1), 50, None, ("isotropic", "isotropic"), 25, False, False, 25, False),
+    ((16, 1), (1, 1), 1024, np.arange(1000), 33, None, ("isotropic", "isotropic"), 25, False, False, 25, False),
 ]
 
 

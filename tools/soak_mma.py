@@ -1,4 +1,4 @@
-"""Soak test of fd_mma_kernel: random shapes it is eligible for (M <= 256, K a multiple of 16, K <= 4096), both chunk widths, one to
+"""Soak test of fd_mma_kernel: random shapes it is eligible for (M <= 256, K <= 4096, mostly multiples of 16), both chunk widths, one to
 three m-tiles per group, selections with offset / stride, FoV / dipole / holes / num_paths / per-user UE rotation, user counts and
 chunkings (chunks are launched back to back: the ticket counter must be back at zero every time); every result compared with the
 packed-FP32 CUDA-core kernel and the generic tile kernel, masks bit for bit.   python tools/soak_mma.py [seconds]"""
@@ -18,7 +18,9 @@ while time.time() - t0 < budget:
         bs = (int(rng.integers(1, 17)), int(rng.integers(1, 17))); ue = (int(rng.integers(1, 3)), int(rng.integers(1, 3)))
         m = bs[0] * bs[1] * ue[0] * ue[1]
         if m <= 256: break
-    k = 16 * int(rng.choice([1, 2, 3, 4, 5, 8, 12, 16, 24, 32, 64, 100, 256])); step = int(rng.choice([1, 1, 3])); start = int(rng.integers(0, 5))
+    k = 16 * int(rng.choice([1, 2, 3, 4, 5, 8, 12, 16, 24, 32, 64, 100, 256]))
+    if rng.random() < 0.3: k = int(rng.choice([1, 2, 7, 52, 63, 65, 72, 130, 257, 1000]))      # not a multiple of the chunk width
+    step = int(rng.choice([1, 1, 3])); start = int(rng.integers(0, 5))
     n_sc = int(2 ** np.ceil(np.log2(start + step * k + 1)))
     n = int(rng.choice([1, 3, 63, 64, 65, 500, 2049, 9000]))
     n = max(1, min(n, (1 << 27) // (8 * m * k)))
