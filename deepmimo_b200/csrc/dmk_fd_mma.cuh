@@ -33,7 +33,7 @@
 
 namespace dmk {
 
-constexpr int kMmWarps  = 3;                       // 8.4 KB of pool per warp (J = 16): 7 CTAs = 21 warps per SM at 96 registers
+constexpr int kMmWarps  = 3;                       // 8.4 - 12.4 KB of pool per warp (J = 16): 6 CTAs = 18 warps per SM at 96 registers
 constexpr int kMmWindow = 4;                       // users examined per pass
 constexpr int kMmSlots  = 32;                      // pool slots (paths) per pass: one chain round
 
