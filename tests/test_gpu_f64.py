@@ -26,7 +26,7 @@ def test_mixed_dtypes_are_refused():
         dmb.Dataset(d).compute_channels(dmb.ChannelGenParameters(s.params), warn=False)
 
 
-@pytest.mark.parametrize("cfg,n,variant", [(1, 400, "small"), (1, 400, "small1"), (2, 10, "tc"), (2, 10, "tc1"), (2, 10, "ffma"), (3, 64, "auto"),
+@pytest.mark.parametrize("cfg,n,variant", [(1, 400, "small"), (1, 400, "small1"), (1, 400, "mma"), (1, 400, "auto"), (6, 60, "auto"), (2, 10, "tc"), (2, 10, "tc1"), (2, 10, "ffma"), (3, 64, "auto"),
                                            (5, 40, "tile"), (4, 200, "auto")])
 def test_float64_inputs_match_oracle_in_every_kernel_family(cfg, n, variant, monkeypatch):
     import deepmimo_b200 as dmb
