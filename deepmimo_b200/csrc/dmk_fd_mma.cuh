@@ -106,21 +106,29 @@ __device__ __forceinline__ void mm_consume(const unsigned char* sAh, const unsig
             bl[2 * q + 1] = make_uint2(__byte_perm(bl[2 * q].x, 0, 0x1032) ^ 0x8000u, __byte_perm(bl[2 * q].y, 0, 0x1032) ^ 0x8000u);
         }
         const bool z0 = k0 + 2 * t >= np, z1 = k0 + 2 * t + 1 >= np;     // the user's last, partial k-step
+        uint4 ah[MP], al[MP];
         #pragma unroll
         for (int i = 0; i < MP; ++i) {
-            uint4 ah = *reinterpret_cast<const uint4*>(ah_row + i * 2048 + ao);        // chunks g, g + 8 of path 2t; of path 2t + 1
-            uint4 al = *reinterpret_cast<const uint4*>(al_row + i * 2048 + ao);
+            ah[i] = *reinterpret_cast<const uint4*>(ah_row + i * 2048 + ao);           // chunks g, g + 8 of path 2t; of path 2t + 1
+            al[i] = *reinterpret_cast<const uint4*>(al_row + i * 2048 + ao);
             if (k0 + 8 > np) {                                           // warp-uniform
-                if (z0) { ah.x = 0u; ah.y = 0u; al.x = 0u; al.y = 0u; }
-                if (z1) { ah.z = 0u; ah.w = 0u; al.z = 0u; al.w = 0u; }
+                if (z0) { ah[i].x = 0u; ah[i].y = 0u; al[i].x = 0u; al[i].y = 0u; }
+                if (z1) { ah[i].z = 0u; ah[i].w = 0u; al[i].z = 0u; al[i].w = 0u; }
             }
-            #pragma unroll
-            for (int n = 0; n < NT; ++n) mma_m16n8k16_f16(acc[i][n], ah, bh[n]);       // NT independent accumulators between
-            #pragma unroll
-            for (int n = 0; n < NT; ++n) mma_m16n8k16_f16(acc[i][n], al, bh[n]);       // two MMAs into the same one
-            #pragma unroll
-            for (int n = 0; n < NT; ++n) mma_m16n8k16_f16(acc[i][n], ah, bl[n]);
         }
+        // MP * NT independent accumulators between two MMAs into the same one
+        #pragma unroll
+        for (int i = 0; i < MP; ++i)
+            #pragma unroll
+            for (int n = 0; n < NT; ++n) mma_m16n8k16_f16(acc[i][n], ah[i], bh[n]);
+        #pragma unroll
+        for (int i = 0; i < MP; ++i)
+            #pragma unroll
+            for (int n = 0; n < NT; ++n) mma_m16n8k16_f16(acc[i][n], al[i], bh[n]);
+        #pragma unroll
+        for (int i = 0; i < MP; ++i)
+            #pragma unroll
+            for (int n = 0; n < NT; ++n) mma_m16n8k16_f16(acc[i][n], ah[i], bl[n]);
     }
     // chunk r = 16 mt + g (+ 8): J complex values at r * J; this lane holds columns 8 q + 2 t, + 1 of both chunks
     #pragma unroll
