@@ -616,6 +616,16 @@ int dmk_channels_td_tau(const dmk_desc* desc, const float* power_dbw, const floa
     rc = device_state(dev);
     if (rc) return rc;
     d.n_sms = dev->sms;
+    if (!d.has_time_axis && desc->kernel_hint != DMK_KERNEL_TILE) {
+        // the reference's own time-domain mode: one warp per user, one store instruction per antenna row (dmk_td.cuh)
+        const long long wgrid = (n_users + kTdwWarps - 1) / kTdwWarps;
+        td_warp_kernel<<<(unsigned)wgrid, kTdwWarps * 32, 0, st>>>(d);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return cuda_fail(e, "td_warp_kernel launch");
+        g_launches.fetch_add(1);
+        snprintf(g_kernel, sizeof(g_kernel), "td_warp_kernel<warp/user> grid=%lld", wgrid);
+        return DMK_OK;
+    }
     td_kernel<<<(unsigned)n_users, kTdThreads, 0, st>>>(d);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "td_kernel launch");

@@ -144,6 +144,90 @@ td_kernel(const __grid_constant__ DevDesc d)
     }
 }
 
+// =================================================================================================
+// td_warp_kernel -- the reference's own time-domain mode (freq_domain = 0, no time axis): one WARP per user.
+//
+// Without a time axis a table entry of td_kernel is used once, so that kernel evaluates a float64-reduced polynomial phasor
+// (plus the integer divisions of its index arithmetic) for every 8 bytes it writes and gives a whole CTA to every user:
+// 0.3 TB/s on 8x1 panels (1.6 KB per user), 1.0-1.3 TB/s on larger ones.  Here
+//   lanes = path columns: the three float64 chains + combine (as everywhere), masks, path slots, tau;
+//   compaction: lane j < P becomes output slot j and fetches the state of the j-th valid column by shuffles
+//     (channel.py:274-287: the valid paths lead, FoV-masked ones keep their slot with a zero, the rest is zero);
+//   the warp walks the antenna rows (y fastest, then z, then the RX element): a float64 multiply-add on the running phase, an SFU
+//     phasor (float64-reduced argument, <= 3.6e-7), a complex multiply and ONE store instruction per row -- 8 P contiguous bytes;
+//     rows are contiguous, so a user is one linear stream.
+// No shared memory, no barriers; warps of a CTA only share the launch.
+// =================================================================================================
+constexpr int kTdwWarps = 4;
+
+__global__ void __launch_bounds__(kTdwWarps * 32)
+td_warp_kernel(const __grid_constant__ DevDesc d)
+{
+    const int lane = threadIdx.x & 31;
+    const long long user = (long long)blockIdx.x * kTdwWarps + (threadIdx.x >> 5);
+    if (user >= d.n_users) return;                          // warp-uniform
+    PathState st;
+    const bool active = lane < d.P0;
+    st.contrib = false; st.valid = false; st.fov = true; st.over = false;
+    st.c = make_float2(0.f, 0.f); st.u[0] = st.u[1] = st.v[0] = st.v[1] = 0.0;
+    if (active) {
+        SideOut s0, s1; GainOut g;
+        if (prologue_needs_angles(d)) { prologue_side<true>(d, user, lane, 0, s0, d.Mt > 1);  prologue_side<true>(d, user, lane, 1, s1, d.Mr > 1); }
+        else                          { prologue_side<false>(d, user, lane, 0, s0, d.Mt > 1); prologue_side<false>(d, user, lane, 1, s1, d.Mr > 1); }
+        prologue_gain<false>(d, user, lane, g);
+        prologue_combine<false>(d, s0, s1, g, st);
+    }
+    const unsigned vb = __ballot_sync(0xffffffffu, active && st.valid);
+    const int nv = __popc(vb);
+    const int rank = __popc(vb & ((1u << lane) - 1u));
+    if (active) {
+        const long long o = user * (long long)d.P0 + lane;
+        if (d.fov_mask)   d.fov_mask[o]   = st.fov ? 1 : 0;
+        if (d.valid_mask) d.valid_mask[o] = st.valid ? 1 : 0;
+        if (d.path_slot)  d.path_slot[o]  = st.valid ? rank : -1;
+    }
+    if (d.tau_out) {                                        // slot j <- ToA of the j-th valid column (sionna_adapter.py:196-198), zeros behind
+        float* tau_u = d.tau_out + user * (long long)d.P;
+        if (active && st.valid) {
+            const long long o = user * (long long)d.ld + lane;
+            tau_u[rank] = d.in_f64 ? (float)reinterpret_cast<const double*>(d.delay)[o] : d.delay[o];
+        }
+        if (lane >= nv && lane < d.P) tau_u[lane] = 0.f;
+    }
+    // slot `lane` takes the state of the lane-th valid column (a non-contributing path -- outside the FoV, NaN angle -- is a zero)
+    const int src = (lane < nv) ? (int)__fns(vb, 0, lane + 1) : 0;
+    const bool on = __shfl_sync(0xffffffffu, (int)st.contrib, src) != 0 && lane < nv;
+    float2 c;
+    c.x = __shfl_sync(0xffffffffu, st.c.x, src); c.y = __shfl_sync(0xffffffffu, st.c.y, src);
+    double u0 = __shfl_sync(0xffffffffu, st.u[0], src), v0 = __shfl_sync(0xffffffffu, st.v[0], src);
+    double u1 = __shfl_sync(0xffffffffu, st.u[1], src), v1 = __shfl_sync(0xffffffffu, st.v[1], src);
+    if (!on) { c = make_float2(0.f, 0.f); u0 = v0 = u1 = v1 = 0.0; }      // empty slots and zeroed paths: (0, 0) x a finite phasor
+
+    const int P = d.P;
+    float2* o = d.out + user * (long long)d.M * P + lane;
+    const bool wr = lane < P;
+    double cyc_r = 0.0;                                      // RX element (y_r, z_r): y_r u_rx + z_r v_rx
+    for (int zr = 0; zr < d.ue1; ++zr) {
+        double cyc_ry = cyc_r;
+        for (int yr = 0; yr < d.ue0; ++yr) {
+            double cyc_z = cyc_ry;                           // + z_t v_tx
+            for (int zt = 0; zt < d.bs1; ++zt) {
+                double cyc = cyc_z;                          // + y_t u_tx
+                #pragma unroll 4
+                for (int yt = 0; yt < d.bs0; ++yt) {
+                    const float2 val = cmul(c, phasor_cycles_sfu(cyc));
+                    if (wr) __stcs(o, val);
+                    o += P;
+                    cyc += u0;
+                }
+                cyc_z += v0;
+            }
+            cyc_ry += u1;
+        }
+        cyc_r += v1;
+    }
+}
+
 // Per-path by-products (Dataset caches): rotated angles, power with antenna gain, FoV mask.
 __global__ void __launch_bounds__(256)
 prologue_kernel(const __grid_constant__ DevDesc d, double* __restrict__ angles_rot, double* __restrict__ power_gain)

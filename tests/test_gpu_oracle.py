@@ -68,7 +68,8 @@ def test_td_without_time_axis_equals_t0_snapshot():
     H0 = make_dataset(dmb, s).compute_channels(p)
     HT = make_dataset(dmb, s).compute_channels(p, times=np.array([0.0, 2e-3]), doppler=s.doppler_hz)
     assert H0.shape == (500, 2, 32, 25) and HT.shape == (500, 2, 32, 25, 2)
-    assert np.array_equal(H0, HT[..., 0])          # exp(j 2 pi f_D * 0) == 1 exactly
+    # exp(j 2 pi f_D * 0) == 1 exactly; the static call runs td_warp_kernel (SFU phasors), the time axis td_kernel (polynomial ones)
+    assert assert_channels_close(H0, np.ascontiguousarray(HT[..., 0]), tol=2e-6, what="t = 0 snapshot") < 2e-6
     assert not np.array_equal(H0, HT[..., 1])
     np.testing.assert_allclose(np.abs(HT[..., 1]), np.abs(H0), rtol=2e-6, atol=1e-12)
 
