@@ -48,7 +48,7 @@ class DmkDesc(ctypes.Structure):
 ABI_VERSION = 3
 FLAG_INDEPENDENT_LAUNCH = 1
 FLAG_F64_INPUTS = 2
-KERNEL_HINTS = {"": 0, "auto": 0, "fast": 0, "tile": 1, "ffma": 2, "tc": 3, "tc1": 4, "small": 5, "small1": 6, "mma": 7}      # enum dmk_kernel_hint ("fast" = the default route)
+KERNEL_HINTS = {"": 0, "auto": 0, "fast": 0, "tile": 1, "ffma": 2, "tc": 3, "tc1": 4, "small": 5, "small1": 6, "mma": 7, "rows": 8}      # enum dmk_kernel_hint ("fast" = the default route)
 
 
 def kernel_hint_from_env(var: str = "DMK_FD_KERNEL") -> int:

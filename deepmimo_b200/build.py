@@ -17,7 +17,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libdmk.so")
 SOURCES = ["dmk_api.cu"]
-HEADERS = ["dmk_common.cuh", "dmk_prologue.cuh", "dmk_fd.cuh", "dmk_fd_tc.cuh", "dmk_fd_ws.cuh", "dmk_fd_small.cuh", "dmk_fd_mma.cuh", "dmk_td.cuh", "dmk_bf.cuh", os.path.join("..", "..", "include", "dmk.h")]
+HEADERS = ["dmk_common.cuh", "dmk_prologue.cuh", "dmk_fd.cuh", "dmk_fd_tc.cuh", "dmk_fd_ws.cuh", "dmk_fd_small.cuh", "dmk_fd_mma.cuh", "dmk_fd_rows.cuh", "dmk_td.cuh", "dmk_bf.cuh", os.path.join("..", "..", "include", "dmk.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -12,6 +12,7 @@
 #include "dmk_fd_ws.cuh"
 #include "dmk_fd_small.cuh"
 #include "dmk_fd_mma.cuh"
+#include "dmk_fd_rows.cuh"
 #include "dmk_td.cuh"
 #include "dmk_bf.cuh"
 
@@ -237,6 +238,27 @@ int dmk_channels_fd(const dmk_desc* desc, const float* power_dbw, const float* p
     // the generic tile kernel, which reads the list.
     if (d.K == 1 && d.subc_step == 0 && !d.subc) d.subc_step = 1;
     const bool affine = (d.subc_step != 0) && !d.rx_filter;      // the LPF runs in the generic tile kernel
+    // A handful of selected subcarriers (K <= 8; the reference's default is ONE, channel.py:61), any list: warp per user with lanes =
+    // antenna rows (dmk_fd_rows.cuh).  Every other kernel spreads the K columns over lanes or MMA columns and idles there.
+    if (!d.has_time_axis && !d.rx_filter && d.K <= 8 && (unsigned long long)d.M * (unsigned long long)(d.Mt > d.bs0 ? d.Mt : d.bs0) < 0xffffffffULL &&
+        (desc->kernel_hint == DMK_KERNEL_AUTO || desc->kernel_hint == DMK_KERNEL_ROWS)) {
+        RowsCfg rc;
+        rc.mul_mt  = d.Mt  > 1 ? (unsigned)((0x100000000ULL + d.Mt - 1) / d.Mt) : 0u;
+        rc.mul_bs0 = d.bs0 > 1 ? (unsigned)((0x100000000ULL + d.bs0 - 1) / d.bs0) : 0u;
+        rc.mul_ue0 = d.ue0 > 1 ? (unsigned)((0x100000000ULL + d.ue0 - 1) / d.ue0) : 0u;
+        const long long rgrid = (n_users + kRowsWarps - 1) / kRowsWarps;
+        if (rgrid > 0x7fffffffLL) return fail(DMK_ERR_INVALID_ARG, "grid too large: split the user range");
+        const dim3 gr((unsigned)rgrid), bl(kRowsWarps * 32);
+        if (d.K <= 1)      fd_rows_kernel<1><<<gr, bl, 0, st>>>(d, rc);
+        else if (d.K <= 2) fd_rows_kernel<2><<<gr, bl, 0, st>>>(d, rc);
+        else if (d.K <= 4) fd_rows_kernel<4><<<gr, bl, 0, st>>>(d, rc);
+        else               fd_rows_kernel<8><<<gr, bl, 0, st>>>(d, rc);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return cuda_fail(e, "fd_rows_kernel launch");
+        g_launches.fetch_add(1);
+        snprintf(g_kernel, sizeof(g_kernel), "fd_rows_kernel<warp/user,lanes=rows,K<=%d> grid=%lld", d.K <= 1 ? 1 : (d.K <= 2 ? 2 : (d.K <= 4 ? 4 : 8)), rgrid);
+        return DMK_OK;
+    }
     FastCfg cfg;
     size_t fast_smem = 0;
     {

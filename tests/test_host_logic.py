@@ -42,7 +42,7 @@ def test_kernel_hint_mapping(monkeypatch):
     from deepmimo_b200 import _lib
     monkeypatch.delenv("DMK_FD_KERNEL", raising=False)
     assert _lib.kernel_hint_from_env() == 0
-    for name, val in (("tile", 1), ("ffma", 2), ("tc", 3), ("tc1", 4), ("small", 5), ("small1", 6), ("mma", 7), ("auto", 0), ("TC", 3)):
+    for name, val in (("tile", 1), ("ffma", 2), ("tc", 3), ("tc1", 4), ("small", 5), ("small1", 6), ("mma", 7), ("rows", 8), ("auto", 0), ("TC", 3)):
         monkeypatch.setenv("DMK_FD_KERNEL", name)
         assert _lib.kernel_hint_from_env() == val
     monkeypatch.setenv("DMK_FD_KERNEL", "fastest")
@@ -50,7 +50,7 @@ def test_kernel_hint_mapping(monkeypatch):
         _lib.kernel_hint_from_env()
     src = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "dmk.h")).read()
     for name, val in (("DMK_KERNEL_TILE", 1), ("DMK_KERNEL_FFMA", 2), ("DMK_KERNEL_TC ", 3), ("DMK_KERNEL_TC1", 4), ("DMK_KERNEL_SMALL ", 5),
-                      ("DMK_KERNEL_SMALL1", 6), ("DMK_KERNEL_MMA", 7)):
+                      ("DMK_KERNEL_SMALL1", 6), ("DMK_KERNEL_MMA", 7), ("DMK_KERNEL_ROWS", 8)):
         assert f"{name.strip()}" in src and f"= {val}" in src.split(name.strip())[1][:12], name
 
 
