@@ -316,7 +316,7 @@ int dmk_channels_fd(const dmk_desc* desc, const float* power_dbw, const float* p
     const bool tc_shape = (d.M >= 64 || n_chunks_u >= 128) && !d.fov_any;
     // Per-user outputs of at most 128 KB go to the warp-level tensor-core kernel (dmk_fd_mma.cuh) instead: the persistent kernel is
     // bound by its helper warps there (8x8 x K=64: 1.4 against 3.5 TB/s, 16x1 x K=1024: 3.46 against 3.61; profiles/README.md).
-    const bool mma_shape = affine && !d.has_time_axis && d.M <= 256 && d.K <= 4096 &&
+    const bool mma_shape = affine && !d.has_time_axis && d.M <= 1024 && d.bs0 < 65536 && d.bs1 < 65536 && d.ue0 < 65536 && d.ue1 < 65536 && d.K <= 4096 &&
                            ((reinterpret_cast<uintptr_t>(out_c64) & 15) == 0);
     const bool mma_pref = mma_shape && hint == DMK_KERNEL_AUTO && (long long)d.M * d.K * 8 <= 128 * 1024;
     const bool use_tc = !mma_pref && affine && !d.has_time_axis && div_ok && (d.K % (kTcN / 2) == 0) && d.K <= 4096 &&
@@ -416,11 +416,11 @@ int dmk_channels_fd(const dmk_desc* desc, const float* power_dbw, const float* p
             return DMK_OK;
         }
     }
-    // Small per-user outputs (M <= 256, K <= 4096): warp-level tensor-core kernel, see dmk_fd_mma.cuh.  Default up to 128 KB per user,
+    // Small per-user outputs (M <= 1024, K <= 4096): warp-level tensor-core kernel, see dmk_fd_mma.cuh.  Default up to 128 KB per user,
     // and for every eligible shape the persistent kernel did not take (FoV-filtered scenarios, fewer than 128 chunks per user);
     // DMK_KERNEL_MMA forces it on every eligible shape, DMK_KERNEL_SMALL keeps the CUDA-core fd_small2_kernel.
     {
-        const bool mma_wanted = hint == DMK_KERNEL_MMA || mma_pref || (hint == DMK_KERNEL_AUTO && (long long)d.M * d.K * 8 <= 256 * 1024);
+        const bool mma_wanted = hint == DMK_KERNEL_MMA || mma_pref || (hint == DMK_KERNEL_AUTO && (long long)d.M * d.K * 8 <= 512 * 1024);
         if (mma_shape && mma_wanted) {
             MmaCfg mc;
             memset(&mc, 0, sizeof(mc));
@@ -438,7 +438,14 @@ int dmk_channels_fd(const dmk_desc* desc, const float* power_dbw, const float* p
             mc.R = d.M * mc.S;
             mc.n_mt = (mc.R + 15) / 16;
             mc.mul_s = mc.S > 1 ? (unsigned)((0x100000000ULL + mc.S - 1) / mc.S) : 0u;
-            const int sb = mc.S % 8 == 0 ? 8 : (mc.S % 4 == 0 ? 4 : 0);      // chunks of one antenna row that share a base phasor
+            // chunks that share a base phasor: SB consecutive segments of one antenna row, or -- rows of 1 or 2 chunks (16 / 32
+            // subcarriers) -- all segments of SB / S consecutive elements along the panel's y axis
+            int sb = mc.S % 8 == 0 ? 8 : (mc.S % 4 == 0 ? 4 : 0);
+            mc.lg_blk_seg = sb == 8 ? 3 : 2;
+            if (sb == 0 && (mc.S == 1 || mc.S == 2)) {
+                if (d.bs0 % (8 / mc.S) == 0) sb = 8; else if (d.bs0 % (4 / mc.S) == 0) sb = 4;
+                mc.lg_blk_seg = mc.S == 2 ? 1 : 0;
+            }
             mc.G = mc.n_mt < 2 ? mc.n_mt : 2;                        // two m-tiles per group: measured best for both chunk widths
             if (desc->ws_split > 0 && desc->ws_split < 100) mc.G = desc->ws_split < mc.n_mt ? desc->ws_split : mc.n_mt;
             size_t off = 0;
@@ -448,7 +455,7 @@ int dmk_channels_fd(const dmk_desc* desc, const float* power_dbw, const float* p
             mc.off_list = take((size_t)32);
             mc.off_meta = take((size_t)(3 * kMmWindow + 1) * sizeof(int));
             mc.warp_bytes = (int)off;
-            mc.off_warps = (int)((((size_t)4 * d.M + mc.S) * sizeof(double) + 15) & ~size_t(15));
+            mc.off_warps = (int)(((d.M > 256 ? (((size_t)d.M * 8 + 15) & ~size_t(15)) : (size_t)d.M * 32) + (size_t)mc.S * sizeof(double) + 15) & ~size_t(15));
             const size_t mma_smem = (size_t)mc.off_warps + off * kMmWarps;
             const bool pair = nt == 4 && mc.n_mt >= 4 && mc.G >= 2;               // two m-tiles per k-step share the B fragments (123 registers)
             // float32 inputs, no FoV filter, isotropic patterns: instantiation without the float64-input / angle / dipole code

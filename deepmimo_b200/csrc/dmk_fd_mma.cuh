@@ -20,7 +20,7 @@
 //   3. chain round, lane = dense pair: the three float64 chains + combine; the user's largest |c_p| (a power of two, by a masked
 //      warp reduction over the lanes of the same user) scales the operands into FP16 range and is undone at the store;
 //   4. operand rows, still lane = path: F (J columns: products of two phasor levels) and, per group of G m-tiles, L (blocks of SB
-//      consecutive chunks of one antenna row share a base phasor -- gain x steering x coarse delay in ONE float64-reduced argument --
+//      consecutive chunks -- of one antenna row, or of SB / S consecutive elements along y when a row has S < SB chunks -- share a base phasor -- gain x steering x coarse delay in ONE float64-reduced argument --
 //      times SB block phasors), each split into FP16 hi + lo and stored in fragment order, path index fastest;
 //   5. per user and m-tile: fragments by 16- and 8-byte shared loads that land in consecutive registers (a lane's two paths of a
 //      k-step are adjacent pool slots), 3 MMAs (hi hi + lo hi + hi lo) per (n-tile, k-step), 16-byte stores.
@@ -45,6 +45,8 @@ struct MmaCfg {
     int n_mt;                         // m-tiles per user = ceil(R / 16)
     int S, R;                         // chunks per antenna row (ceil(K / J)), chunks per user
     int ragged;                       // K % J != 0
+    int lg_blk_seg;                   // log2 of the segments a block of SB chunks spans: SB when S % SB == 0 (one antenna row), else S (a block
+                                      // then holds SB / S consecutive elements along the panel's y axis -- 16 or 32 subcarriers: S = 1 or 2)
     int users_per_warp;               // 0: guided draws (8 / 4 / 2 users); > 0 pins the draw size
     unsigned draw8_above, draw4_above; // users left in the launch above which a warp draws 8 / 4 users
     unsigned mul_s;                   // ceil(2^32 / S) (S > 1): chunk -> antenna row by a multiply-high
@@ -175,13 +177,20 @@ fd_mma_kernel(const __grid_constant__ DevDesc d, const __grid_constant__ MmaCfg 
 {
     constexpr int J = 4 * NT;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    double (*s_coef)[4] = reinterpret_cast<double (*)[4]>(smem_raw);     // [M] element m -> (y_t, z_t, y_r, z_r) panel coordinates
-    double* s_k0 = reinterpret_cast<double*>(smem_raw) + 4 * d.M;        // [S] chunk segment -> subcarrier offset of its first column
+    // element m -> (y_t, z_t, y_r, z_r) panel coordinates: float64 [M][4] up to 256 elements, 16-bit [M][4] for larger panels (8 KB
+    // instead of 32 KB at M = 1024; converted at every use)
+    const bool wide = d.M > 256;
+    double (*s_coef)[4] = reinterpret_cast<double (*)[4]>(smem_raw);
+    ushort4* s_coef16 = reinterpret_cast<ushort4*>(smem_raw);
+    double* s_k0 = reinterpret_cast<double*>(smem_raw + (wide ? (((size_t)d.M * 8 + 15) & ~size_t(15)) : (size_t)d.M * 32));   // [S] chunk segment -> subcarrier offset of its first column
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int m = tid; m < d.M; m += kMmWarps * 32) {
         const int r = m / d.Mt, t = m - r * d.Mt;
-        s_coef[m][0] = (double)(t % d.bs0); s_coef[m][1] = (double)(t / d.bs0);
-        s_coef[m][2] = (double)(r % d.ue0); s_coef[m][3] = (double)(r / d.ue0);
+        if (wide) s_coef16[m] = make_ushort4((unsigned short)(t % d.bs0), (unsigned short)(t / d.bs0), (unsigned short)(r % d.ue0), (unsigned short)(r / d.ue0));
+        else {
+            s_coef[m][0] = (double)(t % d.bs0); s_coef[m][1] = (double)(t / d.bs0);
+            s_coef[m][2] = (double)(r % d.ue0); s_coef[m][3] = (double)(r / d.ue0);
+        }
     }
     for (int s = tid; s < cfg.S; s += kMmWarps * 32) s_k0[s] = (double)d.subc_start + (double)d.subc_step * (double)(J * s);
 
@@ -355,7 +364,8 @@ fd_mma_kernel(const __grid_constant__ DevDesc d, const __grid_constant__ MmaCfg 
             if constexpr (SB > 0) {
                 wb[0] = make_float2(1.f, 0.f);
                 #pragma unroll
-                for (int i = 1; i < SB; ++i) wb[i] = phasor_cycles_sfu(-(st.wcyc * (kstep * (double)(J * i))));
+                for (int i = 1; i < SB; ++i)                                      // chunk i of a block: antenna step i >> lg along y, segment i & mask
+                    wb[i] = phasor_cycles_sfu(fma((double)(i >> cfg.lg_blk_seg), st.u[0], -(st.wcyc * (kstep * (double)(J * (i & ((1 << cfg.lg_blk_seg) - 1)))))));
             }
         }
         float2* out_pass = d.out + cur * (long long)M * K;
@@ -370,8 +380,10 @@ fd_mma_kernel(const __grid_constant__ DevDesc d, const __grid_constant__ MmaCfg 
                         r = min(r, (unsigned)(cfg.R - 1));
                         const unsigned m = cfg.mul_s ? __umulhi(r, cfg.mul_s) : r;
                         const unsigned seg = r - m * (unsigned)cfg.S;
-                        const double cyc = fma(s_coef[m][0], st.u[0], fma(s_coef[m][1], st.v[0], fma(s_coef[m][2], st.u[1],
-                                           fma(s_coef[m][3], st.v[1], -(st.wcyc * s_k0[seg])))));
+                        double c0, c1, c2, c3;
+                        if (wide) { const ushort4 q = s_coef16[m]; c0 = (double)q.x; c1 = (double)q.y; c2 = (double)q.z; c3 = (double)q.w; }
+                        else      { c0 = s_coef[m][0]; c1 = s_coef[m][1]; c2 = s_coef[m][2]; c3 = s_coef[m][3]; }
+                        const double cyc = fma(c0, st.u[0], fma(c1, st.v[0], fma(c2, st.u[1], fma(c3, st.v[1], -(st.wcyc * s_k0[seg])))));
                         return cmul(cs, phasor_cycles_sfu(cyc));
                     };
                     const unsigned r0 = (unsigned)(mt0 + ml) * 16u;

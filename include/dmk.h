@@ -92,7 +92,7 @@ typedef enum dmk_kernel_hint {
     DMK_KERNEL_TC1   = 4,   /* one-CTA-per-user tcgen05 kernel                                      */
     DMK_KERNEL_SMALL = 5,   /* small-array kernel (M <= 16), densely packed                         */
     DMK_KERNEL_SMALL1 = 6,  /* round-1 small-array kernel (one warp per user), kept for A/B timing  */
-    DMK_KERNEL_MMA   = 7,   /* warp-level tensor-core kernel for small per-user outputs (M <= 256, K <= 4096) */
+    DMK_KERNEL_MMA   = 7,   /* warp-level tensor-core kernel for small per-user outputs (M <= 1024, K <= 4096) */
     DMK_KERNEL_ROWS  = 8    /* warp-per-user kernel with lanes = antenna rows for K <= 8 selected subcarriers  */
 } dmk_kernel_hint;
 

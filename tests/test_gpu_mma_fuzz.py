@@ -32,6 +32,10 @@ CASES = [
     ((2, 2), (2, 2), 2048, 5 + 3 * np.arange(301), 75, None, ("halfwave-dipole", "isotropic"), 10, True, True, 25, False),
     ((1, 1), (1, 1), 512, np.arange(1), 50, None, ("isotropic", "isotropic"), 25, False, False, 25, False),
     ((16, 1), (1, 1), 1024, np.arange(1000), 33, None, ("isotropic", "isotropic"), 25, False, False, 25, False),
+    # panels of more than 256 elements (16-bit coordinate table) with few subcarriers
+    ((32, 8), (2, 2), 512, np.arange(16), 21, None, ("isotropic", "isotropic"), 25, False, True, 25, False),                       # M = 1024
+    ((16, 16), (2, 1), 512, 4 + 2 * np.arange(32), 19, ((150, 100), (180, 120)), ("isotropic", "isotropic"), 25, True, False, 25, False),   # M = 512
+    ((32, 8), (2, 2), 64, np.arange(48), 9, None, ("halfwave-dipole", "isotropic"), 25, True, False, 25, False),
 ]
 
 
