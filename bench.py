@@ -38,12 +38,14 @@ UNIT = "coef/s"
 # sensitivity variants: every user with all 25 paths, config 3 without its FoV filter.
 WORKLOADS = {"cfg1": (1, {}), "cfg2": (2, {}), "cfg3": (3, {}), "cfg4": (4, {}), "cfg5": (5, {}),
              "cfg2_dense": (2, {"dense": True}), "cfg5_dense": (5, {"dense": True}), "cfg3_nofov": (3, {"fov": False}),
-             "mid_8x8_K64": (6, {})}      # 64 antennas x 64 subcarriers, 32 KB per user
+             "mid_8x8_K64": (6, {}),      # 64 antennas x 64 subcarriers, 32 KB per user
+             "default_8x8_K1": (7, {}),   # the reference's default OFDM parameters: one selected subcarrier
+             "td_8x8_static": (8, {})}    # the reference's own time-domain mode (no time axis)
 # --impl reference: users per host core in one step (about 3 s of NumPy work per core at the default K + W)
-CPU_SAMPLE_USERS = {1: 12000, 2: 24, 3: 48, 4: 3000, 5: 160, 6: 1500}
+CPU_SAMPLE_USERS = {1: 12000, 2: 24, 3: 48, 4: 3000, 5: 160, 6: 1500, 7: 12000, 8: 6000}
 # cpu_baseline leg of the b200 arm: one core, about 10-30 s of NumPy work
-CPU_BASELINE_USERS = {1: 80000, 2: 128, 3: 256, 4: 20000, 5: 1024, 6: 10000}
-DEFAULT_USERS = {1: 80_000, 2: 4096, 3: 8192, 4: 50_000, 5: 200_000, 6: 131_072}      # SURVEY.md 8 size table (per GPU)
+CPU_BASELINE_USERS = {1: 80000, 2: 128, 3: 256, 4: 20000, 5: 1024, 6: 10000, 7: 80000, 8: 40000}
+DEFAULT_USERS = {1: 80_000, 2: 4096, 3: 8192, 4: 50_000, 5: 200_000, 6: 131_072, 7: 200_000, 8: 200_000}      # SURVEY.md 8 size table (per GPU)
 FP32_LANES_PER_SM = 128
 PARITY_USERS = 64              # users pulled out of the timed buffers and compared with the oracle (untimed)
 
@@ -525,7 +527,7 @@ def gpu_main(args):
     if args.others:
         # the city-scale configuration runs at EVERY N (one base station per rank through the sharding path); the remaining
         # shapes and the sensitivity variants only at N = 1
-        names = ["cfg5"] if world > 1 else ["cfg1", "cfg3", "cfg4", "cfg5", "cfg2_dense", "cfg5_dense", "cfg3_nofov", "mid_8x8_K64"]
+        names = ["cfg5"] if world > 1 else ["cfg1", "cfg3", "cfg4", "cfg5", "cfg2_dense", "cfg5_dense", "cfg3_nofov", "mid_8x8_K64", "default_8x8_K1", "td_8x8_static"]
         for w in [w for w in names if w != args.workload]:
             try:
                 r = run_workload(w, None, 5, 3, rank, world, dist, flush, want_clocks=True)

@@ -159,6 +159,18 @@ def _scenario(cfg: int, n_ue: Optional[int], bs_index: int, so: int, dense: bool
         return Scenario("mid_8x8_K64", d, _params([8, 8], [1, 1], 64, 64, 10e6, bs_rot=[5, 10, 15]),
                         notes="not a BASELINE config: the common 64 antennas x 64 subcarriers dataset (32 KB per user), 8x8 rotated BS UPA, "
                               "1 UE antenna, N=K=64, B=10 MHz (no path beyond the OFDM symbol)")
+    if cfg == 7:
+        n = 200_000 if n_ue is None else n_ue
+        d = make_paths(n, 1007 + so, n_sc=512, bandwidth=10e6, dense=dense)
+        return Scenario("default_8x8_K1", d, _params([8, 8], [1, 1], 512, 1, 10e6),
+                        notes="not a BASELINE config: the reference's default OFDM parameters (512 subcarriers, ONE selected, channel.py:58-62) "
+                              "on an 8x8 BS panel: 512 bytes of output per user")
+    if cfg == 8:
+        n = 200_000 if n_ue is None else n_ue
+        d = make_paths(n, 1008 + so, n_sc=512, bandwidth=10e6, dense=dense)
+        return Scenario("td_8x8_static", d, _params([8, 8], [1, 1], 512, 1, 10e6, freq_domain=0),
+                        notes="not a BASELINE config: the reference's own time-domain mode (freq_domain = 0, no time axis), 8x8 BS panel, "
+                              "25 path slots: 12.8 KB of output per user")
     raise ValueError(f"unknown config {cfg}")
 
 
