@@ -426,8 +426,11 @@ int dmk_channels_fd(const dmk_desc* desc, const float* power_dbw, const float* p
             memset(&mc, 0, sizeof(mc));
             // chunk width J = 32 where the chunks of an antenna row still share base phasors in blocks of >= 4 (K / 32 a multiple of 4)
             // and a user has >= 256 chunks of 16; else 16 (measured: tools/mma_sweep.py, profiles/README.md)
-            int J = (d.K % 128 == 0 && (long long)d.M * d.K / 16 >= 256) ? 32 : 16;
-            if (desc->ws_helpers == 16 || (desc->ws_helpers == 32 && d.K % 32 == 0)) J = desc->ws_helpers;      // A/B timing
+            // (rows of ceil(K / 32) chunks that are a multiple of 4, or padded to one at a cost of at most a third, see below)
+            const int s32 = (d.K + 31) / 32;
+            const bool j32_blocks = s32 % 4 == 0 || 3 * ((s32 + 3) & ~3) <= 4 * s32;
+            int J = (j32_blocks && (long long)d.M * ((d.K + 15) / 16) >= 256) ? 32 : 16;
+            if (desc->ws_helpers == 16 || desc->ws_helpers == 32) J = desc->ws_helpers;      // A/B timing
             const int nt = J / 4;
             mc.S = (d.K + J - 1) / J;                                // the last chunk of a row may be cut off (K % J != 0)
             mc.ragged = d.K % J != 0;
