@@ -312,16 +312,19 @@ int dmk_channels_fd(const dmk_desc* desc, const float* power_dbw, const float* p
     const bool want_tc = hint == DMK_KERNEL_TC || hint == DMK_KERNEL_TC1;
     // Where the tensor-core kernels pay: at least one full stage of 128 chunks (512 B each) per user, or a panel of >= 64 elements.
     // FoV-sparse scenarios leave few paths per user (per-user overhead dominates): packed-FP32 kernel.  Measured: profiles/README.md.
-    const long long n_chunks_u = (long long)d.M * (d.K / (kTcN / 2));
+    const long long n_chunks_u = (long long)d.M * ((d.K + kTcN / 2 - 1) / (kTcN / 2));
     const bool tc_shape = (d.M >= 64 || n_chunks_u >= 128) && !d.fov_any;
     // Per-user outputs of at most 128 KB go to the warp-level tensor-core kernel (dmk_fd_mma.cuh) instead: the persistent kernel is
     // bound by its helper warps there (8x8 x K=64: 1.4 against 3.5 TB/s, 16x1 x K=1024: 3.46 against 3.61; profiles/README.md).
     const bool mma_shape = affine && !d.has_time_axis && d.M <= 1024 && d.bs0 < 65536 && d.bs1 < 65536 && d.ue0 < 65536 && d.ue1 < 65536 && d.K <= 4096 &&
                            ((reinterpret_cast<uintptr_t>(out_c64) & 15) == 0);
     const bool mma_pref = mma_shape && hint == DMK_KERNEL_AUTO && (long long)d.M * d.K * 8 <= 128 * 1024;
-    const bool use_tc = !mma_pref && affine && !d.has_time_axis && div_ok && (d.K % (kTcN / 2) == 0) && d.K <= 4096 &&
+    // K not a multiple of 64 (12 x n resource blocks ...): the persistent kernel cuts the last chunk of every row off; taken from
+    // 256 subcarriers up (at most a quarter of a segment wasted); the one-CTA-per-user kernel does not have that store path
+    const bool ws_rag = d.K % (kTcN / 2) != 0;
+    const bool use_tc = !mma_pref && affine && !d.has_time_axis && div_ok && (!ws_rag || (d.K >= 256 && hint != DMK_KERNEL_TC1)) && d.K <= 4096 &&
                         !want_tile && !want_ffma && hint != DMK_KERNEL_SMALL && hint != DMK_KERNEL_SMALL1 && hint != DMK_KERNEL_MMA && (tc_shape || want_tc);
-    const bool use_tc1 = use_tc && tc_smem <= (size_t)kSmemTc;            // one-CTA-per-user tensor-core kernel: fallback of the persistent one
+    const bool use_tc1 = use_tc && !ws_rag && tc_smem <= (size_t)kSmemTc;   // one-CTA-per-user tensor-core kernel: fallback of the persistent one
     const bool use_fast = !use_tc1 && affine && !d.has_time_axis && div_ok && fast_smem <= (size_t)kSmemFast && !want_tile;
     const int tile_w_tc1 = (kTcN / 2) * tcfg.nsub;
     const int tile_w = use_tc1 ? tile_w_tc1 : (use_fast ? kTKW : kTK);
@@ -341,7 +344,8 @@ int dmk_channels_fd(const dmk_desc* desc, const float* power_dbw, const float* p
         WsCfg w;
         memset(&w, 0, sizeof(w));
         const int pc = (d.P > 0 ? d.P : 1) + 1;                  // + the zero row the builders read for padding slots
-        w.S = d.K / (kTcN / 2);
+        w.S = (d.K + kTcN / 2 - 1) / (kTcN / 2);
+        w.rag = ws_rag ? 1 : 0; w.row_floats = 2 * d.K; w.last_valid = 2 * d.K - (w.S - 1) * kTcN;
         const long long n_chunks = (long long)d.M * w.S;
         w.n_chunks = (int)n_chunks;
         w.n_stages = (int)((n_chunks + kTcN - 1) / kTcN);

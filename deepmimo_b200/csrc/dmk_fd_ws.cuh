@@ -96,7 +96,8 @@ __device__ __forceinline__ void st_split8_f16_rowpair(unsigned char* hi, unsigne
 }
 
 // Flat-chunk formulation (round 2).  A user's output [M rows][K columns] complex64 is a flat array of 512-byte CHUNKS: chunk
-// c = m * S + seg holds the 64 subcarriers (128 floats) of segment seg of antenna row m, S = K / 64.  With the delay phasor split as
+// c = m * S + seg holds the 64 subcarriers (128 floats) of segment seg of antenna row m, S = K / 64 (K not a multiple of 64:
+// S = ceil(K / 64), the last chunk of a row is cut off -- ws_store_chunks_rag).  With the delay phasor split as
 //     W[p, 64 seg + j] = wS[p, seg] * wF[p, j],        wS = exp(-j 2 pi wcyc (start + 64 step seg)),  wF = exp(-j 2 pi wcyc step j)
 // the coarse factor moves to the antenna side:  H[c, j] = sum_p (A[m, p] wS[p, seg]) wF[p, j].  One tcgen05 stage then computes
 //     D[2j + s, n] = sum_{p, e} Mside[2j + s, 2p + e] * Nside[n, 2p + e]          n = chunk c0 + n, up to 128 chunks per stage
@@ -111,6 +112,7 @@ struct WsCfg {
     int sY, sQ, sB, sL, sS;                             // per-path table strides (float2 units), odd
     int S, n_chunks, n_stages;                          // segments per row, chunks per user, ceil(n_chunks / 128)
     int bufs_per_helper;                                // 2 or 3 user buffers per helper warp
+    int rag, row_floats, last_valid;                    // K % 64 != 0: S = ceil(K / 64); floats per antenna row (2 K); floats of a row's last chunk
     unsigned mul_mt, mul_bs0, mul_s;                    // ceil(2^32 / d) reciprocals (0: d == 1)
 };
 
@@ -223,6 +225,19 @@ __device__ __forceinline__ void ws_store_chunks(uint32_t taddr, float* out, int 
         #pragma unroll
         for (int i = 0; i < 32; ++i)
             if (first + i < rows) __stcs(out + i * kTcN, __uint_as_float(v[i]) * scale);
+    }
+}
+
+// K not a multiple of 64 (12 x n resource blocks: 300, 600, 624, 1200 ... subcarriers): a row has S = ceil(K / 64) chunks, the last one is
+// cut off at column K, and the chunks of consecutive rows are no longer 512 bytes apart (row pitch 2 K floats).  (m, seg) of the 32
+// chunks run as warp-uniform counters; `out` points at float q * 32 + lane of chunk `c0`, `lane_ok` = this float exists in a last chunk.
+__device__ __forceinline__ void ws_store_chunks_rag(const uint32_t (&v)[32], float* out, int seg, int S, int delta, int left, bool lane_ok, float scale)
+{
+    #pragma unroll
+    for (int i = 0; i < 32; ++i) {
+        if (i < left && (seg < S - 1 || lane_ok)) __stcs(out, __uint_as_float(v[i]) * scale);
+        out += kTcN;
+        if (++seg == S) { seg = 0; out += delta; }           // next antenna row: + 2 K - 128 S floats
     }
 }
 
@@ -456,7 +471,7 @@ fd_ws_kernel(const __grid_constant__ DevDesc d, const __grid_constant__ WsCfg cf
             const int ks = (int)(item % (unsigned)ksplit);
             const int np = ub.sh.np;
             const float scale = ub.scale;
-            float* out_u = reinterpret_cast<float*>(d.out) + user * (long long)n_chunks * kTcN;
+            float* out_u = reinterpret_cast<float*>(d.out) + user * (cfg.rag ? (long long)d.M * cfg.row_floats : (long long)n_chunks * kTcN);
 #ifdef DMK_TC_TRACE
             if (tid == 0) { if (!tr_first) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tr_first)); ++tr_users; }
 #endif
@@ -466,7 +481,38 @@ fd_ws_kernel(const __grid_constant__ DevDesc d, const __grid_constant__ WsCfg cf
                 if (d.valid_mask) d.valid_mask[o] = ub.m_valid[lane];
                 if (d.clip_mask)  d.clip_mask[o]  = ub.m_clip[lane];
             }
-            if (np == 0) {
+            if (cfg.rag) {
+                // cut-off last chunks: per-chunk addresses from running (row, segment) counters; zero users take the same route
+                const bool lane_ok = q * 32 + lane < cfg.last_valid;
+                const int delta = cfg.row_floats - cfg.S * kTcN;
+                for (int stg = ks; stg < n_stages; stg += ksplit) {
+                    const int rows = min(kTcN, n_chunks - stg * kTcN);
+                    uint32_t taddr = 0; unsigned ab = 0;
+                    if (np != 0) {
+                        ab = g & 1;
+                        mbar_wait(&bars.mma_done[ab], (g >> 1) & 1u);
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        taddr = tmem_base + ((uint32_t)(q * 32) << 16) + ab * (uint32_t)kTcN;
+                    }
+                    for (int r = 0; r < rows; r += 32) {
+                        const unsigned c0 = (unsigned)(stg * kTcN + r);
+                        const unsigned m0 = cfg.mul_s ? __umulhi(c0, cfg.mul_s) : c0;
+                        const int seg0 = (int)(c0 - m0 * (unsigned)cfg.S);
+                        uint32_t v[32];
+                        if (np != 0) { tmem_ld<32>(taddr + r, v); asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+                        else {
+                            #pragma unroll
+                            for (int i = 0; i < 32; ++i) v[i] = 0u;
+                        }
+                        ws_store_chunks_rag(v, out_u + (long long)m0 * cfg.row_floats + seg0 * kTcN + q * 32 + lane, seg0, cfg.S, delta, rows - r, lane_ok, np != 0 ? scale : 1.f);
+                    }
+                    if (np != 0) {
+                        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                        mbar_arrive(&bars.acc_empty[ab]);
+                        ++g;
+                    }
+                }
+            } else if (np == 0) {
                 // users without contributing paths: zeros (channel.py:257,:269-271); a stage is 64 KB of contiguous output
                 const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
                 for (int stg = ks; stg < n_stages; stg += ksplit) {

@@ -10,7 +10,7 @@ from util import per_user_rel_fro
 pytestmark = pytest.mark.gpu
 
 
-def _one(rng, monkeypatch, helpers):
+def _one(rng, monkeypatch, helpers, ragged=False):
     import torch
     import deepmimo_b200 as dmb
     from deepmimo_b200 import _lib
@@ -25,6 +25,8 @@ def _one(rng, monkeypatch, helpers):
     step = int(rng.choice([1, 1, 2, 3]))
     start = int(rng.integers(0, 5))
     k = 64 * nseg
+    if ragged:                                          # K not a multiple of 64: cut-off last chunk of every antenna row (K >= 256)
+        k = int(rng.choice([257, 300, 330, 383, 450, 600, 624, 1000]))
     n_sc = int(2 ** np.ceil(np.log2(start + step * k + 1)))
     n = int(rng.choice([1, 3, 50, 290, 300, 700, 2500]))
     n = max(1, min(n, (1 << 28) // (8 * m * k)))
@@ -59,4 +61,15 @@ def test_ws_kernel_random_shapes_match_fp32_kernel(helpers, monkeypatch):
     seen = set()
     for _ in range(24):
         seen.add(_one(rng, monkeypatch, helpers).split("<")[0])
+    assert "fd_ws_kernel" in seen
+
+
+@pytest.mark.parametrize("helpers", ["1", "4"])
+def test_ws_kernel_subcarrier_counts_that_are_not_multiples_of_64(helpers, monkeypatch):
+    """12 x n resource blocks (300, 600, 624 ...) and odd counts: the persistent kernel cuts the last chunk of every row off
+    (ws_store_chunks_rag); zero-path users go through the same store route."""
+    rng = np.random.default_rng(4048 + int(helpers))
+    seen = set()
+    for _ in range(16):
+        seen.add(_one(rng, monkeypatch, helpers, ragged=True).split("<")[0])
     assert "fd_ws_kernel" in seen
