@@ -32,7 +32,8 @@ fd_rows_kernel(const __grid_constant__ DevDesc d, const __grid_constant__ RowsCf
     float2 (*tw)[KM] = s_w[warp];
     const int K = d.K;
 
-    // ---- chains, lane = path column
+    // ---- chains, lane = path column (a single-element unrotated side -- the reference's default UE -- skips its chain)
+    const bool triv0 = side_angles_trivial(d, 0), triv1 = side_angles_trivial(d, 1);
     PathState st;
     const bool active = lane < d.P0;
     st.contrib = false; st.valid = false; st.fov = true; st.over = false;
@@ -40,7 +41,7 @@ fd_rows_kernel(const __grid_constant__ DevDesc d, const __grid_constant__ RowsCf
     if (active) {
         SideOut s0, s1; GainOut g;
         if (prologue_needs_angles(d)) { prologue_side<true>(d, user, lane, 0, s0, d.Mt > 1);  prologue_side<true>(d, user, lane, 1, s1, d.Mr > 1); }
-        else                          { prologue_side<false>(d, user, lane, 0, s0, d.Mt > 1); prologue_side<false>(d, user, lane, 1, s1, d.Mr > 1); }
+        else                          { prologue_side_auto<false>(d, user, lane, 0, s0, d.Mt > 1, triv0); prologue_side_auto<false>(d, user, lane, 1, s1, d.Mr > 1, triv1); }
         prologue_gain<true>(d, user, lane, g);
         prologue_combine<true>(d, s0, s1, g, st);
         const long long o = user * (long long)d.P0 + lane;

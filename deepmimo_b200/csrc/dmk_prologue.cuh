@@ -197,6 +197,18 @@ __device__ __forceinline__ void prologue_side(const DevDesc& d, long long user, 
     o.gain = 1.0;
 }
 
+// prologue_side with the short chain where the side's angles are trivial (side_angles_trivial, evaluated once per kernel)
+template <bool kNeedAngles>
+__device__ __forceinline__ void prologue_side_auto(const DevDesc& d, long long user, int p, int side, SideOut& o, bool steer, bool triv)
+{
+    if (triv) {
+        const long long off = user * (long long)d.ld + p;
+        prologue_side_trivial(d.el[side][off], d.az[side][off], o);
+    } else {
+        prologue_side<kNeedAngles>(d, user, p, side, o, steer);
+    }
+}
+
 // float32 inputs: the gain chain from loaded values
 template <bool kFreqDomain>
 __device__ __forceinline__ void prologue_gain_f32(const DevDesc& d, int p, float pw_db, float phase_deg, float delay_s, float doppler, GainOut& g)

@@ -166,6 +166,7 @@ td_warp_kernel(const __grid_constant__ DevDesc d)
     const int lane = threadIdx.x & 31;
     const long long user = (long long)blockIdx.x * kTdwWarps + (threadIdx.x >> 5);
     if (user >= d.n_users) return;                          // warp-uniform
+    const bool triv0 = side_angles_trivial(d, 0), triv1 = side_angles_trivial(d, 1);
     PathState st;
     const bool active = lane < d.P0;
     st.contrib = false; st.valid = false; st.fov = true; st.over = false;
@@ -173,7 +174,7 @@ td_warp_kernel(const __grid_constant__ DevDesc d)
     if (active) {
         SideOut s0, s1; GainOut g;
         if (prologue_needs_angles(d)) { prologue_side<true>(d, user, lane, 0, s0, d.Mt > 1);  prologue_side<true>(d, user, lane, 1, s1, d.Mr > 1); }
-        else                          { prologue_side<false>(d, user, lane, 0, s0, d.Mt > 1); prologue_side<false>(d, user, lane, 1, s1, d.Mr > 1); }
+        else                          { prologue_side_auto<false>(d, user, lane, 0, s0, d.Mt > 1, triv0); prologue_side_auto<false>(d, user, lane, 1, s1, d.Mr > 1, triv1); }
         prologue_gain<false>(d, user, lane, g);
         prologue_combine<false>(d, s0, s1, g, st);
     }

@@ -39,7 +39,7 @@ def test_rows_kernel_matches_oracle(case):
         rng = np.random.default_rng(77 + case)
         for k in ("power", "phase", "delay", "aoa_az", "aoa_el", "aod_az", "aod_el"):
             d[k] = d[k].astype(np.float64) * (1.0 + 1e-9 * rng.standard_normal(d[k].shape))
-    ue_rot = np.random.default_rng(50 + case).uniform(-60, 60, (n, 3)) if per_user else np.array([10, -20, 30])
+    ue_rot = np.random.default_rng(50 + case).uniform(-60, 60, (n, 3)) if per_user else (np.array([0, 0, 0]) if case in (0, 1) else np.array([10, -20, 30]))      # cases 0, 1: the default UE (short chain)
     p = {"bs_antenna": {"shape": np.array(bs), "spacing": 0.5, "rotation": np.array([5, 10, 20]), "radiation_pattern": pats[0]},
          "ue_antenna": {"shape": np.array(ue), "spacing": 0.4, "rotation": ue_rot, "radiation_pattern": pats[1]},
          "enable_doppler": 0, "enable_dual_polar": 0, "num_paths": num_paths, "freq_domain": 1,
