@@ -318,11 +318,12 @@ int dmk_channels_fd(const dmk_desc* desc, const float* power_dbw, const float* p
     // bound by its helper warps there (8x8 x K=64: 1.4 against 3.5 TB/s, 16x1 x K=1024: 3.46 against 3.61; profiles/README.md).
     const bool mma_shape = affine && !d.has_time_axis && d.M <= 1024 && d.bs0 < 65536 && d.bs1 < 65536 && d.ue0 < 65536 && d.ue1 < 65536 && d.K <= 4096 &&
                            ((reinterpret_cast<uintptr_t>(out_c64) & 15) == 0);
-    const bool mma_pref = mma_shape && hint == DMK_KERNEL_AUTO && (long long)d.M * d.K * 8 <= 128 * 1024;
+    const bool ws_rag = d.K % (kTcN / 2) != 0;           // the persistent kernel would cut the last chunk of every row off
+    const bool mma_pref = mma_shape && hint == DMK_KERNEL_AUTO && (long long)d.M * d.K * 8 <= (ws_rag ? 256 : 128) * 1024;
     // K not a multiple of 64 (12 x n resource blocks ...): the persistent kernel cuts the last chunk of every row off; taken while the
-    // padding is at most a quarter of K; the one-CTA-per-user kernel does not have that store path
-    const bool ws_rag = d.K % (kTcN / 2) != 0;
-    const bool use_tc = !mma_pref && affine && !d.has_time_axis && div_ok && (!ws_rag || (4 * (((d.K + 63) / 64) * 64 - d.K) <= d.K && hint != DMK_KERNEL_TC1)) && d.K <= 4096 &&
+    // padding is at most half of K (it is bound by its stores, and only valid columns are stored: K = 88 on a 1024-element panel
+    // 3.7 against 2.4 TB/s; tools/rag_ab.py) and above 256 KB per user; the one-CTA-per-user kernel does not have that store path
+    const bool use_tc = !mma_pref && affine && !d.has_time_axis && div_ok && (!ws_rag || (2 * (((d.K + 63) / 64) * 64 - d.K) <= d.K && hint != DMK_KERNEL_TC1)) && d.K <= 4096 &&
                         !want_tile && !want_ffma && hint != DMK_KERNEL_SMALL && hint != DMK_KERNEL_SMALL1 && hint != DMK_KERNEL_MMA && (tc_shape || want_tc);
     const bool use_tc1 = use_tc && !ws_rag && tc_smem <= (size_t)kSmemTc;   // one-CTA-per-user tensor-core kernel: fallback of the persistent one
     const bool use_fast = !use_tc1 && affine && !d.has_time_axis && div_ok && fast_smem <= (size_t)kSmemFast && !want_tile;

@@ -25,8 +25,8 @@ def _one(rng, monkeypatch, helpers, ragged=False):
     step = int(rng.choice([1, 1, 2, 3]))
     start = int(rng.integers(0, 5))
     k = 64 * nseg
-    if ragged:                                          # K not a multiple of 64: cut-off last chunk of every antenna row (padding <= K / 4)
-        k = int(rng.choice([120, 180, 257, 300, 330, 383, 450, 600, 624, 1000]))
+    if ragged:                                          # K not a multiple of 64: cut-off last chunk of every antenna row (padding <= K / 2)
+        k = int(rng.choice([88, 100, 120, 180, 257, 300, 330, 383, 450, 600, 624, 1000]))
     n_sc = int(2 ** np.ceil(np.log2(start + step * k + 1)))
     n = int(rng.choice([1, 3, 50, 290, 300, 700, 2500]))
     n = max(1, min(n, (1 << 28) // (8 * m * k)))
