@@ -170,8 +170,8 @@ __device__ __forceinline__ void mm_consume(const unsigned char* sAh, const unsig
 // the instantiation without the float64-input, angle (acos / atan2) and dipole code is half the size, which the instruction fetch of
 // 18 warps in different phases of a ~2 500-instruction pass feels.
 template <int NT, int SB, int MP, bool kPlain>
-// MP = 1: 96 registers: 7 CTAs = 21 warps per SM with the 8.4 KB pools of J = 16 (a minimum-blocks launch bound makes ptxas stop at 80 and
-// spill: measured 13 % slower); J = 32 is limited by its pools, not by registers.
+// MP = 1: 96 registers: 6 CTAs = 18 warps per SM with the 8.4 - 12.4 KB pools of J = 16 (a minimum-blocks launch bound makes ptxas stop at
+// 80 and spill: measured 13 % slower; 80 registers without spilling buy 24 warps and no time); J = 32 is limited by its pools.
 __global__ void __maxnreg__(NT == 4 ? (MP == 2 ? 128 : 96) : 168)
 fd_mma_kernel(const __grid_constant__ DevDesc d, const __grid_constant__ MmaCfg cfg, unsigned int* ticket)
 {
