@@ -72,3 +72,22 @@ def test_pinned_cap_env(monkeypatch):
     assert pinned_cap_bytes() == 16 << 30
     monkeypatch.setenv("DMK_PINNED_CAP_GIB", "0.5")
     assert pinned_cap_bytes() == 1 << 29
+
+
+def test_bench_workloads_are_consistent_and_scenarios_build():
+    """Every bench workload names a scenario the generator knows, with user counts for the GPU leg and both CPU legs; the oracle
+    runs on a handful of its users (the parity block of the bench does exactly that)."""
+    import importlib.util
+    import numpy as np
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(root, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    from deepmimo_b200.synth import scenario, coef_count
+    from util import oracle_on_users
+    for name, (cfg, var) in bench.WORKLOADS.items():
+        assert cfg in bench.DEFAULT_USERS and cfg in bench.CPU_SAMPLE_USERS and cfg in bench.CPU_BASELINE_USERS, name
+        s = scenario(cfg, 6, **var)
+        assert coef_count(s) > 0
+        o = oracle_on_users(s, np.arange(3), procs=1)
+        assert o["H"].shape[0] == 3 and not np.isnan(o["H"].view(np.float32)).any(), name
