@@ -20,7 +20,10 @@ namespace {
 
 thread_local char g_err[512] = "";
 thread_local char g_kernel[192] = "";
-std::atomic<unsigned> ticket_seq{0};          // launches in flight use different slots of g_tc_ticket
+// Launches in flight use different slots of g_tc_ticket: the persistent tcgen05 kernel one counter out of the lower half, the warp-level
+// tensor-core kernel a (next user, finished warps) pair out of the upper half -- 256 and 128 launches, both >= the 128 grids a device
+// runs concurrently, and the two families never share a slot.
+std::atomic<unsigned> ticket_seq{0};
 std::atomic<long long> g_launches{0};
 
 int fail(int code, const char* fmt, ...)
@@ -410,7 +413,7 @@ int dmk_channels_fd(const dmk_desc* desc, const float* power_dbw, const float* p
             at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
             at[0].val.programmaticStreamSerializationAllowed = 1;
             lc.attrs = at; lc.numAttrs = 1;
-            unsigned int* tk = tickets + (ticket_seq.fetch_add(1) % kTcTickets);
+            unsigned int* tk = tickets + (ticket_seq.fetch_add(1) % (kTcTickets / 2));
             if (n_helpers == 1)      e = cudaLaunchKernelEx(&lc, fd_ws_kernel<1>, d, w, (int)wsplit, (unsigned)items, tk, pdl_wait);
             else if (n_helpers == 2) e = cudaLaunchKernelEx(&lc, fd_ws_kernel<2>, d, w, (int)wsplit, (unsigned)items, tk, pdl_wait);
             else                     e = cudaLaunchKernelEx(&lc, fd_ws_kernel<4>, d, w, (int)wsplit, (unsigned)items, tk, pdl_wait);
@@ -495,7 +498,7 @@ int dmk_channels_fd(const dmk_desc* desc, const float* power_dbw, const float* p
                 unsigned int* tickets = nullptr;
                 cudaError_t e0 = cudaGetSymbolAddress(reinterpret_cast<void**>(&tickets), g_tc_ticket);
                 if (e0 != cudaSuccess) return cuda_fail(e0, "cudaGetSymbolAddress(g_tc_ticket)");
-                kern<<<(unsigned)sgrid, kMmWarps * 32, mma_smem, st>>>(d, mc, tickets + 2 * (ticket_seq.fetch_add(1) % (kTcTickets / 2)));
+                kern<<<(unsigned)sgrid, kMmWarps * 32, mma_smem, st>>>(d, mc, tickets + kTcTickets / 2 + 2 * (ticket_seq.fetch_add(1) % (kTcTickets / 4)));
                 cudaError_t e = cudaGetLastError();
                 if (e != cudaSuccess) return cuda_fail(e, "fd_mma_kernel launch");
                 g_launches.fetch_add(1);
